@@ -1,0 +1,216 @@
+/*
+ * radialog_b200 — C-ABI of the B200-native RaDialog image->report hot path.
+ *
+ * The reference (ChantalMP/RaDialog) is pure Python/PyTorch and has no FFI; its boundary for this path is a set of
+ * Python call surfaces.  This header is the C boundary a maintainer binds from Python
+ * (ctypes stub in INTEGRATION.md); each entry point cites the reference code it replaces (paths relative to the
+ * reference root).  Conventions:
+ *   - every function returns 0 on success, <0 on error; rd_last_error() gives the message (thread-local);
+ *   - all pointers named *_dev are device pointers owned by the caller (e.g. torch tensors' data_ptr());
+ *   - `stream` is a cudaStream_t passed as void*; no function synchronises unless it says so;
+ *   - `dtype`: RD_F16 (reference dtype, test.py:289) or RD_BF16; accumulation is always fp32;
+ *   - handles are not thread-safe, distinct handles are independent.
+ */
+#ifndef RADIALOG_B200_H
+#define RADIALOG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RD_F16 0
+#define RD_BF16 1
+
+#define RD_OK 0
+#define RD_ERR_INVALID -1
+#define RD_ERR_CUDA -2
+#define RD_ERR_UNSUPPORTED -3
+
+const char* rd_last_error(void);
+int rd_version(void);
+/* 1 if device `dev` is sm_100 (B200); the library refuses to run anywhere else. */
+int rd_device_ok(int dev);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Op level
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Epilogue of rd_linear.  Order of operations (each "T(.)" is one rounding to the storage dtype):
+ *   v = acc (+ bias[n])                                           fp32
+ *   residual, res_mode 2 : v += residual[m,n]   (Q-Former / conv residuals, evaluated in fp32 by the reference)
+ *   act == RD_ACT_NONE   : y = T(v)
+ *   act == RD_ACT_RELU   : y = T(max(v,0))            torchvision Bottleneck / biovil_t/modules.py:45
+ *   act == RD_ACT_GELU   : y = T(gelu_erf(v))         Qformer.py:358-361
+ *   act == RD_ACT_SWIGLU : W has 2N rows (gate rows [0,N), up rows [N,2N)):
+ *                          y = T( T(silu(T(acc_gate))) * T(acc_up) )      modeling_llama_imgemb.py:158-159
+ *   lora_r > 0           : y = T( y + T(lora_scale * T(sum_r lora_t[m,r]*lora_B[n,r])) )   peft unmerged LoRA
+ *   residual, res_mode 1 : y = T( residual[m,n] + y )       fp16 residual stream, modeling_llama_imgemb.py:302,308 */
+#define RD_ACT_NONE 0
+#define RD_ACT_RELU 1
+#define RD_ACT_GELU 2
+#define RD_ACT_SWIGLU 3
+
+typedef struct rd_epilogue {
+  const float* bias_dev;     /* [N] fp32 or NULL */
+  const void* residual_dev;  /* [M, ld_res] storage dtype or NULL */
+  int64_t ld_res;
+  int res_mode;              /* 1 or 2, see above */
+  int act;
+  const void* lora_t_dev;    /* [M, lora_r] storage dtype: A.x already computed (rd_rmsnorm) */
+  const void* lora_b_dev;    /* [N, lora_r] storage dtype */
+  int lora_r;
+  float lora_scale;
+} rd_epilogue;
+
+/* out[M,N] = epilogue(x[M,K] . W[N,K]^T); row-major, leading dimensions in elements (multiples of 8).
+ * Replaces every nn.Linear / 1x1 conv on the path (q/k/v/o/gate/up/down/lm_head: modeling_llama_imgemb.py:153-159,
+ * 178-181,680; Q-Former denses: Qformer.py:128-130,282,352,367; img_proj_layer: test.py:295).
+ * `algo`: 0 auto (M<=4 -> streaming GEMV; otherwise tcgen05 tensor-core tiles), 1 force GEMV (M<=4), 2 force
+ * tcgen05, 3 SIMT validation kernel.  `ws_dev` is split-K workspace (may be NULL when algo picks no split;
+ * size from rd_linear_workspace_bytes).                                                                        */
+int rd_linear(const void* x_dev, int64_t ldx, const void* w_dev, int64_t ldw, void* out_dev, int64_t ldo,
+              int M, int N, int K, const rd_epilogue* epi, int dtype, int algo, void* ws_dev, int64_t ws_bytes,
+              void* stream);
+/* Split-K workspace: must be zero-initialised once by its owner (the kernels re-arm their counters themselves). */
+int64_t rd_linear_workspace_bytes(int M, int N, int K);
+/* Test hook: force the split-K factor of the tcgen05 path (0 = heuristic). */
+int rd_linear_force_splits(int splits);
+/* Launch every kernel with the programmatic-dependent-launch attribute (prologue of kernel N+1 — barrier init, TMEM
+ * allocation, the first weight tiles — overlaps the tail of kernel N).  Off by default. */
+int rd_set_pdl(int on);
+
+/* LlamaRMSNorm.forward (modeling_llama_imgemb.py:85-93): fp32 mean of squares, x*rsqrt in fp32, round, then
+ * multiply by the weight in the storage dtype.  If lora_a_dev != NULL also writes lora_t[M, lora_rows] =
+ * T(out[m,:] . lora_a[r,:]) (the lora_A Linear of peft, fed to rd_linear's epilogue).                           */
+int rd_rmsnorm(const void* x_dev, const void* w_dev, void* out_dev, int M, int H, float eps,
+               const void* lora_a_dev, int lora_rows, void* lora_t_dev, int dtype, void* stream);
+
+/* nn.LayerNorm over the last dim (fp32 statistics): ln_vision blip2.py:199-205 (eps 1e-5), BERT post-LN
+ * Qformer.py:285-289,371-375 (eps 1e-12).  gamma/beta fp32.                                                     */
+int rd_layernorm(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* out_dev, int M, int H,
+                 float eps, int dtype, void* stream);
+
+/* apply_rotary_pos_emb (modeling_llama_imgemb.py:135-142) on q,k of qkv[M,3H] + KV-cache append (replaces the
+ * torch.cat at :209-212).  Token m = b*q_len+i goes to cache slot ctx_len[0]+i.  q is rotated in place.
+ * cos/sin: [max_pos, hd] storage dtype (tables of :97-109 cast as in :123-124).  Caches: [B, nh, cmax, hd].    */
+int rd_rope_kv_store(void* qkv_dev, const int32_t* pos_dev, const int32_t* ctx_len_dev, const void* cos_dev,
+                     const void* sin_dev, void* kcache_dev, void* vcache_dev, int B, int q_len, int nh, int hd,
+                     int cmax, int dtype, void* stream);
+
+/* LlamaAttention core (modeling_llama_imgemb.py:216-234) for q_len new tokens per row against the cache:
+ * fp16 scores, /sqrt(hd), + causal/padding mask, clamp to finfo.min, fp32 softmax rounded to the storage dtype,
+ * .V.  keymask[B,cmax] is the HF attention_mask (1 = attend).  out[M, nh*hd].                                   */
+int rd_attention(const void* qkv_dev, int64_t ldq, const void* kcache_dev, const void* vcache_dev,
+                 const uint8_t* keymask_dev, const int32_t* ctx_len_dev, void* out_dev, int B, int q_len, int nh,
+                 int hd, int cmax, int dtype, void* stream);
+
+/* LlamaModel.forward splice (modeling_llama_imgemb.py:571-594, split_at_img :498-520): out[b,t,:] = img[b,t-p,:]
+ * for t in [p,p+32) where p = first index of 32000 in row b (0 if none), else embed[ids[b,t]].  img may be NULL
+ * (plain embedding).                                                                                            */
+int rd_embed_splice(const int64_t* ids_dev, const void* embed_dev, const void* img_dev, void* out_dev, int B, int T,
+                    int H, int vocab, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LLM engine: LlamaForCausalLM.forward + transformers 4.28.1 greedy_search
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct rd_llm rd_llm;
+
+typedef struct rd_llm_config {
+  int vocab, hidden, inter, layers, heads, max_pos;
+  float rms_eps;
+  int dtype;
+  int lora_r;          /* 0 = no adapter */
+  float lora_scale;    /* alpha / r (finetune.py:167-168 -> 2.0) */
+  int qformer_hidden;  /* 768 */
+  int max_batch, max_ctx;
+  int pad_id, eos_id, img_id;
+} rd_llm_config;
+
+/* weight slots for rd_llm_set_weight; layer = -1 for the global ones */
+#define RD_W_EMBED 0       /* [vocab, H]                      model.embed_tokens.weight            */
+#define RD_W_FINAL_NORM 1  /* [H]                             model.norm.weight                    */
+#define RD_W_LM_HEAD 2     /* [vocab, H]                      lm_head.weight                       */
+#define RD_W_IMG_PROJ_W 3  /* [H, 768]                        model.img_proj_layer.weight          */
+#define RD_W_IMG_PROJ_B 4  /* [H] fp32                        model.img_proj_layer.bias            */
+#define RD_W_ROPE_COS 5    /* [max_pos, hd]                                                        */
+#define RD_W_ROPE_SIN 6
+#define RD_W_QKV 10        /* [3H, H]  q_proj|k_proj|v_proj rows                                   */
+#define RD_W_O 11          /* [H, H]                                                               */
+#define RD_W_GATE_UP 12    /* [2I, H]  gate_proj rows then up_proj rows                            */
+#define RD_W_DOWN 13       /* [H, I]                                                               */
+#define RD_W_LN1 14        /* [H] input_layernorm                                                  */
+#define RD_W_LN2 15        /* [H] post_attention_layernorm                                         */
+#define RD_W_LORA_A 16     /* [2r, H]  q lora_A rows then v lora_A rows                            */
+#define RD_W_LORA_B 17     /* [3H, 2r] block matrix: q rows use cols [0,r), v rows cols [r,2r)     */
+
+int rd_llm_create(const rd_llm_config* cfg, rd_llm** out);
+void rd_llm_destroy(rd_llm* h);
+int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* ptr_dev);
+/* GEMM path: 0 auto, 1 GEMV, 2 tcgen05, 3 SIMT (validation) */
+int rd_llm_set_algo(rd_llm* h, int algo);
+
+/* Start generation: clears the KV cache, infers attention_mask = (ids != pad) and position_ids = cumsum-1
+ * (prepare_inputs_for_generation, modeling_llama_imgemb.py:795-836), runs the prefill forward over ids[B,T] with
+ * the image rows spliced in (img_embeds_dev: [B,32,768] storage dtype, or NULL = no image), and selects the first
+ * token (greedy).  If all_logits_dev != NULL the full [B,T,vocab] logits are written there (parity dumps; the
+ * reference computes them at :768) — otherwise only the last position goes through lm_head.
+ * suppress_eos != 0 masks EOS in the argmax (fixed-work throughput runs).                                       */
+int rd_llm_prefill(rd_llm* h, const int64_t* ids_dev, const void* img_embeds_dev, int B, int T,
+                   void* all_logits_dev, int suppress_eos, void* stream);
+/* Multi-turn: append ids[B,T] to the existing context (KV prefix reuse; identical tokens to a full re-prefill of
+ * the concatenated conversation, demo.py:282-297) and select the next token.                                    */
+int rd_llm_extend(rd_llm* h, const int64_t* ids_dev, int B, int T, int suppress_eos, void* stream);
+/* Roll the context back to its first new_ctx cached tokens before rd_llm_extend (npos_host[b] = attended tokens among
+ * them, HOST pointer).  Synchronises the stream. */
+int rd_llm_truncate(rd_llm* h, int new_ctx, const int32_t* npos_host, void* stream);
+/* A CUDA-graph replay of a captured rd_llm_decode_step advances the device-side counters only; this keeps the host
+ * mirror used for bounds checks in step (n may be -1 to undo the bump of the capture call itself). */
+int rd_llm_note_replayed_steps(rd_llm* h, int n);
+/* One greedy decode step for all rows (graph-capturable: no host-dependent state). */
+int rd_llm_decode_step(rd_llm* h, void* stream);
+/* Device-side generation state: tokens chosen so far [B, n_generated] (row-major, ld = max_ctx), per-row
+ * finished flags (1 = row has emitted EOS), last-step logits [B, vocab].                                                                */
+int rd_llm_state(rd_llm* h, const int64_t** gen_tokens_dev, const int32_t** finished_dev,
+                 const void** last_logits_dev, const void** hidden_dev, int* n_generated_host);
+/* Per-kernel-class CUDA-event timing of the eager path (bench.py roofline): enable, run steps, read back.
+ * classes: 0 rmsnorm 1 qkv 2 rope 3 attn 4 o 5 gate_up 6 down 7 lm_head 8 argmax 9 embed                         */
+int rd_llm_profile(rd_llm* h, int enable);
+int rd_llm_profile_read(rd_llm* h, float* ms_per_class, int* launches_per_class, int n_classes);
+int64_t rd_llm_launch_count(rd_llm* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Vision engine: Blip2Qformer.forward_image (blip2_qformer.py:467-484) = BioViL-T ResNet-50 trunk
+ * (biovil_t/resnet.py:25-47) + backbone_to_vit + projector (biovil_t/encoder.py:124-130, modules.py:43-47) +
+ * ln_vision + Q-Former query branch (Qformer.py:804-965)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct rd_vision rd_vision;
+
+typedef struct rd_vision_config {
+  int image_size;
+  int layers[4];
+  int width;
+  int backbone_to_vit, joint;
+  int num_query, q_hidden, q_heads, q_layers, q_inter, cross_freq;
+  float ln_vision_eps, q_ln_eps;
+  int dtype;
+  int max_batch;
+} rd_vision_config;
+
+int rd_vision_create(const rd_vision_config* cfg, rd_vision** out);
+void rd_vision_destroy(rd_vision* h);
+/* Weights by name (the reference state_dict key with BatchNorm already folded by the host packer, see
+ * radialog_b200/vision.py): conv weights are [Cout, kh*kw*Cin] storage dtype (NHWC im2col order), biases and
+ * LayerNorm parameters fp32.                                                                                    */
+int rd_vision_set_weight(rd_vision* h, const char* name, const void* ptr_dev);
+/* images: [B,3,S,S] fp32 NCHW in [0,1] (ReportDataset.py:96-106).  q_out: [B,32,768] fp32, image_embeds
+ * [B,196,1408] fp32 (may be NULL).                                                                              */
+int rd_vision_forward(rd_vision* h, const float* images_dev, int B, float* q_out_dev, float* image_embeds_dev,
+                      void* stream);
+int64_t rd_vision_launch_count(rd_vision* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

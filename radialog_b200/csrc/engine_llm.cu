@@ -1,0 +1,363 @@
+// LLM engine: LlamaForCausalLM.forward (modeling_llama_imgemb.py:523-672, 705-793) + the greedy loop of
+// transformers 4.28.1 as a native runtime: flat pre-allocated KV cache (replaces the
+// per-step torch.cat at :209-212), device-resident generation state, one host call per decode step that is
+// CUDA-graph capturable.
+#include <vector>
+#include "common.cuh"
+
+extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const int32_t*, int, int, int, int, void*);
+extern "C" int rd_argmax_step(const void*, int64_t, int, int64_t*, int64_t*, int64_t, int32_t*, uint8_t*, int, int32_t*,
+                              int32_t*, int32_t*, int32_t*, uint32_t*, int, int, int, int, int, int, void*);
+
+enum { C_RMSNORM = 0, C_QKV, C_ROPE, C_ATTN, C_O, C_GATEUP, C_DOWN, C_LMHEAD, C_ARGMAX, C_EMBED, C_NCLASS };
+
+struct LayerW {
+  const void *qkv = nullptr, *o = nullptr, *gate_up = nullptr, *down = nullptr, *ln1 = nullptr, *ln2 = nullptr,
+             *lora_a = nullptr, *lora_b = nullptr;
+};
+
+struct rd_llm {
+  rd_llm_config c;
+  std::vector<LayerW> L;
+  const void *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr, *img_w = nullptr, *cos = nullptr, *sin = nullptr;
+  const float* img_b = nullptr;
+  int algo = 0;
+  int esz = 2;
+  int64_t max_tokens = 0;
+  int vpad = 0;
+  // device buffers
+  char *x = nullptr, *xn = nullptr, *qkv = nullptr, *att = nullptr, *mid = nullptr, *xl = nullptr, *logits = nullptr,
+       *img = nullptr, *lora_t = nullptr, *ws = nullptr;
+  int64_t ws_bytes = 0;
+  char *kc = nullptr, *vc = nullptr;     // [layers][B, nh, cmax, hd]
+  int64_t kv_layer_bytes = 0;
+  uint8_t* keymask = nullptr;
+  int32_t *pos = nullptr, *pos_cur = nullptr, *npos = nullptr, *finished = nullptr, *ctx_len = nullptr, *n_gen = nullptr;
+  uint32_t* done_ctr = nullptr;
+  int64_t *cur_tok = nullptr, *gen = nullptr;
+  int B = 0;               // rows of the generation in flight
+  int n_generated = 0;     // host mirror of n_gen
+  int ctx_host = 0;
+  int suppress_eos = 0;
+  // profiling
+  bool prof = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_used;   // (class, index of start event; stop = +1)
+  size_t ev_next = 0;
+  int64_t launches = 0;
+};
+
+static int dalloc(char** p, int64_t bytes) {
+  RD_CHECK_CUDA(cudaMalloc((void**)p, (size_t)(bytes > 0 ? bytes : 16)));
+  RD_CHECK_CUDA(cudaMemset(*p, 0, (size_t)(bytes > 0 ? bytes : 16)));
+  return RD_OK;
+}
+
+extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
+  RD_REQUIRE(cfg && out, "rd_llm_create: null argument");
+  RD_REQUIRE(cfg->hidden % cfg->heads == 0 && cfg->hidden / cfg->heads == 128,
+             "rd_llm_create: head_dim must be 128 (hidden=%d heads=%d)", cfg->hidden, cfg->heads);
+  RD_REQUIRE(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0, "rd_llm_create: hidden/inter must be multiples of 8");
+  RD_REQUIRE(cfg->max_batch > 0 && cfg->max_ctx > 0 && cfg->max_ctx <= cfg->max_pos, "rd_llm_create: bad max_batch/max_ctx");
+  RD_REQUIRE(cfg->dtype == RD_F16 || cfg->dtype == RD_BF16, "rd_llm_create: bad dtype");
+  int dev = 0;
+  RD_CHECK_CUDA(cudaGetDevice(&dev));
+  if (!rd_device_ok(dev)) return RD_ERR_UNSUPPORTED;
+  rd_llm* h = new rd_llm();
+  h->c = *cfg;
+  h->L.resize(cfg->layers);
+  const int64_t H = cfg->hidden, I = cfg->inter, Bm = cfg->max_batch, C = cfg->max_ctx, e = 2;
+  h->max_tokens = Bm * C;
+  h->vpad = (cfg->vocab + 7) / 8 * 8;
+  const int64_t Mt = h->max_tokens;
+  int r = RD_OK;
+  auto A = [&](char** p, int64_t bytes) { if (r == RD_OK) r = dalloc(p, bytes); };
+  A(&h->x, Mt * H * e); A(&h->xn, Mt * H * e); A(&h->qkv, Mt * 3 * H * e); A(&h->att, Mt * H * e); A(&h->mid, Mt * I * e);
+  A(&h->xl, Bm * H * e); A(&h->logits, Bm * h->vpad * e); A(&h->img, Bm * 32 * H * e);
+  A(&h->lora_t, Mt * 2 * (cfg->lora_r > 0 ? cfg->lora_r : 1) * e);
+  h->kv_layer_bytes = Bm * C * H * e;
+  A(&h->kc, h->kv_layer_bytes * cfg->layers); A(&h->vc, h->kv_layer_bytes * cfg->layers);
+  A((char**)&h->keymask, Bm * C);
+  A((char**)&h->pos, Mt * 4); A((char**)&h->pos_cur, Bm * 4); A((char**)&h->npos, Bm * 4); A((char**)&h->finished, Bm * 4);
+  A((char**)&h->ctx_len, 16); A((char**)&h->n_gen, 16); A((char**)&h->done_ctr, 16);
+  A((char**)&h->cur_tok, Bm * 8); A((char**)&h->gen, Bm * C * 8);
+  int64_t ws = 0;
+  const int Ms[2] = {(int)Bm, 256};
+  for (int mi = 0; mi < 2; ++mi) {
+    int M = Ms[mi];
+    int64_t cand[5] = {rd_linear_tc_workspace_bytes(M, 3 * H, H), rd_linear_tc_workspace_bytes(M, H, H),
+                       rd_linear_tc_workspace_bytes(M, I, H), rd_linear_tc_workspace_bytes(M, H, I),
+                       rd_linear_tc_workspace_bytes(M, cfg->vocab, H)};
+    for (int i = 0; i < 5; ++i) ws = cand[i] > ws ? cand[i] : ws;
+  }
+  h->ws_bytes = ws;
+  A(&h->ws, ws);
+  if (r != RD_OK) { rd_llm_destroy(h); return r; }
+  *out = h;
+  return RD_OK;
+}
+
+extern "C" void rd_llm_destroy(rd_llm* h) {
+  if (!h) return;
+  void* ptrs[] = {h->x, h->xn, h->qkv, h->att, h->mid, h->xl, h->logits, h->img, h->lora_t, h->ws, h->kc, h->vc, h->keymask,
+                  h->pos, h->pos_cur, h->npos, h->finished, h->ctx_len, h->n_gen, h->done_ctr, h->cur_tok, h->gen};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  delete h;
+}
+
+extern "C" int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* p) {
+  RD_REQUIRE(h && p, "rd_llm_set_weight: null argument");
+  RD_REQUIRE(((uintptr_t)p & 15) == 0, "rd_llm_set_weight: pointer for slot %d must be 16-byte aligned", slot);
+  if (slot < 10) {
+    switch (slot) {
+      case RD_W_EMBED: h->embed = p; break;
+      case RD_W_FINAL_NORM: h->final_norm = p; break;
+      case RD_W_LM_HEAD: h->lm_head = p; break;
+      case RD_W_IMG_PROJ_W: h->img_w = p; break;
+      case RD_W_IMG_PROJ_B: h->img_b = (const float*)p; break;
+      case RD_W_ROPE_COS: h->cos = p; break;
+      case RD_W_ROPE_SIN: h->sin = p; break;
+      default: rd_set_error("rd_llm_set_weight: unknown slot %d", slot); return RD_ERR_INVALID;
+    }
+    return RD_OK;
+  }
+  RD_REQUIRE(layer >= 0 && layer < h->c.layers, "rd_llm_set_weight: layer %d out of range", layer);
+  LayerW& w = h->L[layer];
+  switch (slot) {
+    case RD_W_QKV: w.qkv = p; break;
+    case RD_W_O: w.o = p; break;
+    case RD_W_GATE_UP: w.gate_up = p; break;
+    case RD_W_DOWN: w.down = p; break;
+    case RD_W_LN1: w.ln1 = p; break;
+    case RD_W_LN2: w.ln2 = p; break;
+    case RD_W_LORA_A: w.lora_a = p; break;
+    case RD_W_LORA_B: w.lora_b = p; break;
+    default: rd_set_error("rd_llm_set_weight: unknown slot %d", slot); return RD_ERR_INVALID;
+  }
+  return RD_OK;
+}
+
+extern "C" int rd_llm_set_algo(rd_llm* h, int algo) {
+  RD_REQUIRE(h && algo >= 0 && algo <= 3, "rd_llm_set_algo: bad argument");
+  h->algo = algo;
+  return RD_OK;
+}
+
+static int check_weights(rd_llm* h) {
+  RD_REQUIRE(h->embed && h->final_norm && h->lm_head && h->cos && h->sin, "rd_llm: global weights not set");
+  for (int l = 0; l < h->c.layers; ++l) {
+    const LayerW& w = h->L[l];
+    RD_REQUIRE(w.qkv && w.o && w.gate_up && w.down && w.ln1 && w.ln2, "rd_llm: weights of layer %d not set", l);
+    RD_REQUIRE(h->c.lora_r == 0 || (w.lora_a && w.lora_b), "rd_llm: LoRA weights of layer %d not set", l);
+  }
+  return RD_OK;
+}
+
+struct ProfScope {
+  rd_llm* h; cudaStream_t st; int cls; int idx = -1;
+  ProfScope(rd_llm* h_, cudaStream_t st_, int cls_) : h(h_), st(st_), cls(cls_) {
+    h->launches++;
+    if (!h->prof) return;
+    if (h->ev_next + 2 > h->ev_pool.size()) {
+      for (int i = 0; i < 512; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+    }
+    idx = (int)h->ev_next; h->ev_next += 2;
+    cudaEventRecord(h->ev_pool[idx], st);
+  }
+  ~ProfScope() {
+    if (idx < 0) return;
+    cudaEventRecord(h->ev_pool[idx + 1], st);
+    h->ev_used.push_back({cls, idx});
+  }
+};
+
+static int linear(rd_llm* h, int cls, const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M,
+                  int N, int K, const rd_epilogue* e, cudaStream_t st) {
+  ProfScope ps(h, st, cls);
+  int algo = h->algo;
+  if (algo == 1 && M > 4) algo = 3;     // forced-GEMV validation mode falls back to SIMT for wide batches
+  return rd_linear(x, ldx, w, ldw, out, ldo, M, N, K, e, h->c.dtype, algo, h->ws, h->ws_bytes, st);
+}
+
+// layers over M = B*q_len tokens whose embeddings are in h->x; positions in `pos`
+static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStream_t st) {
+  const rd_llm_config& c = h->c;
+  const int H = c.hidden, I = c.inter, M = B * q_len, nh = c.heads, hd = H / nh, dt = c.dtype;
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerW& w = h->L[l];
+    char* kc = h->kc + (int64_t)l * h->kv_layer_bytes;
+    char* vc = h->vc + (int64_t)l * h->kv_layer_bytes;
+    { ProfScope ps(h, st, C_RMSNORM);
+      RD_CHECK(rd_rmsnorm(h->x, w.ln1, h->xn, M, H, c.rms_eps, c.lora_r ? w.lora_a : nullptr, 2 * c.lora_r, h->lora_t, dt, st)); }
+    rd_epilogue e{};
+    if (c.lora_r) { e.lora_t_dev = h->lora_t; e.lora_b_dev = w.lora_b; e.lora_r = 2 * c.lora_r; e.lora_scale = c.lora_scale; }
+    RD_CHECK(linear(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, 3 * H, M, 3 * H, H, &e, st));
+    { ProfScope ps(h, st, C_ROPE);
+      RD_CHECK(rd_rope_kv_store(h->qkv, pos, h->ctx_len, h->cos, h->sin, kc, vc, B, q_len, nh, hd, c.max_ctx, dt, st)); }
+    { ProfScope ps(h, st, C_ATTN);
+      RD_CHECK(rd_attention(h->qkv, 3 * H, kc, vc, h->keymask, h->ctx_len, h->att, B, q_len, nh, hd, c.max_ctx, dt, st)); }
+    rd_epilogue eo{};
+    eo.residual_dev = h->x; eo.ld_res = H; eo.res_mode = 1;
+    RD_CHECK(linear(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, st));
+    { ProfScope ps(h, st, C_RMSNORM);
+      RD_CHECK(rd_rmsnorm(h->x, w.ln2, h->xn, M, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
+    rd_epilogue eg{};
+    eg.act = RD_ACT_SWIGLU;
+    RD_CHECK(linear(h, C_GATEUP, h->xn, H, w.gate_up, H, h->mid, I, M, I, H, &eg, st));
+    RD_CHECK(linear(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, st));
+  }
+  return RD_OK;
+}
+
+// final norm + lm_head on the last position of every row + greedy selection
+static int head_and_select(rd_llm* h, int B, int q_len, void* all_logits, cudaStream_t st) {
+  const rd_llm_config& c = h->c;
+  const int H = c.hidden, V = c.vocab, dt = c.dtype;
+  const void* logits; int64_t ld;
+  if (all_logits) {
+    const int M = B * q_len;
+    { ProfScope ps(h, st, C_RMSNORM);
+      RD_CHECK(rd_rmsnorm(h->x, h->final_norm, h->xn, M, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
+    RD_CHECK(linear(h, C_LMHEAD, h->xn, H, h->lm_head, H, all_logits, V, M, V, H, nullptr, st));
+    logits = (const char*)all_logits + (int64_t)(q_len - 1) * V * 2; ld = (int64_t)q_len * V;
+  } else {
+    const void* xin = h->x;
+    if (q_len > 1) {   // only the last position is consumed by greedy search (HF takes logits[:, -1]); skip the rest
+      RD_CHECK_CUDA(cudaMemcpy2DAsync(h->xl, (size_t)H * 2, h->x + (int64_t)(q_len - 1) * H * 2, (size_t)q_len * H * 2,
+                                      (size_t)H * 2, B, cudaMemcpyDeviceToDevice, st));
+      xin = h->xl;
+    }
+    { ProfScope ps(h, st, C_RMSNORM);
+      RD_CHECK(rd_rmsnorm(xin, h->final_norm, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
+    RD_CHECK(linear(h, C_LMHEAD, h->xn, H, h->lm_head, H, h->logits, h->vpad, B, V, H, nullptr, st));
+    logits = h->logits; ld = h->vpad;
+  }
+  { ProfScope ps(h, st, C_ARGMAX);
+    RD_CHECK(rd_argmax_step(logits, ld, V, h->cur_tok, h->gen, c.max_ctx, h->finished, h->keymask, c.max_ctx, h->pos_cur,
+                            h->npos, h->ctx_len, h->n_gen, h->done_ctr, B, q_len, c.pad_id, c.eos_id, h->suppress_eos, dt, st)); }
+  return RD_OK;
+}
+
+static int extend_impl(rd_llm* h, const int64_t* ids, const void* img_embeds, int B, int T, void* all_logits, cudaStream_t st) {
+  const rd_llm_config& c = h->c;
+  RD_REQUIRE(h->ctx_host + T + 1 <= c.max_ctx, "rd_llm: context %d + %d new tokens exceeds max_ctx %d", h->ctx_host, T, c.max_ctx);
+  const int H = c.hidden, dt = c.dtype;
+  RD_CHECK(rd_llm_prep(ids, h->keymask, h->pos, h->npos, h->ctx_len, B, T, c.max_ctx, c.pad_id, st));
+  h->launches++;
+  const void* img_rows = nullptr;
+  if (img_embeds) {
+    RD_REQUIRE(h->img_w && h->img_b, "rd_llm: img_proj_layer weights not set");
+    rd_epilogue e{};
+    e.bias_dev = h->img_b;
+    // img_proj_layer: Linear(768 -> H) with bias on the fp16-cast Q-Former output (modeling_llama_imgemb.py:577/579)
+    RD_CHECK(linear(h, C_EMBED, img_embeds, c.qformer_hidden, h->img_w, c.qformer_hidden, h->img, H, B * 32, H, c.qformer_hidden, &e, st));
+    img_rows = h->img;
+  }
+  { ProfScope ps(h, st, C_EMBED);
+    RD_CHECK(rd_embed_splice(ids, h->embed, img_rows, h->x, B, T, H, c.vocab, dt, st)); }
+  RD_CHECK(run_layers(h, B, T, h->pos, st));
+  RD_CHECK(head_and_select(h, B, T, all_logits, st));
+  h->ctx_host += T;
+  h->n_generated += 1;
+  return RD_OK;
+}
+
+extern "C" int rd_llm_prefill(rd_llm* h, const int64_t* ids, const void* img_embeds, int B, int T, void* all_logits,
+                              int suppress_eos, void* stream) {
+  RD_REQUIRE(h && ids, "rd_llm_prefill: null argument");
+  RD_REQUIRE(B > 0 && B <= h->c.max_batch && T > 0, "rd_llm_prefill: B=%d T=%d out of range (max_batch %d)", B, T, h->c.max_batch);
+  RD_REQUIRE(img_embeds == nullptr || T >= 32, "rd_llm_prefill: image splice needs T>=32 (got %d)", T);
+  RD_CHECK(check_weights(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  const rd_llm_config& c = h->c;
+  h->B = B; h->n_generated = 0; h->ctx_host = 0; h->suppress_eos = suppress_eos;
+  RD_CHECK_CUDA(cudaMemsetAsync(h->ctx_len, 0, 16, st));
+  RD_CHECK_CUDA(cudaMemsetAsync(h->n_gen, 0, 16, st));
+  RD_CHECK_CUDA(cudaMemsetAsync(h->done_ctr, 0, 16, st));
+  RD_CHECK_CUDA(cudaMemsetAsync(h->npos, 0, (size_t)c.max_batch * 4, st));
+  RD_CHECK_CUDA(cudaMemsetAsync(h->keymask, 0, (size_t)c.max_batch * c.max_ctx, st));
+  RD_CHECK_CUDA(cudaMemsetAsync(h->finished, 0, (size_t)c.max_batch * 4, st));
+  return extend_impl(h, ids, img_embeds, B, T, all_logits, st);
+}
+
+// Multi-turn prefix reuse.  rd_llm_truncate rolls the context back to its first `new_ctx` cached tokens (the
+// longest prefix the new conversation shares with what is cached; npos_host[b] = number of attended tokens among
+// them), rd_llm_extend then runs only the remaining ids through the layers.  Token-identical to the reference's
+// full re-prefill of the whole conversation (demo.py:282-297) because cache slots, masks and positions are the same.
+extern "C" int rd_llm_truncate(rd_llm* h, int new_ctx, const int32_t* npos_host, void* stream) {
+  RD_REQUIRE(h && npos_host && h->B > 0, "rd_llm_truncate: no generation in flight");
+  RD_REQUIRE(new_ctx >= 0 && new_ctx <= h->ctx_host, "rd_llm_truncate: new_ctx %d outside [0,%d]", new_ctx, h->ctx_host);
+  cudaStream_t st = (cudaStream_t)stream;
+  RD_CHECK_CUDA(cudaStreamSynchronize(st));
+  int32_t v[4] = {new_ctx, 0, 0, 0};
+  RD_CHECK_CUDA(cudaMemcpy(h->ctx_len, v, 4, cudaMemcpyHostToDevice));
+  RD_CHECK_CUDA(cudaMemset(h->n_gen, 0, 16));
+  RD_CHECK_CUDA(cudaMemcpy(h->npos, npos_host, (size_t)h->B * 4, cudaMemcpyHostToDevice));
+  RD_CHECK_CUDA(cudaMemset(h->finished, 0, (size_t)h->c.max_batch * 4));
+  h->ctx_host = new_ctx; h->n_generated = 0;
+  return RD_OK;
+}
+
+extern "C" int rd_llm_extend(rd_llm* h, const int64_t* ids, int B, int T, int suppress_eos, void* stream) {
+  RD_REQUIRE(h && ids, "rd_llm_extend: null argument");
+  RD_REQUIRE(B == h->B && T > 0, "rd_llm_extend: B=%d must equal the batch of the generation in flight (%d)", B, h->B);
+  h->suppress_eos = suppress_eos;
+  return extend_impl(h, ids, nullptr, B, T, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int rd_llm_decode_step(rd_llm* h, void* stream) {
+  RD_REQUIRE(h && h->B > 0, "rd_llm_decode_step: no generation in flight (call rd_llm_prefill first)");
+  RD_REQUIRE(h->ctx_host + 2 <= h->c.max_ctx, "rd_llm_decode_step: context %d reached max_ctx %d", h->ctx_host, h->c.max_ctx);
+  cudaStream_t st = (cudaStream_t)stream;
+  const rd_llm_config& c = h->c;
+  { ProfScope ps(h, st, C_EMBED);
+    RD_CHECK(rd_embed_splice(h->cur_tok, h->embed, nullptr, h->x, h->B, 1, c.hidden, c.vocab, c.dtype, st)); }
+  RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
+  RD_CHECK(head_and_select(h, h->B, 1, nullptr, st));
+  h->ctx_host += 1;
+  h->n_generated += 1;
+  return RD_OK;
+}
+
+// CUDA-graph replays advance the device-side counters without going through rd_llm_decode_step; the host mirror
+// is bumped here so bounds checks stay meaningful.
+extern "C" int rd_llm_note_replayed_steps(rd_llm* h, int n) {
+  RD_REQUIRE(h, "rd_llm_note_replayed_steps: null handle");
+  RD_REQUIRE(h->ctx_host + n + 1 <= h->c.max_ctx && h->ctx_host + n >= 0, "rd_llm_note_replayed_steps: context out of range");
+  h->ctx_host += n; h->n_generated += n;
+  return RD_OK;
+}
+
+extern "C" int rd_llm_state(rd_llm* h, const int64_t** gen, const int32_t** finished, const void** last_logits,
+                            const void** hidden, int* n_generated) {
+  RD_REQUIRE(h, "rd_llm_state: null handle");
+  if (gen) *gen = h->gen;
+  if (finished) *finished = h->finished;
+  if (last_logits) *last_logits = h->logits;
+  if (hidden) *hidden = h->x;
+  if (n_generated) *n_generated = h->n_generated;
+  return RD_OK;
+}
+
+extern "C" int rd_llm_profile(rd_llm* h, int enable) {
+  RD_REQUIRE(h, "rd_llm_profile: null handle");
+  h->prof = enable != 0;
+  h->ev_used.clear();
+  h->ev_next = 0;
+  return RD_OK;
+}
+
+extern "C" int rd_llm_profile_read(rd_llm* h, float* ms, int* launches, int n) {
+  RD_REQUIRE(h && ms && launches && n >= C_NCLASS, "rd_llm_profile_read: need room for %d classes", (int)C_NCLASS);
+  RD_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < n; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  for (auto& u : h->ev_used) {
+    float t = 0.f;
+    RD_CHECK_CUDA(cudaEventElapsedTime(&t, h->ev_pool[u.second], h->ev_pool[u.second + 1]));
+    ms[u.first] += t; launches[u.first] += 1;
+  }
+  return RD_OK;
+}
+
+extern "C" int64_t rd_llm_launch_count(rd_llm* h) { return h ? h->launches : 0; }

@@ -1,0 +1,404 @@
+// tcgen05 tensor-core path of rd_linear (sm_100a).
+//
+//   out[M,N] = epilogue( x[M,K] . W[N,K]^T )        both operands K-major (row-major), fp16/bf16, fp32 accumulate
+//
+// "Swap-AB" tiling: the WEIGHT tile is the UMMA A operand (128 rows of W fill the 128 TMEM lanes) and the
+// ACTIVATION tile is the UMMA B operand (NT token rows -> NT accumulator columns, NT in {16..256}).  That keeps
+// the tensor core fed at any token count: a 32-row decode batch streams every weight byte exactly once through
+// TMA -> swizzled smem -> tcgen05.mma with no padding of the token dimension to 128, which is what makes the
+// decode step HBM-bound rather than tile-quantisation-bound; the same kernel at NT=256 is the prefill / Q-Former /
+// conv GEMM.
+//
+// One CTA = one 128-row weight tile x one NT-token tile x one K split.
+//   warp 0   : TMA producer  (cp.async.bulk.tensor 2D, 128B swizzle, mbarrier complete_tx, L2 cache hints)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
+//   warps 2-5: epilogue: tcgen05.ld accumulators -> registers -> fused epilogue (bias/act/SwiGLU/LoRA/residual)
+// Split-K (decode: few weight tiles, many SMs) writes fp32 partials to a workspace; the last CTA of a tile reduces
+// them in fixed split order, so results are deterministic run to run.
+// PDL: weight tiles never depend on the previous kernel, so the producer issues the first pipeline stages of W
+// before griddepcontrol.wait and only then loads the activations.
+#include <cuda.h>
+#include "common.cuh"
+
+bool rd_pdl_enabled();
+
+namespace {
+
+constexpr int BLOCK_N = 128;   // weight rows per tile  (UMMA M)
+constexpr int BLOCK_K = 64;    // 64 x 2 B = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+constexpr uint64_t HINT_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
+constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major operand, 128-byte swizzle, rows of 128 B,
+// 8-row groups 1024 B apart.  [0,14) addr>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4,
+// [46,48) version=1 (sm_100), [61,64) layout=2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=f32, A/B = fmt (0 f16, 1 bf16), both K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int umma_m, int umma_n) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+
+constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+template <int NT, bool SWIGLU> struct TcCfg {
+  static constexpr int ACCS = SWIGLU ? 2 : 1;
+  static constexpr int A_BYTES = BLOCK_N * BLOCK_K * 2;          // 16 KB per weight tile
+  static constexpr int B_BYTES = NT * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = ACCS * A_BYTES + B_BYTES;
+  // small-token (decode) tiles: keep two CTAs resident per SM so one CTA's prologue/epilogue hides behind the
+  // other's weight stream; wide tiles take the whole SM.
+  static constexpr int SMEM_BUDGET = (NT <= 64) ? 108 * 1024 : 200 * 1024;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = tmem_cols_for(ACCS * NT);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+};
+
+struct TcParams {
+  int M, N, K;
+  int64_t ldo;
+  int splits;
+  float* ws_part;        // [splits][tiles][ACCS][NT][128] fp32
+  uint32_t* ws_ctr;      // [tiles]
+  uint64_t hint_w, hint_x;
+  EpiParams epi;
+};
+
+template <class T, int NT, bool SWIGLU>
+__global__ void __launch_bounds__(TC_THREADS)
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, T* __restrict__ out,
+                 const TcParams p) {
+  using Cfg = TcCfg<NT, SWIGLU>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint32_t* flag_smem = tmem_ptr_smem + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  const int n0 = n_tile * BLOCK_N, m0 = m_tile * NT;
+  const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_begin = (int)(((int64_t)kb_total * split) / p.splits);
+  const int kb_end = (int)(((int64_t)kb_total * (split + 1)) / p.splits);
+  const int nkb = kb_end - kb_begin;
+
+  pdl_launch_dependents();
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      auto stage_ptr = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+      auto load_w = [&](int s, int kb) {
+        uint8_t* sp = stage_ptr(s);
+        tma_load_2d(sp, &map_w, &full_bar[s], kb * BLOCK_K, n0, p.hint_w);
+        if (SWIGLU) tma_load_2d(sp + Cfg::A_BYTES, &map_w, &full_bar[s], kb * BLOCK_K, p.N + n0, p.hint_w);
+      };
+      auto load_x = [&](int s, int kb) {
+        tma_load_2d(stage_ptr(s) + Cfg::ACCS * Cfg::A_BYTES, &map_x, &full_bar[s], kb * BLOCK_K, m0, p.hint_x);
+      };
+      const int pre = nkb < STAGES ? nkb : STAGES;
+      for (int i = 0; i < pre; ++i) {            // weights first: independent of the previous kernel
+        mbar_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+        load_w(i, kb_begin + i);
+      }
+      pdl_wait();                                // activations were written by the previous kernel
+      for (int i = 0; i < pre; ++i) load_x(i, kb_begin + i);
+      for (int i = pre; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        load_w(s, kb_begin + i);
+        load_x(s, kb_begin + i);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(Tr<T>::umma_fmt, BLOCK_N, NT);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + Cfg::ACCS * Cfg::A_BYTES;
+        const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(b_addr);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);     // advance inside the 128-byte swizzle row
+          tc_mma_f16(tmem_base, da + koff, db + koff, idesc, acc);
+          if (SWIGLU) tc_mma_f16(tmem_base + NT, make_smem_desc(a_addr + Cfg::A_BYTES) + koff, db + koff, idesc, acc);
+        }
+        tc_commit(&empty_bar[s]);                 // frees the smem stage once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);                   // accumulators complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    pdl_wait();
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int n_local = quad * 32 + lane;
+    const int n = n0 + n_local;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int m_valid = min(NT, p.M - m0);
+    const int tiles = gridDim.x * gridDim.y;
+    const int tile_id = m_tile * gridDim.x + n_tile;
+    if (p.splits == 1) {
+      for (int c = 0; c < m_valid; c += 16) {
+        uint32_t r[16], ru[16];
+        tc_ld16(taddr + c, r);
+        if (SWIGLU) tc_ld16(taddr + NT + c, ru);
+        tc_wait_ld();
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = m0 + c + j;
+            if (m < p.M)
+              out[(int64_t)m * p.ldo + n] = epilogue_elem<T>(p.epi, __uint_as_float(r[j]), SWIGLU ? __uint_as_float(ru[j]) : 0.f, m, n);
+          }
+        }
+      }
+    } else {
+      // split-K: publish the fp32 partial tile, the last CTA of the tile reduces all splits in order
+      float* part = p.ws_part + ((int64_t)split * tiles + tile_id) * (Cfg::ACCS * NT * BLOCK_N);
+      for (int c = 0; c < m_valid; c += 16) {
+#pragma unroll
+        for (int a = 0; a < Cfg::ACCS; ++a) {
+          uint32_t r[16];
+          tc_ld16(taddr + a * NT + c, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c + j < m_valid) __stcg(part + ((int64_t)a * NT + c + j) * BLOCK_N + n_local, __uint_as_float(r[j]));
+        }
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const uint32_t prev = atomicAdd(p.ws_ctr + tile_id, 1u);
+        *flag_smem = (prev == (uint32_t)p.splits - 1) ? 1u : 0u;
+        if (prev == (uint32_t)p.splits - 1) p.ws_ctr[tile_id] = 0;     // re-arm for the next launch
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*flag_smem) {
+        __threadfence();
+        if (n < p.N) {
+          for (int j = 0; j < m_valid; ++j) {
+            float acc = 0.f, accu = 0.f;
+            for (int s = 0; s < p.splits; ++s) {
+              const float* ps = p.ws_part + ((int64_t)s * tiles + tile_id) * (Cfg::ACCS * NT * BLOCK_N);
+              acc += __ldcg(ps + (int64_t)j * BLOCK_N + n_local);
+              if (SWIGLU) accu += __ldcg(ps + ((int64_t)NT + j) * BLOCK_N + n_local);
+            }
+            const int m = m0 + j;
+            out[(int64_t)m * p.ldo + n] = epilogue_elem<T>(p.epi, acc, accu, m, n);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int box_rows, int dtype) {
+  PFN_encodeTiled enc = get_encode();
+  RD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == RD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                   gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) ptr=%p ld=%lld rows=%d K=%d box=%d", (int)r, ptr, (long long)ld, rows, K, box_rows);
+  return RD_OK;
+}
+
+int pick_nt(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256; }
+
+int pick_splits(int M, int N, int K) {
+  const int nt = pick_nt(M);
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N, m_tiles = (M + nt - 1) / nt;
+  const int kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (nt > 64 || n_tiles * m_tiles >= 256) return 1;
+  int s = (296 + n_tiles * m_tiles / 2) / (n_tiles * m_tiles);
+  const int smax = kb / 4 > 0 ? kb / 4 : 1;      // at least 4 k-blocks (32 KB of weights) per CTA
+  s = s < 1 ? 1 : s;
+  s = s > smax ? smax : s;
+  s = s > 16 ? 16 : s;
+  return s;
+}
+
+template <class T, int NT, bool SWIGLU>
+int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
+              const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, int splits, cudaStream_t st) {
+  using Cfg = TcCfg<NT, SWIGLU>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RD_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<T, NT, SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap map_w, map_x;
+  RD_CHECK(make_map(&map_w, w, ldw, SWIGLU ? 2 * N : N, K, BLOCK_N, dtype));
+  RD_CHECK(make_map(&map_x, x, ldx, M, K, NT, dtype));
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N, m_tiles = (M + NT - 1) / NT;
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K; p.ldo = ldo; p.splits = splits; p.epi = epi;
+  // decode: every weight byte is read once (evict-first), the small activation tile is shared by all CTAs (evict-last)
+  p.hint_w = m_tiles == 1 ? HINT_EVICT_FIRST : HINT_EVICT_NORMAL;
+  p.hint_x = m_tiles == 1 ? HINT_EVICT_LAST : HINT_EVICT_NORMAL;
+  if (splits > 1) {
+    const int64_t part_bytes = (int64_t)splits * n_tiles * m_tiles * Cfg::ACCS * NT * BLOCK_N * 4;
+    const int64_t need = part_bytes + (int64_t)n_tiles * m_tiles * 4;
+    RD_REQUIRE(ws != nullptr && ws_bytes >= need, "rd_linear: split-K workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+    p.ws_ctr = reinterpret_cast<uint32_t*>(ws);                                   // counters first (zero-initialised by the owner)
+    p.ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((int64_t)n_tiles * m_tiles * 4 + 255) / 256 * 256);
+  }
+  RD_CHECK_CUDA(rd_launch(linear_tc_kernel<T, NT, SWIGLU>, dim3(n_tiles, m_tiles, splits), dim3(TC_THREADS), Cfg::SMEM_BYTES, st,
+                          rd_pdl_enabled(), map_w, map_x, (T*)out, p));
+  return RD_OK;
+}
+
+template <class T, bool SWIGLU>
+int dispatch_nt(int nt, const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
+                const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, int splits, cudaStream_t st) {
+  switch (nt) {
+    case 16: return launch_tc<T, 16, SWIGLU>(x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, ws, ws_bytes, splits, st);
+    case 32: return launch_tc<T, 32, SWIGLU>(x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, ws, ws_bytes, splits, st);
+    case 64: return launch_tc<T, 64, SWIGLU>(x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, ws, ws_bytes, splits, st);
+    case 128: return launch_tc<T, 128, SWIGLU>(x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, ws, ws_bytes, splits, st);
+    default: return launch_tc<T, 256, SWIGLU>(x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, ws, ws_bytes, splits, st);
+  }
+}
+
+}  // namespace
+
+static int g_force_splits = 0;   // test hook: 0 = heuristic
+extern "C" int rd_linear_force_splits(int s) { g_force_splits = s; return RD_OK; }
+
+int64_t rd_linear_tc_workspace_bytes(int M, int N, int K) {
+  const int nt = pick_nt(M);
+  const int64_t n_tiles = (N + BLOCK_N - 1) / BLOCK_N, m_tiles = (M + nt - 1) / nt;
+  const int64_t splits = 16;      // upper bound of pick_splits / the test hook
+  return (n_tiles * m_tiles * 4 + 255) / 256 * 256 + splits * n_tiles * m_tiles * 2 * nt * BLOCK_N * 4 + 256;
+}
+
+int rd_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
+                 const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const int nt = pick_nt(M);
+  int splits = g_force_splits > 0 ? g_force_splits : pick_splits(M, N, K);
+  const int kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (splits > kb) splits = kb;
+  if (splits > 16) splits = 16;
+  if (splits > 1 && ws == nullptr) splits = 1;
+  const bool sw = epi.act == RD_ACT_SWIGLU;
+  RD_DISPATCH_DTYPE(dtype, T, {
+    if (sw) return dispatch_nt<T, true>(nt, x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, ws, ws_bytes, splits, st);
+    return dispatch_nt<T, false>(nt, x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, ws, ws_bytes, splits, st);
+  });
+}

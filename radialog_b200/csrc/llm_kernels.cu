@@ -1,0 +1,398 @@
+// Non-GEMM kernels of the Llama decoder path.  Every rounding point follows the reference
+// (model/lavis/models/blip2_models/modeling_llama_imgemb.py).
+#include "common.cuh"
+
+bool rd_pdl_enabled();
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm (+ LoRA-A side product)                                      modeling_llama_imgemb.py:85-93
+// one CTA per token row; the normalised row stays in shared memory for the lora_A dot products
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ out, int H, float eps,
+               const T* __restrict__ lora_a, int lora_rows, T* __restrict__ lora_t) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float srow[];      // H floats
+  __shared__ float sred[8];
+  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* xr = x + (int64_t)m * H;
+  float ss = 0.f;
+  for (int k = tid * 8; k < H; k += 256 * 8) {
+    Vec8<T> v = ld16(xr + k);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { float f = Tr<T>::f(v.v[e]); srow[k + e] = f; ss = fmaf(f, f, ss); }
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) sred[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += sred[i];
+  const float rs = 1.0f / sqrtf(tot / (float)H + eps);       // torch.rsqrt(variance + eps), fp32
+  for (int k = tid * 8; k < H; k += 256 * 8) {
+    Vec8<T> wv = ld16(w + k), o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = Tr<T>::rr(srow[k + e] * rs);                   // .to(weight.dtype)
+      float r = Tr<T>::rr(Tr<T>::f(wv.v[e]) * y);              // weight * hidden_states
+      o.v[e] = Tr<T>::r(r);
+      srow[k + e] = r;
+    }
+    *reinterpret_cast<uint4*>(out + (int64_t)m * H + k) = *reinterpret_cast<uint4*>(&o);
+  }
+  if (lora_a == nullptr) return;
+  __syncthreads();
+  for (int r = warp; r < lora_rows; r += 8) {                  // lora_A: Linear(H -> r), fp32 accumulate
+    const T* ar = lora_a + (int64_t)r * H;
+    float acc = 0.f;
+    for (int k = lane * 8; k < H; k += 32 * 8) {
+      Vec8<T> av = ld16(ar + k);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(Tr<T>::f(av.v[e]), srow[k + e], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) lora_t[(int64_t)m * lora_rows + r] = Tr<T>::r(acc);
+  }
+}
+
+extern "C" int rd_rmsnorm(const void* x, const void* w, void* out, int M, int H, float eps, const void* lora_a,
+                          int lora_rows, void* lora_t, int dtype, void* stream) {
+  RD_REQUIRE(M > 0 && H > 0 && H % 8 == 0, "rd_rmsnorm: bad shape M=%d H=%d", M, H);
+  RD_REQUIRE(H * 4 <= 200 * 1024, "rd_rmsnorm: H=%d too large", H);
+  RD_DISPATCH_DTYPE(dtype, T, {
+    static bool attr_set = false;
+    if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(rmsnorm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    RD_CHECK_CUDA(rd_launch(rmsnorm_kernel<T>, dim3(M), dim3(256), (size_t)H * 4, (cudaStream_t)stream, rd_pdl_enabled(),
+                            (const T*)x, (const T*)w, (T*)out, H, eps, (const T*)lora_a, lora_rows, (T*)lora_t));
+    return RD_OK;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE + KV-cache append                                 modeling_llama_imgemb.py:128-142, 209-212
+// q_embed = (q*cos) + (rotate_half(q)*sin): three separately rounded ops; cache keeps post-RoPE K.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+rope_kv_store_kernel(T* __restrict__ qkv, const int32_t* __restrict__ pos, const int32_t* __restrict__ ctx_len,
+                     const T* __restrict__ cos_t, const T* __restrict__ sin_t, T* __restrict__ kc, T* __restrict__ vc,
+                     int q_len, int nh, int hd, int cmax) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x, b = m / q_len, i = m % q_len;
+  const int H = nh * hd, half = hd / 2;
+  const int slot = ctx_len[0] + i;
+  const int p = pos[m];
+  T* row = qkv + (int64_t)m * 3 * H;
+  const T* cr = cos_t + (int64_t)p * hd;
+  const T* sr = sin_t + (int64_t)p * hd;
+  for (int idx = threadIdx.x; idx < nh * half; idx += blockDim.x) {
+    const int h = idx / half, d = idx % half;
+    const float c_lo = Tr<T>::f(cr[d]), c_hi = Tr<T>::f(cr[d + half]);
+    const float s_lo = Tr<T>::f(sr[d]), s_hi = Tr<T>::f(sr[d + half]);
+    const int64_t cache_off = (((int64_t)b * nh + h) * cmax + slot) * hd;
+    {
+      T* q = row + h * hd;
+      float lo = Tr<T>::f(q[d]), hi = Tr<T>::f(q[d + half]);
+      q[d] = Tr<T>::r(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
+      q[d + half] = Tr<T>::r(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
+    }
+    {
+      const T* k = row + H + h * hd;
+      float lo = Tr<T>::f(k[d]), hi = Tr<T>::f(k[d + half]);
+      kc[cache_off + d] = Tr<T>::r(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
+      kc[cache_off + d + half] = Tr<T>::r(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
+    }
+    {
+      const T* v = row + 2 * H + h * hd;
+      vc[cache_off + d] = v[d];
+      vc[cache_off + d + half] = v[d + half];
+    }
+  }
+}
+
+extern "C" int rd_rope_kv_store(void* qkv, const int32_t* pos, const int32_t* ctx_len, const void* cos_t,
+                                const void* sin_t, void* kc, void* vc, int B, int q_len, int nh, int hd, int cmax,
+                                int dtype, void* stream) {
+  RD_REQUIRE(B > 0 && q_len > 0 && hd % 2 == 0, "rd_rope_kv_store: bad shape");
+  RD_DISPATCH_DTYPE(dtype, T, {
+    RD_CHECK_CUDA(rd_launch(rope_kv_store_kernel<T>, dim3(B * q_len), dim3(256), 0, (cudaStream_t)stream, rd_pdl_enabled(),
+                            (T*)qkv, pos, ctx_len, (const T*)cos_t, (const T*)sin_t, (T*)kc, (T*)vc, q_len, nh, hd, cmax));
+    return RD_OK;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention against the flat KV cache                               modeling_llama_imgemb.py:216-234
+// One CTA per (query row, head, batch row); 8 key-groups x 16 lanes, each lane owns 8 of the 128 dims
+// (one 128-bit load per key per lane).  Scores are materialised in shared memory so the softmax is the
+// reference's two-pass fp32 softmax with probabilities rounded to the storage dtype before P.V.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_GROUPS = ATT_THREADS / 16;
+
+template <class T>
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __restrict__ kc, const T* __restrict__ vc,
+                 const uint8_t* __restrict__ keymask, const int32_t* __restrict__ ctx_len_p, T* __restrict__ out,
+                 int q_len, int nh, int cmax) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int HD = 128;
+  extern __shared__ float sc[];                 // scores / probabilities [c_tot]
+  __shared__ float sred[ATT_THREADS / 32];
+  __shared__ float spart[ATT_GROUPS][HD];
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = tid >> 4, l16 = tid & 15;
+  const int ctx = ctx_len_p[0];
+  const int c_tot = ctx + q_len;
+  const int jcausal = ctx + i;                  // last key this query may see
+  const uint8_t* km = keymask + (int64_t)b * cmax;
+  const float lowest = Tr<T>::lowest();
+
+  int any = 0;
+  for (int j = tid; j <= jcausal; j += ATT_THREADS) any |= km[j];
+  any = __syncthreads_or(any);
+  // rows with at least one visible key: masked keys past the causal limit contribute exp(min - max) == 0 exactly,
+  // so they are skipped.  All-masked (left-pad) rows are evaluated literally over every key like the reference.
+  const int jend = any ? (jcausal + 1) : c_tot;
+
+  const int64_t m = (int64_t)b * q_len + i;
+  float q[8];
+  {
+    Vec8<T> qv = ld16(qkv + m * ldq + h * HD + l16 * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = Tr<T>::f(qv.v[e]);
+  }
+  const T* kbase = kc + ((int64_t)b * nh + h) * cmax * HD;
+  const T* vbase = vc + ((int64_t)b * nh + h) * cmax * HD;
+  const float inv_sqrt_d = 11.313708498984761f;  // math.sqrt(128)
+  for (int j0 = g; j0 < jend; j0 += ATT_GROUPS * 2) {
+    const int j1 = j0 + ATT_GROUPS;
+    Vec8<T> k0 = ld_stream16(kbase + (int64_t)j0 * HD + l16 * 8);
+    Vec8<T> k1 = (j1 < jend) ? ld_stream16(kbase + (int64_t)j1 * HD + l16 * 8) : k0;
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { d0 = fmaf(q[e], Tr<T>::f(k0.v[e]), d0); d1 = fmaf(q[e], Tr<T>::f(k1.v[e]), d1); }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+    if (l16 == 0) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = t ? j1 : j0;
+        if (j < jend) {
+          float s = Tr<T>::rr(t ? d1 : d0);                      // matmul output in the storage dtype
+          s = Tr<T>::rr(s / inv_sqrt_d);                         // / math.sqrt(head_dim)
+          float madd = km[j] ? 0.f : lowest;                     // _expand_mask
+          if (q_len > 1 && j > jcausal) madd = Tr<T>::rr(madd + lowest);   // + _make_causal_mask (may be -inf)
+          s = Tr<T>::rr(s + madd);
+          s = fmaxf(s, lowest);                                  // torch.max(attn_weights, finfo.min)
+          sc[j] = s;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j < jend; j += ATT_THREADS) mx = fmaxf(mx, sc[j]);
+  mx = warp_max(mx);
+  if (lane == 0) sred[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(sred[0], sred[1]), fmaxf(sred[2], sred[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j < jend; j += ATT_THREADS) { float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+  sum = warp_sum(sum);
+  if (lane == 0) sred[warp] = sum;
+  __syncthreads();
+  sum = (sred[0] + sred[1]) + (sred[2] + sred[3]);
+  for (int j = tid; j < jend; j += ATT_THREADS) sc[j] = Tr<T>::rr(sc[j] / sum);   // softmax(fp32).to(dtype)
+  __syncthreads();
+
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j0 = g; j0 < jend; j0 += ATT_GROUPS * 2) {
+    const int j1 = j0 + ATT_GROUPS;
+    const bool has1 = j1 < jend;
+    Vec8<T> v0 = ld_stream16(vbase + (int64_t)j0 * HD + l16 * 8);
+    Vec8<T> v1 = has1 ? ld_stream16(vbase + (int64_t)j1 * HD + l16 * 8) : v0;
+    const float p0 = sc[j0], p1 = has1 ? sc[j1] : 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { acc[e] = fmaf(p0, Tr<T>::f(v0.v[e]), acc[e]); acc[e] = fmaf(p1, Tr<T>::f(v1.v[e]), acc[e]); }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) spart[g][l16 * 8 + e] = acc[e];
+  __syncthreads();
+  if (tid < HD) {
+    float o = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < ATT_GROUPS; ++gg) o += spart[gg][tid];
+    out[m * (int64_t)(nh * HD) + h * HD + tid] = Tr<T>::r(o);
+  }
+}
+
+extern "C" int rd_attention(const void* qkv, int64_t ldq, const void* kc, const void* vc, const uint8_t* keymask,
+                            const int32_t* ctx_len, void* out, int B, int q_len, int nh, int hd, int cmax, int dtype,
+                            void* stream) {
+  RD_REQUIRE(hd == 128, "rd_attention: head_dim must be 128 (Vicuna-7B); got %d", hd);
+  RD_REQUIRE(B > 0 && q_len > 0 && cmax > 0 && cmax * 4 <= 160 * 1024, "rd_attention: bad shape");
+  RD_DISPATCH_DTYPE(dtype, T, {
+    static bool attr_set = false;
+    if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+    RD_CHECK_CUDA(rd_launch(attention_kernel<T>, dim3(q_len, nh, B), dim3(ATT_THREADS), (size_t)cmax * 4, (cudaStream_t)stream,
+                            rd_pdl_enabled(), (const T*)qkv, ldq, (const T*)kc, (const T*)vc, keymask, ctx_len, (T*)out, q_len, nh, cmax));
+    return RD_OK;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Embedding gather with <IMG> splice                     modeling_llama_imgemb.py:498-520, 581-588
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(128)
+embed_splice_kernel(const int64_t* __restrict__ ids, const T* __restrict__ embed, const T* __restrict__ img,
+                    T* __restrict__ out, int Tlen, int H, int vocab, int img_id, int n_img) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x, b = m / Tlen, t = m % Tlen;
+  __shared__ int s_first;
+  const T* src;
+  if (img != nullptr) {
+    if (threadIdx.x == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    int first = 0x7fffffff;
+    for (int j = threadIdx.x; j < Tlen; j += blockDim.x)
+      if (ids[(int64_t)b * Tlen + j] == img_id) first = min(first, j);
+    if (first != 0x7fffffff) atomicMin(&s_first, first);
+    __syncthreads();
+    const int p = (s_first == 0x7fffffff) ? 0 : s_first;   // rows without <IMG> default to position 0 (:507-510)
+    if (t >= p && t < p + n_img) src = img + ((int64_t)b * n_img + (t - p)) * H;
+    else {
+      int64_t id = ids[m];
+      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+      src = embed + id * H;
+    }
+  } else {
+    int64_t id = ids[m];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    src = embed + id * H;
+  }
+  for (int k = threadIdx.x * 8; k < H; k += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(out + (int64_t)m * H + k) = *reinterpret_cast<const uint4*>(src + k);
+}
+
+extern "C" int rd_embed_splice(const int64_t* ids, const void* embed, const void* img, void* out, int B, int T_, int H,
+                               int vocab, int dtype, void* stream) {
+  RD_REQUIRE(B > 0 && T_ > 0 && H % 8 == 0, "rd_embed_splice: bad shape");
+  RD_DISPATCH_DTYPE(dtype, T, {
+    RD_CHECK_CUDA(rd_launch(embed_splice_kernel<T>, dim3(B * T_), dim3(128), 0, (cudaStream_t)stream, rd_pdl_enabled(),
+                            ids, (const T*)embed, (const T*)img, (T*)out, T_, H, vocab, 32000, 32));
+    return RD_OK;
+  });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generation bookkeeping
+// ------------------------------------------------------------------------------------------------
+// attention_mask = ids != pad (HF 4.28.1 generate infers it; test.py:304 relies on that); position_ids =
+// cumsum(mask)-1 with pads forced to 1 (prepare_inputs_for_generation, modeling_llama_imgemb.py:804-808).
+// One thread per row (T is at most a few hundred and this runs once per prefill).
+__global__ void llm_prep_kernel(const int64_t* __restrict__ ids, uint8_t* __restrict__ keymask, int32_t* __restrict__ pos,
+                                int32_t* __restrict__ npos, const int32_t* __restrict__ ctx_len, int B, int Tlen, int cmax,
+                                int pad_id) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int c0 = ctx_len[0];
+  int n = npos[b];
+  for (int t = 0; t < Tlen; ++t) {
+    const int mk = ids[(int64_t)b * Tlen + t] != pad_id;
+    keymask[(int64_t)b * cmax + c0 + t] = (uint8_t)mk;
+    n += mk;
+    pos[(int64_t)b * Tlen + t] = mk ? (n - 1) : 1;
+  }
+  npos[b] = n;
+}
+
+extern "C" int rd_llm_prep(const int64_t* ids, uint8_t* keymask, int32_t* pos, int32_t* npos, const int32_t* ctx_len,
+                           int B, int T_, int cmax, int pad_id, void* stream) {
+  RD_CHECK_CUDA(rd_launch(llm_prep_kernel, dim3((B + 63) / 64), dim3(64), 0, (cudaStream_t)stream, rd_pdl_enabled(), ids,
+                          keymask, pos, npos, ctx_len, B, T_, cmax, pad_id));
+  return RD_OK;
+}
+
+// Greedy selection of HF 4.28.1 greedy_search on the last-position logits: argmax in the storage dtype (first
+// index on ties), finished rows emit pad, unfinished &= (tok != eos), attention mask grows by a column of ones,
+// next position = number of attended tokens so far.  The last CTA to finish advances the shared counters, so the
+// whole decode step has no host-visible state (CUDA-graph replayable).
+template <class T>
+__global__ void __launch_bounds__(1024)
+argmax_step_kernel(const T* __restrict__ logits, int64_t ld, int V, int64_t* __restrict__ cur_tok,
+                   int64_t* __restrict__ gen, int64_t ldgen, int32_t* __restrict__ finished, uint8_t* __restrict__ keymask,
+                   int cmax, int32_t* __restrict__ pos_cur, int32_t* __restrict__ npos, int32_t* __restrict__ ctx_len,
+                   int32_t* __restrict__ n_gen, uint32_t* __restrict__ done_ctr, int q_len, int pad_id, int eos_id,
+                   int suppress_eos) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* row = logits + (int64_t)b * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = tid; j < V; j += 1024) {
+    float v = Tr<T>::f(row[j]);
+    if (suppress_eos && j == eos_id) v = Tr<T>::lowest();
+    if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = sv[lane]; bi = si[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      const int ctx = ctx_len[0], step = n_gen[0];
+      const int fin = finished[b];
+      const int64_t tok = fin ? (int64_t)pad_id : (int64_t)bi;
+      cur_tok[b] = tok;
+      gen[(int64_t)b * ldgen + step] = tok;
+      finished[b] = fin || (tok == eos_id);
+      if (ctx + q_len < cmax) keymask[(int64_t)b * cmax + ctx + q_len] = 1;
+      pos_cur[b] = npos[b];
+      npos[b] += 1;
+      __threadfence();
+      const uint32_t prev = atomicAdd(done_ctr, 1u);
+      if (prev == gridDim.x - 1) {
+        *done_ctr = 0;
+        ctx_len[0] = ctx + q_len;
+        n_gen[0] = step + 1;
+      }
+    }
+  }
+}
+
+extern "C" int rd_argmax_step(const void* logits, int64_t ld, int V, int64_t* cur_tok, int64_t* gen, int64_t ldgen,
+                              int32_t* finished, uint8_t* keymask, int cmax, int32_t* pos_cur, int32_t* npos,
+                              int32_t* ctx_len, int32_t* n_gen, uint32_t* done_ctr, int B, int q_len, int pad_id,
+                              int eos_id, int suppress_eos, int dtype, void* stream) {
+  RD_DISPATCH_DTYPE(dtype, T, {
+    RD_CHECK_CUDA(rd_launch(argmax_step_kernel<T>, dim3(B), dim3(1024), 0, (cudaStream_t)stream, rd_pdl_enabled(),
+                            (const T*)logits, ld, V, cur_tok, gen, ldgen, finished, keymask, cmax, pos_cur, npos, ctx_len,
+                            n_gen, done_ctr, q_len, pad_id, eos_id, suppress_eos));
+    return RD_OK;
+  });
+}

@@ -1,0 +1,499 @@
+"""Host-side mirror of the reference's LLM surface for the image->report path.
+
+Drop-in for ``model.lavis.models.blip2_models.modeling_llama_imgemb.LlamaForCausalLM`` as used by ``test.py:288-348``
+and ``demo.py:221-297``: same attribute names (``.model`` / ``.base_model`` with a settable ``img_proj_layer``,
+``.config.hidden_size``, ``.device``), ``resize_token_embeddings``, ``.cuda()/.half()/.eval()``, a peft-like
+``PeftModelForCausalLM.from_pretrained`` and ``generate(input_ids, dicom=..., use_img=..., max_new_tokens=...,
+return_dict_in_generate=True, output_scores=True)`` returning ``.sequences`` / ``.scores`` with the semantics of
+transformers 4.28.1 greedy search.  All compute happens in ``libradialog_b200.so`` (sm_100a CUDA); PyTorch only owns
+device memory and streams.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .synth import IMG_TOKEN_ID, NUM_IMG_TOKENS, LlamaCfg
+
+EMB_PKL_TRAIN = "pretraining/embs/stage1_pt_instruct_blip_origlr_img448_embeddings_train_all.pkl"
+EMB_PKL_TEST = "pretraining/embs/stage1_pt_instruct_blip_origlr_img448_embeddings_test.pkl"
+CHAT_IMG_FILE = "current_chat_img.pt"
+
+
+class _Config:
+    """The attributes of HF ``LlamaConfig`` that callers read (``config.hidden_size``: test.py:295, demo.py:229)."""
+
+    def __init__(self, cfg: LlamaCfg):
+        self.vocab_size = cfg.vocab_size
+        self.hidden_size = cfg.hidden_size
+        self.intermediate_size = cfg.intermediate_size
+        self.num_hidden_layers = cfg.num_hidden_layers
+        self.num_attention_heads = cfg.num_attention_heads
+        self.max_position_embeddings = cfg.max_position_embeddings
+        self.rms_norm_eps = cfg.rms_norm_eps
+        self.pad_token_id = cfg.pad_token_id
+        self.bos_token_id = cfg.bos_token_id
+        self.eos_token_id = cfg.eos_token_id
+
+
+@dataclass
+class GreedySearchDecoderOnlyOutput:
+    """``.sequences`` [B, T+n] (prompt included, pad after EOS) and ``.scores`` (tuple of n [B,V] tensors)."""
+    sequences: torch.Tensor
+    scores: Optional[Tuple[torch.Tensor, ...]] = None
+
+
+def rope_tables(head_dim: int, max_pos: int, base: float = 10000.0):
+    """LlamaRotaryEmbedding.__init__ (modeling_llama_imgemb.py:97-109): fp32 tables built on the host."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2).float() / head_dim))
+    t = torch.arange(max_pos, dtype=inv_freq.dtype)
+    freqs = torch.einsum("i,j->ij", t, inv_freq)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos(), emb.sin()
+
+
+class LlamaModel:
+    """``lang_model.model`` / ``lang_model.base_model``: holds the packed weights and the image-embedding side channels
+    (modeling_llama_imgemb.py:433-462)."""
+
+    def __init__(self, cfg: LlamaCfg, dtype: torch.dtype, device: torch.device, load_embedding_pickles: bool = False):
+        self.cfg = cfg
+        self.config = _Config(cfg)
+        self.dtype = dtype
+        self.device = device
+        self.img_proj_layer: Optional[nn.Linear] = None       # set by callers exactly like test.py:295 / demo.py:229
+        self.blip_embeddings: Dict[str, np.ndarray] = {}
+        if load_embedding_pickles:                              # reference behaviour (:454-462): train optional, test required
+            import pickle
+            try:
+                with open(EMB_PKL_TRAIN, "rb") as f:
+                    self.blip_embeddings = pickle.load(f)
+            except Exception:
+                self.blip_embeddings = {}
+                print("WARNING: no train blip embeddings found! For inference that is ok, if you want to train a new model, "
+                      "please generate them as described in the readme.")
+            with open(EMB_PKL_TEST, "rb") as f:                 # FileNotFoundError propagates like the reference
+                self.blip_embeddings.update(pickle.load(f))
+        self.w: Dict[str, torch.Tensor] = {}
+        self.layers_w: List[Dict[str, torch.Tensor]] = []
+        self.has_lora = False
+
+
+class LlamaForCausalLM:
+    # ------------------------------------------------------------------------------------------
+    # construction
+    # ------------------------------------------------------------------------------------------
+    def __init__(self, cfg: LlamaCfg, torch_dtype: torch.dtype = torch.float16, device: Union[str, torch.device] = "cuda:0",
+                 load_embedding_pickles: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("radialog_b200.LlamaForCausalLM needs a CUDA device (sm_100a); there is no CPU path")
+        self._lib = _lib.load()
+        self.cfg = cfg
+        self.config = _Config(cfg)
+        self.dtype = torch_dtype
+        self.device = torch.device(device)
+        self.model = LlamaModel(cfg, torch_dtype, self.device, load_embedding_pickles)
+        self._h = None
+        self._cap = (0, 0)
+        self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self._cached_ids: Optional[torch.Tensor] = None     # host copy of the ids whose KV are in the cache
+        self._img_w_packed = None
+        self.algo = _lib.ALGO_AUTO
+        self.use_cuda_graph = True
+        self.last_stats: Dict[str, float] = {}
+
+    @property
+    def base_model(self):
+        return self.model
+
+    # no-ops kept for call-site compatibility (test.py:299-302, demo.py:236)
+    def cuda(self, *a, **k): return self
+    def half(self): return self
+    def eval(self): return self
+    def to(self, *a, **k): return self
+
+    @classmethod
+    def from_state_dict(cls, cfg: LlamaCfg, sd: Dict[str, torch.Tensor], torch_dtype=torch.float16, device="cuda:0",
+                        **kw) -> "LlamaForCausalLM":
+        m = cls(cfg, torch_dtype, device, **kw)
+        m.load_state_dict(sd)
+        return m
+
+    @classmethod
+    def from_pretrained(cls, path: str, torch_dtype=torch.float16, device_map=None, device="cuda:0", **kw) -> "LlamaForCausalLM":
+        """Loads an HF-format LLaMA directory (config.json + pytorch_model*.bin shards), test.py:289 / demo.py:225."""
+        cfg_path = os.path.join(path, "config.json")
+        if not os.path.exists(cfg_path):
+            raise OSError(f"{path} does not contain config.json (no network access: weights must be on disk)")
+        with open(cfg_path) as f:
+            hc = json.load(f)
+        cfg = LlamaCfg(vocab_size=hc["vocab_size"], hidden_size=hc["hidden_size"], intermediate_size=hc["intermediate_size"],
+                       num_hidden_layers=hc["num_hidden_layers"], num_attention_heads=hc["num_attention_heads"],
+                       max_position_embeddings=hc.get("max_position_embeddings", 2048), rms_norm_eps=hc.get("rms_norm_eps", 1e-6),
+                       pad_token_id=hc.get("pad_token_id", 0) or 0, bos_token_id=hc.get("bos_token_id", 1), eos_token_id=hc.get("eos_token_id", 2))
+        sd: Dict[str, torch.Tensor] = {}
+        for fn in sorted(os.listdir(path)):
+            if fn.startswith("pytorch_model") and fn.endswith(".bin"):
+                sd.update(torch.load(os.path.join(path, fn), map_location="cpu"))
+        if not sd:
+            raise OSError(f"no pytorch_model*.bin shards under {path}")
+        return cls.from_state_dict(cfg, sd, torch_dtype, device, load_embedding_pickles=kw.get("load_embedding_pickles", True))
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """Packs reference-named tensors into the engine layout: fused q|k|v, fused gate|up, LoRA kept unmerged."""
+        cfg, dt, dev = self.cfg, self.dtype, self.device
+        H, r = cfg.hidden_size, cfg.lora_r
+
+        def g(name):
+            return sd[name].to(device=dev, dtype=dt).contiguous()
+
+        m = self.model
+        m.w["embed"] = g("model.embed_tokens.weight")
+        m.w["final_norm"] = g("model.norm.weight")
+        m.w["lm_head"] = g("lm_head.weight")
+        cos, sin = rope_tables(cfg.head_dim, cfg.max_position_embeddings)
+        m.w["cos"], m.w["sin"] = cos.to(dev, dt).contiguous(), sin.to(dev, dt).contiguous()    # :123-124 cast to x.dtype
+        lora_prefix = "base_model.model.model.layers.{}.self_attn.{}."
+        m.has_lora = (lora_prefix.format(0, "q_proj") + "lora_A.weight") in sd
+        m.layers_w = []
+        for i in range(cfg.num_hidden_layers):
+            p = f"model.layers.{i}."
+            lw = {
+                "qkv": torch.cat([g(p + f"self_attn.{n}.weight") for n in ("q_proj", "k_proj", "v_proj")], 0).contiguous(),
+                "o": g(p + "self_attn.o_proj.weight"),
+                "gate_up": torch.cat([g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")], 0).contiguous(),
+                "down": g(p + "mlp.down_proj.weight"),
+                "ln1": g(p + "input_layernorm.weight"),
+                "ln2": g(p + "post_attention_layernorm.weight"),
+            }
+            if m.has_lora:
+                aq, av = g(lora_prefix.format(i, "q_proj") + "lora_A.weight"), g(lora_prefix.format(i, "v_proj") + "lora_A.weight")
+                bq, bv = g(lora_prefix.format(i, "q_proj") + "lora_B.weight"), g(lora_prefix.format(i, "v_proj") + "lora_B.weight")
+                lw["lora_a"] = torch.cat([aq, av], 0).contiguous()                     # [2r, H]
+                lb = torch.zeros(3 * H, 2 * r, device=dev, dtype=dt)                   # block matrix, k rows stay zero
+                lb[:H, :r] = bq
+                lb[2 * H:, r:] = bv
+                lw["lora_b"] = lb
+            m.layers_w.append(lw)
+        if "model.img_proj_layer.weight" in sd:
+            lin = nn.Linear(cfg.qformer_hidden, H)
+            lin.weight.data = sd["model.img_proj_layer.weight"].float().clone()
+            lin.bias.data = sd["model.img_proj_layer.bias"].float().clone()
+            m.img_proj_layer = lin.to(dev)
+        self._destroy_engine()
+        return self
+
+    def load_adapter(self, adapter_sd: Dict[str, torch.Tensor]):
+        """peft adapter_model.bin: lora_A/lora_B of q_proj,v_proj and img_proj_layer (finetune.py:139-145)."""
+        merged = {}
+        for k, v in adapter_sd.items():
+            merged[k] = v
+            if k.endswith("img_proj_layer.weight"):
+                merged["model.img_proj_layer.weight"] = v
+            if k.endswith("img_proj_layer.bias"):
+                merged["model.img_proj_layer.bias"] = v
+        cfg, dt, dev, H, r = self.cfg, self.dtype, self.device, self.cfg.hidden_size, self.cfg.lora_r
+        m = self.model
+        for i, lw in enumerate(m.layers_w):
+            p = f"base_model.model.model.layers.{i}.self_attn."
+            aq, av = merged[p + "q_proj.lora_A.weight"].to(dev, dt), merged[p + "v_proj.lora_A.weight"].to(dev, dt)
+            lw["lora_a"] = torch.cat([aq, av], 0).contiguous()
+            lb = torch.zeros(3 * H, 2 * r, device=dev, dtype=dt)
+            lb[:H, :r] = merged[p + "q_proj.lora_B.weight"].to(dev, dt)
+            lb[2 * H:, r:] = merged[p + "v_proj.lora_B.weight"].to(dev, dt)
+            lw["lora_b"] = lb
+        m.has_lora = True
+        if "model.img_proj_layer.weight" in merged:
+            lin = nn.Linear(cfg.qformer_hidden, H)
+            lin.weight.data = merged["model.img_proj_layer.weight"].float().clone()
+            lin.bias.data = merged["model.img_proj_layer.bias"].float().clone()
+            m.img_proj_layer = lin.to(dev)
+        self._destroy_engine()
+        return self
+
+    def resize_token_embeddings(self, n: int):
+        """HF semantics (test.py:297): grow/shrink embed_tokens and lm_head; new rows N(0, 0.02)."""
+        m = self.model
+        old = m.w["embed"].shape[0]
+        if n == old:
+            return
+        for key in ("embed", "lm_head"):
+            w = m.w[key]
+            new = torch.zeros(n, w.shape[1], device=w.device, dtype=w.dtype)
+            k = min(n, old)
+            new[:k] = w[:k]
+            if n > old:
+                new[old:] = (torch.randn(n - old, w.shape[1], device=w.device) * 0.02).to(w.dtype)
+            m.w[key] = new.contiguous()
+        self.cfg.vocab_size = n
+        self.config.vocab_size = n
+        m.config.vocab_size = n
+        self._destroy_engine()
+
+    # ------------------------------------------------------------------------------------------
+    # engine plumbing
+    # ------------------------------------------------------------------------------------------
+    def _destroy_engine(self):
+        if self._h is not None:
+            torch.cuda.synchronize()
+            self._lib.rd_llm_destroy(self._h)
+            self._h = None
+        self._graphs = {}
+        self._cap = (0, 0)
+        self._cached_ids = None
+
+    def __del__(self):
+        try:
+            self._destroy_engine()
+        except Exception:
+            pass
+
+    def reserve(self, max_batch: int, max_ctx: int):
+        """(Re)creates the native engine with room for ``max_batch`` rows of ``max_ctx`` tokens (KV cache + scratch)."""
+        if self._h is not None and max_batch <= self._cap[0] and max_ctx <= self._cap[1]:
+            return
+        max_batch = max(max_batch, self._cap[0])
+        max_ctx = min(max(max_ctx, self._cap[1]), self.cfg.max_position_embeddings)
+        self._destroy_engine()
+        cfg, m = self.cfg, self.model
+        c = _lib.LlmConfig(vocab=cfg.vocab_size, hidden=cfg.hidden_size, inter=cfg.intermediate_size, layers=cfg.num_hidden_layers,
+                           heads=cfg.num_attention_heads, max_pos=cfg.max_position_embeddings, rms_eps=cfg.rms_norm_eps,
+                           dtype=_lib.dtype_code(self.dtype), lora_r=cfg.lora_r if m.has_lora else 0, lora_scale=cfg.lora_scaling,
+                           qformer_hidden=cfg.qformer_hidden, max_batch=max_batch, max_ctx=max_ctx, pad_id=cfg.pad_token_id,
+                           eos_id=cfg.eos_token_id, img_id=IMG_TOKEN_ID)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.rd_llm_create(C.byref(c), C.byref(h)), "rd_llm_create")
+        self._h = h
+        self._cap = (max_batch, max_ctx)
+        sw = self._lib.rd_llm_set_weight
+        for slot, key in ((_lib.W_EMBED, "embed"), (_lib.W_FINAL_NORM, "final_norm"), (_lib.W_LM_HEAD, "lm_head"),
+                          (_lib.W_ROPE_COS, "cos"), (_lib.W_ROPE_SIN, "sin")):
+            _lib.check(sw(h, -1, slot, _lib.ptr(m.w[key])), f"set_weight {key}")
+        slots = {"qkv": _lib.W_QKV, "o": _lib.W_O, "gate_up": _lib.W_GATE_UP, "down": _lib.W_DOWN, "ln1": _lib.W_LN1,
+                 "ln2": _lib.W_LN2, "lora_a": _lib.W_LORA_A, "lora_b": _lib.W_LORA_B}
+        for i, lw in enumerate(m.layers_w):
+            for key, t in lw.items():
+                _lib.check(sw(h, i, slots[key], _lib.ptr(t)), f"set_weight layer {i} {key}")
+        _lib.check(self._lib.rd_llm_set_algo(h, self.algo), "set_algo")
+
+    def _bind_img_proj(self):
+        lin = self.model.img_proj_layer
+        if lin is None:
+            raise AttributeError("img_proj_layer is not set (callers assign nn.Linear(768, hidden_size): test.py:295)")
+        w = lin.weight.detach().to(self.device, self.dtype).contiguous()
+        # bias is rounded to the storage dtype first (the reference's Linear holds it in fp16 after .half()), kept as fp32 for the epilogue
+        b = lin.bias.detach().to(self.device, self.dtype).float().contiguous()
+        self._img_w_packed = (w, b)
+        _lib.check(self._lib.rd_llm_set_weight(self._h, -1, _lib.W_IMG_PROJ_W, _lib.ptr(w)), "set img_proj w")
+        _lib.check(self._lib.rd_llm_set_weight(self._h, -1, _lib.W_IMG_PROJ_B, _lib.ptr(b)), "set img_proj b")
+
+    def set_algo(self, algo: int):
+        self.algo = algo
+        self._graphs = {}
+        if self._h is not None:
+            _lib.check(self._lib.rd_llm_set_algo(self._h, algo), "set_algo")
+
+    def _state(self):
+        gen, fin, logits, hidden = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_int()
+        _lib.check(self._lib.rd_llm_state(self._h, C.byref(gen), C.byref(fin), C.byref(logits), C.byref(hidden), C.byref(n)), "state")
+        return gen.value, fin.value, logits.value, hidden.value, n.value
+
+    def _wrap(self, ptr: int, shape, dtype):
+        """Zero-copy torch view over engine-owned device memory (read-only use)."""
+        typestr = {torch.int64: "<i8", torch.int32: "<i4", torch.float16: "<f2", torch.uint8: "|u1", torch.bfloat16: "<i2"}[dtype]
+        iface = {"shape": tuple(int(s) for s in shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+        holder = type("_Dev", (), {"__cuda_array_interface__": iface})()
+        t = torch.as_tensor(holder, device=self.device)
+        return t.view(torch.bfloat16) if dtype == torch.bfloat16 else t
+
+    # ------------------------------------------------------------------------------------------
+    # forward for parity dumps: full-position logits like LlamaForCausalLM.forward (:705-793)
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def prefill_logits(self, input_ids: torch.Tensor, img_embeds: Optional[torch.Tensor] = None) -> torch.Tensor:
+        ids = input_ids.to(self.device).long().contiguous()
+        B, T = ids.shape
+        self.reserve(B, T + 2)
+        img = self._prep_img(ids, img_embeds)
+        out = torch.empty(B, T, self.cfg.vocab_size, device=self.device, dtype=self.dtype)
+        _lib.check(self._lib.rd_llm_prefill(self._h, _lib.ptr(ids), _lib.ptr(img), B, T, _lib.ptr(out), 0, _lib.current_stream()), "prefill")
+        torch.cuda.synchronize()
+        self._cached_ids = None
+        return out
+
+    def _prep_img(self, ids: torch.Tensor, img_embeds: Optional[torch.Tensor]):
+        if img_embeds is None:
+            return None
+        B = ids.shape[0]
+        img = img_embeds
+        if img.dim() == 2:
+            img = img[None]
+        if img.shape[0] == 1 and B > 1:
+            img = img.expand(B, -1, -1)
+        if tuple(img.shape) != (B, NUM_IMG_TOKENS, self.cfg.qformer_hidden):
+            raise ValueError(f"image embeddings must be [{B},{NUM_IMG_TOKENS},{self.cfg.qformer_hidden}], got {tuple(img.shape)}")
+        cnt = (ids == IMG_TOKEN_ID).sum(-1)
+        if not bool(((cnt == 0) | (cnt == NUM_IMG_TOKENS)).all()):
+            raise ValueError("each row must contain either no <IMG> token or one run of exactly 32 (split_at_img, "
+                             "modeling_llama_imgemb.py:498-520)")
+        self._bind_img_proj()
+        return img.to(self.device, self.dtype).contiguous()       # .half() cast of the Q-Former output (:576/:579)
+
+    # ------------------------------------------------------------------------------------------
+    # generate
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor = None, dicom: Optional[Sequence[str]] = None, use_img: bool = False,
+                 return_dict_in_generate: bool = False, output_scores: bool = False, max_new_tokens: int = 20, num_beams: int = 1,
+                 img_embeds: Optional[torch.Tensor] = None, suppress_eos: bool = False, reuse_cache: bool = False,
+                 check_every: int = 16, **unused):
+        """Greedy decoding with the semantics of transformers 4.28.1 ``generate`` as the reference calls it
+        (test.py:339-348, demo.py:290-297): attention mask inferred as ``ids != pad``, left padding, EOS rows emit pad.
+
+        ``dicom`` looks the Q-Former tokens up in ``self.model.blip_embeddings`` (KeyError if unknown, like the reference);
+        ``use_img`` reads ``current_chat_img.pt`` from the CWD; ``img_embeds`` is the direct device-tensor hand-off.
+        ``reuse_cache`` keeps the KV cache of the previous call and only runs the new suffix (multi-turn chat)."""
+        if num_beams != 1:
+            raise NotImplementedError("beam search is out of scope of the hot path (SURVEY.md section 8f row 4)")
+        if input_ids is None:
+            raise ValueError("You have to specify either decoder_input_ids or decoder_inputs_embeds")
+        ids = input_ids.to(self.device).long().contiguous()
+        if ids.dim() != 2:
+            raise ValueError(f"input_ids must be [B,T], got {tuple(ids.shape)}")
+        B, T = ids.shape
+        if img_embeds is None:
+            if use_img:
+                img_embeds = torch.load(CHAT_IMG_FILE)                                       # modeling_llama_imgemb.py:576
+            elif dicom is not None:
+                img_embeds = torch.tensor(np.array([self.model.blip_embeddings[d] for d in dicom]))   # :579 (KeyError propagates)
+        if T + max_new_tokens + 1 > self.cfg.max_position_embeddings:
+            raise ValueError(f"prompt ({T}) + max_new_tokens ({max_new_tokens}) exceeds max_position_embeddings")
+        need_ctx = T + max_new_tokens + 1
+        if not (reuse_cache and self._h is not None and B <= self._cap[0] and need_ctx <= self._cap[1]):
+            self.reserve(B, max(need_ctx, 128))
+        st = _lib.current_stream()
+        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ev0.record()
+
+        # ---- prefill (or suffix-only extend when the cached conversation is a prefix of the new one) --------------------
+        ids_host = ids.cpu()
+        start = 0
+        if reuse_cache and self._cached_ids is not None and self._cached_ids.shape[0] == B:
+            start = self._common_prefix(ids_host)
+        if start > 0:
+            npos = (ids_host[:, :start] != self.cfg.pad_token_id).sum(-1).to(torch.int32).contiguous()
+            _lib.check(self._lib.rd_llm_truncate(self._h, start, npos.data_ptr(), st), "truncate")
+            suffix = ids[:, start:].contiguous()
+            _lib.check(self._lib.rd_llm_extend(self._h, _lib.ptr(suffix), B, T - start, int(suppress_eos), st), "extend")
+        else:
+            img = self._prep_img(ids, img_embeds)
+            _lib.check(self._lib.rd_llm_prefill(self._h, _lib.ptr(ids), _lib.ptr(img), B, T, None, int(suppress_eos), st), "prefill")
+        ev1.record()
+        gen_p, fin_p, logits_p, _, _ = self._state()
+        Cmax, V = self._cap[1], self.cfg.vocab_size
+        vpad = (V + 7) // 8 * 8
+        gen_t = self._wrap(gen_p, (self._cap[0], Cmax), torch.int64)
+        fin_t = self._wrap(fin_p, (self._cap[0],), torch.int32)
+        logits_t = self._wrap(logits_p, (self._cap[0], vpad), self.dtype)
+        scores = []
+        if output_scores:
+            scores.append(logits_t[:B, :V].clone())
+
+        # ---- decode loop: one native call (or one CUDA-graph replay) per token ------------------------------------------------
+        n_done = 1
+        stop = False
+        while n_done < max_new_tokens and not stop:
+            self._decode_one(B, st, n_done)
+            n_done += 1
+            if output_scores:
+                scores.append(logits_t[:B, :V].clone())
+            if not suppress_eos and (n_done % check_every == 0 or n_done == max_new_tokens):
+                stop = bool(fin_t[:B].all().item())
+        ev2.record()
+        torch.cuda.synchronize()
+        gen = gen_t[:B, :n_done].clone()
+        n_keep = n_done
+        if not suppress_eos:
+            # HF stops right after the step at which the last unfinished row emitted EOS
+            is_eos = gen == self.cfg.eos_token_id
+            has = is_eos.any(-1)
+            if bool(has.all()):
+                first = torch.where(is_eos, torch.arange(n_done, device=gen.device)[None], n_done).min(-1).values
+                n_keep = int(first.max().item()) + 1
+        gen = gen[:, :n_keep]
+        sequences = torch.cat([ids, gen], dim=-1)
+        # ids whose K/V are in the cache now: prompt + all generated tokens but the last one selected
+        self._cached_ids = torch.cat([ids_host, gen_t[:B, :n_done - 1].cpu()], dim=-1) if n_done > 0 else ids_host
+        self._n_prompt_cached = T
+        self.last_stats = {"prefill_ms": ev0.elapsed_time(ev1), "decode_ms": ev1.elapsed_time(ev2), "new_tokens": n_done,
+                           "prefill_tokens": T - start, "reused_tokens": start}
+        if return_dict_in_generate:
+            return GreedySearchDecoderOnlyOutput(sequences=sequences, scores=tuple(scores[:n_keep]) if output_scores else None)
+        return sequences
+
+    def _decode_one(self, B: int, st: int, n_done: int):
+        if not self.use_cuda_graph or n_done < 2:
+            # the first decode step always runs eagerly (lazy function-attribute setup must not happen under capture)
+            _lib.check(self._lib.rd_llm_decode_step(self._h, st), "decode_step")
+            return
+        g = self._graphs.get(B)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                _lib.check(self._lib.rd_llm_decode_step(self._h, _lib.current_stream()), "decode_step(capture)")
+            _lib.check(self._lib.rd_llm_note_replayed_steps(self._h, -1), "note")   # capture recorded, did not run
+            self._graphs[B] = g
+        g.replay()
+        _lib.check(self._lib.rd_llm_note_replayed_steps(self._h, 1), "note")
+
+    def _common_prefix(self, ids_host: torch.Tensor) -> int:
+        """Longest prefix (same for all rows) of the new conversation whose KV entries are already cached and valid."""
+        cached = self._cached_ids
+        L = min(cached.shape[1], ids_host.shape[1] - 1)       # always leave one token to run
+        if L <= 0:
+            return 0
+        eq = cached[:, :L] == ids_host[:, :L]
+        # a generated pad(0) has mask 1 in the cache but would be masked by a fresh prefill: stop before it
+        gen_region = torch.arange(L)[None] >= self._n_prompt_cached
+        ok = eq & ~(gen_region & (ids_host[:, :L] == self.cfg.pad_token_id))
+        bad = (~ok).float().cumsum(-1) > 0
+        per_row = (~bad).sum(-1)
+        start = int(per_row.min().item())
+        # the <IMG> block must be entirely inside the reused prefix (extend does not splice)
+        img_pos = (ids_host == IMG_TOKEN_ID)
+        if bool(img_pos.any()):
+            last_img = int(torch.where(img_pos.any(0))[0].max().item())
+            if start <= last_img:
+                return 0
+        return start
+
+
+class PeftModelForCausalLM:
+    """Shim with the call shape of ``peft.PeftModelForCausalLM.from_pretrained(model, path, torch_dtype=...,
+    use_ram_optimized_load=False)`` (test.py:301, demo.py:232-234): loads adapter_model.bin into the wrapped model
+    (LoRA stays unmerged, like peft in eval) and returns it."""
+
+    @staticmethod
+    def from_pretrained(model: LlamaForCausalLM, path_or_state_dict, torch_dtype=None, use_ram_optimized_load=False, **kw):
+        if isinstance(path_or_state_dict, dict):
+            sd = path_or_state_dict
+        else:
+            fn = os.path.join(path_or_state_dict, "adapter_model.bin")
+            sd = torch.load(fn, map_location="cpu")
+            cfg_fn = os.path.join(path_or_state_dict, "adapter_config.json")
+            if os.path.exists(cfg_fn):
+                with open(cfg_fn) as f:
+                    ac = json.load(f)
+                model.cfg.lora_r = ac.get("r", model.cfg.lora_r)
+                model.cfg.lora_alpha = ac.get("lora_alpha", model.cfg.lora_alpha)
+        return model.load_adapter(sd)

@@ -1,0 +1,162 @@
+"""GPU parity of rd_linear through the C-ABI: streaming GEMV (M<=4), tcgen05 tiles (all NT widths, split-K, SwiGLU,
+LoRA, residual, bias/act) and the SIMT cross-check kernel, against a plain PyTorch fp32 reference of the same op with
+the same rounding points.  Tolerance: one storage-dtype ulp of the result magnitude (different fp32 summation order is
+the only difference allowed)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from radialog_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_linear(x, w, dtype, bias=None, act=0, residual=None, res_mode=1, lora_t=None, lora_b=None, lora_scale=0.0, N=None):
+    xf, wf = x.float(), w.float()
+    if act == _lib.ACT_SWIGLU:
+        g = (xf @ wf[:N].t()).to(dtype)
+        u = (xf @ wf[N:].t()).to(dtype)
+        return torch.nn.functional.silu(g.float()).to(dtype) * u
+    v = xf @ wf.t()
+    if bias is not None:
+        v = v + bias
+    if residual is not None and res_mode == 2:
+        v = v + residual.float()
+    if act == _lib.ACT_RELU:
+        v = torch.relu(v)
+    elif act == _lib.ACT_GELU:
+        v = torch.nn.functional.gelu(v)
+    y = v.to(dtype)
+    if residual is not None and res_mode == 2:
+        return y
+    if lora_t is not None:
+        s = (lora_t.float() @ lora_b.float().t()).to(dtype)
+        y = y + s * lora_scale
+    if residual is not None:
+        y = residual + y
+    return y
+
+
+def run_linear(lib, x, w, M, N, K, dtype, algo, bias=None, act=0, residual=None, res_mode=1, lora_t=None, lora_b=None,
+               lora_scale=0.0, ws=None):
+    out = torch.full((M, N), float("nan"), device=x.device, dtype=dtype)
+    e = _lib.Epilogue()
+    e.bias_dev = _lib.ptr(bias)
+    e.residual_dev = _lib.ptr(residual)
+    e.ld_res = N
+    e.res_mode = res_mode
+    e.act = act
+    e.lora_t_dev = _lib.ptr(lora_t)
+    e.lora_b_dev = _lib.ptr(lora_b)
+    e.lora_r = 0 if lora_t is None else lora_t.shape[1]
+    e.lora_scale = lora_scale
+    wsp, wsn = (_lib.ptr(ws), ws.numel()) if ws is not None else (None, 0)
+    st = lib.rd_linear(_lib.ptr(x), K, _lib.ptr(w), K, _lib.ptr(out), N, M, N, K, C.byref(e), _lib.dtype_code(dtype), algo, wsp, wsn,
+                       _lib.current_stream())
+    _lib.check(st, "rd_linear")
+    torch.cuda.synchronize()
+    return out
+
+
+def assert_close_ulp(out, ref, dtype, what):
+    assert torch.isfinite(out.float()).all(), f"{what}: non-finite output"
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    scale = ref.float().abs().clamp_min(1e-3)
+    err = ((out.float() - ref.float()).abs() / scale)
+    # <= 2 ulp everywhere, and exact on the overwhelming majority
+    assert err.max().item() <= 2.5 * eps, f"{what}: max rel err {err.max().item():.3e} (> 2.5 ulp {2.5 * eps:.3e})"
+    frac_exact = (out == ref).float().mean().item()
+    assert frac_exact > 0.80, f"{what}: only {frac_exact:.3f} of elements bit-equal"
+
+
+def make(M, N, K, dtype, dev, seed, wrows=None):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.randn(M, K, generator=g) * 0.5).to(dtype).to(dev)
+    w = (torch.randn(wrows or N, K, generator=g) * 0.05).to(dtype).to(dev)
+    return x, w
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M", [1, 2, 3, 4])
+def test_gemv_matches_reference(lib, cuda_dev, dtype, M):
+    for (N, K) in [(256, 256), (1001, 704), (4096, 4096)]:
+        x, w = make(M, N, K, dtype, cuda_dev, seed=N + K + M)
+        out = run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_GEMV)
+        assert_close_ulp(out, ref_linear(x, w, dtype), dtype, f"gemv M={M} N={N} K={K}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M", [5, 16, 32, 33, 64, 100, 128, 200, 256, 300, 1000])
+def test_tcgen05_plain(lib, cuda_dev, dtype, M):
+    ws = torch.zeros(64 << 20, dtype=torch.uint8, device=cuda_dev)
+    for (N, K) in [(128, 64), (256, 256), (1001, 704), (768, 3072)]:
+        x, w = make(M, N, K, dtype, cuda_dev, seed=N + K + M)
+        out = run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, ws=ws)
+        assert_close_ulp(out, ref_linear(x, w, dtype), dtype, f"tc M={M} N={N} K={K}")
+
+
+@pytest.mark.parametrize("splits", [1, 2, 3, 7])
+def test_tcgen05_split_k_is_deterministic_and_correct(lib, cuda_dev, splits):
+    dtype = torch.float16
+    M, N, K = 32, 512, 4096
+    ws = torch.zeros(64 << 20, dtype=torch.uint8, device=cuda_dev)
+    x, w = make(M, N, K, dtype, cuda_dev, seed=7)
+    lib.rd_linear_force_splits(splits)
+    try:
+        a = run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, ws=ws)
+        b = run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, ws=ws)
+    finally:
+        lib.rd_linear_force_splits(0)
+    assert torch.equal(a, b), "split-K result changed between two launches"
+    assert_close_ulp(a, ref_linear(x, w, dtype), dtype, f"tc split={splits}")
+
+
+@pytest.mark.parametrize("algo", [_lib.ALGO_TC, _lib.ALGO_SIMT, _lib.ALGO_GEMV])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_epilogues(lib, cuda_dev, algo, dtype):
+    M = 4 if algo == _lib.ALGO_GEMV else 48
+    N, K = 384, 512
+    ws = torch.zeros(64 << 20, dtype=torch.uint8, device=cuda_dev)
+    g = torch.Generator().manual_seed(5)
+    x, w = make(M, N, K, dtype, cuda_dev, seed=11)
+    bias = (torch.randn(N, generator=g) * 0.1).to(cuda_dev)
+    res = (torch.randn(M, N, generator=g)).to(dtype).to(cuda_dev)
+    # bias + relu / gelu
+    for act in (_lib.ACT_RELU, _lib.ACT_GELU, _lib.ACT_NONE):
+        out = run_linear(lib, x, w, M, N, K, dtype, algo, bias=bias, act=act, ws=ws)
+        assert_close_ulp(out, ref_linear(x, w, dtype, bias=bias, act=act), dtype, f"algo{algo} bias act{act}")
+    # residual, both rounding modes
+    for mode in (1, 2):
+        out = run_linear(lib, x, w, M, N, K, dtype, algo, bias=bias if mode == 2 else None, residual=res, res_mode=mode, ws=ws)
+        assert_close_ulp(out, ref_linear(x, w, dtype, bias=bias if mode == 2 else None, residual=res, res_mode=mode), dtype,
+                         f"algo{algo} residual mode{mode}")
+    # LoRA side product
+    lt = (torch.randn(M, 16, generator=g) * 0.3).to(dtype).to(cuda_dev)
+    lb = (torch.randn(N, 16, generator=g) * 0.05).to(dtype).to(cuda_dev)
+    out = run_linear(lib, x, w, M, N, K, dtype, algo, lora_t=lt, lora_b=lb, lora_scale=2.0, ws=ws)
+    assert_close_ulp(out, ref_linear(x, w, dtype, lora_t=lt, lora_b=lb, lora_scale=2.0), dtype, f"algo{algo} lora")
+    # SwiGLU (gate rows then up rows)
+    x2, w2 = make(M, N, K, dtype, cuda_dev, seed=13, wrows=2 * N)
+    out = run_linear(lib, x2, w2, M, N, K, dtype, algo, act=_lib.ACT_SWIGLU, ws=ws)
+    ref = ref_linear(x2, w2, dtype, act=_lib.ACT_SWIGLU, N=N)
+    assert torch.isfinite(out.float()).all()
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    tol = 4 * eps * ref.float().abs().clamp_min(1e-2)
+    assert ((out.float() - ref.float()).abs() <= tol).all(), f"algo{algo} swiglu"
+
+
+def test_vicuna_decode_shapes_tc_vs_gemv_vs_simt(lib, cuda_dev):
+    """The five GEMM shapes of a Vicuna-7B decode step at batch 32 / 4: tcgen05, GEMV and SIMT agree with each other."""
+    dtype = torch.float16
+    ws = torch.zeros(256 << 20, dtype=torch.uint8, device=cuda_dev)
+    for (N, K, act) in [(12288, 4096, 0), (4096, 4096, 0), (11008, 4096, _lib.ACT_SWIGLU), (4096, 11008, 0), (32001, 4096, 0)]:
+        wrows = 2 * N if act else N
+        x, w = make(32, N, K, dtype, cuda_dev, seed=N, wrows=wrows)
+        tc = run_linear(lib, x, w, 32, N, K, dtype, _lib.ALGO_TC, act=act, ws=ws)
+        simt = run_linear(lib, x, w, 32, N, K, dtype, _lib.ALGO_SIMT, act=act)
+        gemv = run_linear(lib, x[:4].contiguous(), w, 4, N, K, dtype, _lib.ALGO_GEMV, act=act)
+        eps = 2.0 ** -10
+        for name, a, b in (("tc-simt", tc, simt), ("gemv-simt", gemv, simt[:4])):
+            err = (a.float() - b.float()).abs() / b.float().abs().clamp_min(1e-2)
+            assert err.max().item() <= 4 * eps, f"{name} N={N} K={K}: {err.max().item():.3e}"

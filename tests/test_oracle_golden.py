@@ -1,0 +1,102 @@
+"""CPU: pins the oracle (oracle/radialog_oracle.py) against the outputs of the REFERENCE's own modules, committed as
+fixtures by oracle/make_golden.py (the reference ships no tests or golden vectors for this path)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from radialog_b200 import synth
+from oracle import radialog_oracle as O
+
+DT = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}
+
+
+def _load_llm(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, f"llm_{tag}.npz"))
+    v, h, i, l, nh, mp = (int(x) for x in z["cfg"])
+    cfg = synth.LlamaCfg(vocab_size=v, hidden_size=h, intermediate_size=i, num_hidden_layers=l, num_attention_heads=nh,
+                         max_position_embeddings=mp)
+    dtype = DT[str(z["dtype"])]
+    sd = synth.make_llama_weights(cfg, seed=int(z["seed"]), dtype=torch.float32)
+    sd = {k: t.to(torch.float16).float() for k, t in sd.items()}
+    g = torch.Generator().manual_seed(int(z["img_seed"]))
+    prompts = torch.from_numpy(z["prompts"])
+    img = (torch.randn(prompts.shape[0], 32, cfg.qformer_hidden, generator=g) * 0.5).float()
+    return z, cfg, dtype, sd, prompts, img
+
+
+@pytest.mark.parametrize("tag", ["tiny_f32", "tiny_f16", "tiny_bf16"])
+def test_llm_oracle_matches_reference(golden_dir, tag):
+    z, cfg, dtype, sd, prompts, img = _load_llm(golden_dir, tag)
+    orc = O.LlamaOracle(cfg, sd, dtype)
+    mask = prompts.ne(0).long()
+    logits, _ = orc.forward(prompts, mask, orc.positions_from_mask(mask), None, img)
+    ref_last = torch.from_numpy(z["prefill_logits_last"])
+    tol = {"float32": 2e-5, "float16": 4e-3, "bfloat16": 3e-2}[str(z["dtype"])]
+    assert (logits[:, -1].float() - ref_last).abs().max().item() <= tol
+    ids = orc.generate(prompts, img, int(z["new_tokens"]))
+    assert torch.equal(ids, torch.from_numpy(z["sequences"])), "oracle greedy ids differ from the reference's"
+
+
+def test_llm_oracle_real_width_layers(golden_dir):
+    z, cfg, dtype, sd, prompts, img = _load_llm(golden_dir, "wide2_f16")
+    assert cfg.hidden_size == 4096 and cfg.intermediate_size == 11008
+    orc = O.LlamaOracle(cfg, sd, dtype)
+    ids = orc.generate(prompts, img, int(z["new_tokens"]))
+    assert torch.equal(ids, torch.from_numpy(z["sequences"]))
+
+
+def test_vision_oracle_matches_reference_resnet50(golden_dir):
+    z = np.load(os.path.join(golden_dir, "vision_r50_448.npz"))
+    cfg = synth.VisionCfg(image_size=int(z["image_size"]))
+    sd = synth.make_vision_weights(cfg, seed=int(z["seed"]))
+    imgs = synth.make_images(int(z["B"]), size=cfg.image_size, seed=int(z["img_seed"]))
+    torch.set_num_threads(os.cpu_count() or 1)
+    q, e = O.forward_image(imgs, sd, cfg)
+    assert (q - torch.from_numpy(z["q_out"])).abs().max().item() <= 1e-4
+    assert (e[:, ::7, ::11] - torch.from_numpy(z["image_embeds_sub"])).abs().max().item() <= 1e-4
+
+
+def test_oracle_edge_cases():
+    """Left padding, a row without <IMG> (first 32 positions overwritten), EOS rows emitting pad."""
+    cfg = synth.tiny_llama_cfg()
+    sd = synth.make_llama_weights(cfg, seed=1, dtype=torch.float32)
+    sd["lm_head.weight"][cfg.eos_token_id] *= 4.0
+    orc = O.LlamaOracle(cfg, sd, torch.float32)
+    prompts = synth.make_prompts(3, seed=5, ragged=True)
+    prompts[2] = torch.randint(3, 32000, (prompts.shape[1],), generator=torch.Generator().manual_seed(1))   # no <IMG>
+    img = torch.randn(3, 32, cfg.qformer_hidden, generator=torch.Generator().manual_seed(2))
+    emb = orc.embed(prompts, img)
+    w, b = orc.sd["model.img_proj_layer.weight"], orc.sd["model.img_proj_layer.bias"]
+    assert torch.allclose(emb[2, :32], img[2] @ w.t() + b, atol=1e-5)
+    ids = orc.generate(prompts, img, 16)
+    new = ids[:, prompts.shape[1]:]
+    for r in range(3):
+        hit = (new[r] == cfg.eos_token_id).nonzero()
+        if len(hit):
+            assert (new[r, int(hit[0]) + 1:] == cfg.pad_token_id).all()
+    # position ids: cumsum(mask)-1 with pads forced to 1
+    m = torch.tensor([[0, 0, 1, 1, 1]])
+    assert orc.positions_from_mask(m).tolist() == [[1, 1, 0, 1, 2]]
+
+
+def test_prompter_matches_reference_behaviour(tmp_path, monkeypatch):
+    from radialog_b200 import Prompter
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(ValueError):
+        Prompter("")            # default "alpaca" template does not exist (utils/prompter.py:15-20)
+    p = Prompter("vicuna_v11")
+    assert p.generate_prompt("do x") == "do x"
+    assert p.generate_prompt("do x", "with y") == "do x with y"
+    assert p.generate_prompt("do x", None, " ok") == "do x ok"
+    assert p.get_response("USER: a ASSISTANT: b USER: c ASSISTANT:  d ") == "d"
+    assert p.get_response("no marker ") == "no marker"
+    o = O.Prompter({"prompt_input": "{instruction} {input}", "prompt_no_input": "{instruction}", "response_split": "ASSISTANT:"})
+    for args in [("i",), ("i", "j"), ("i", None, "l"), ("i", "j", "l")]:
+        assert o.generate_prompt(*args) == p.generate_prompt(*args)
+    os.makedirs("data/templates")
+    with open("data/templates/custom.json", "w") as f:
+        f.write('{"description": "d", "prompt_input": "<{instruction}|{input}>", "prompt_no_input": "<{instruction}>", "response_split": "##"}')
+    c = Prompter("custom")
+    assert c.generate_prompt("a", "b") == "<a|b>" and c.get_response("x ## y") == "y"
