@@ -77,6 +77,9 @@ int rd_linear(const void* x_dev, int64_t ldx, const void* w_dev, int64_t ldw, vo
 int64_t rd_linear_workspace_bytes(int M, int N, int K);
 /* Test hook: force the split-K factor of the tcgen05 path (0 = heuristic). */
 int rd_linear_force_splits(int splits);
+/* Split-K reduction: 0 (default) thread-block cluster + distributed shared memory when splits <= 8, 1 always through
+ * the global fp32 workspace.  Both reduce in fixed split order (deterministic). */
+int rd_linear_splitk_mode(int mode);
 /* Launch every kernel with the programmatic-dependent-launch attribute (prologue of kernel N+1 — barrier init, TMEM
  * allocation, the first weight tiles — overlaps the tail of kernel N).  Off by default. */
 int rd_set_pdl(int on);
@@ -105,6 +108,12 @@ int rd_rope_kv_store(void* qkv_dev, const int32_t* pos_dev, const int32_t* ctx_l
 int rd_attention(const void* qkv_dev, int64_t ldq, const void* kcache_dev, const void* vcache_dev,
                  const uint8_t* keymask_dev, const int32_t* ctx_len_dev, void* out_dev, int B, int q_len, int nh,
                  int hd, int cmax, int dtype, void* stream);
+
+/* Single-token decode: rd_rope_kv_store + rd_attention (q_len == 1) fused in one launch; pos_dev[B] are the position
+ * ids of the new tokens, which are appended at cache slot ctx_len[0].                                            */
+int rd_attention_decode(const void* qkv_dev, int64_t ldq, const int32_t* pos_dev, const void* cos_dev, const void* sin_dev,
+                        void* kcache_dev, void* vcache_dev, const uint8_t* keymask_dev, const int32_t* ctx_len_dev,
+                        void* out_dev, int B, int nh, int hd, int cmax, int dtype, void* stream);
 
 /* LlamaModel.forward splice (modeling_llama_imgemb.py:571-594, split_at_img :498-520): out[b,t,:] = img[b,t-p,:]
  * for t in [p,p+32) where p = first index of 32000 in row b (0 if none), else embed[ids[b,t]].  img may be NULL

@@ -5,6 +5,8 @@
 #include <vector>
 #include "common.cuh"
 
+extern "C" int rd_attention_decode(const void*, int64_t, const int32_t*, const void*, const void*, void*, void*, const uint8_t*,
+                                   const int32_t*, void*, int, int, int, int, int, void*);
 extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const int32_t*, int, int, int, int, void*);
 extern "C" int rd_argmax_step(const void*, int64_t, int, int64_t*, int64_t*, int64_t, int32_t*, uint8_t*, int, int32_t*,
                               int32_t*, int32_t*, int32_t*, uint32_t*, int, int, int, int, int, int, void*);
@@ -193,10 +195,15 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     rd_epilogue e{};
     if (c.lora_r) { e.lora_t_dev = h->lora_t; e.lora_b_dev = w.lora_b; e.lora_r = 2 * c.lora_r; e.lora_scale = c.lora_scale; }
     RD_CHECK(linear(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, 3 * H, M, 3 * H, H, &e, st));
-    { ProfScope ps(h, st, C_ROPE);
-      RD_CHECK(rd_rope_kv_store(h->qkv, pos, h->ctx_len, h->cos, h->sin, kc, vc, B, q_len, nh, hd, c.max_ctx, dt, st)); }
-    { ProfScope ps(h, st, C_ATTN);
-      RD_CHECK(rd_attention(h->qkv, 3 * H, kc, vc, h->keymask, h->ctx_len, h->att, B, q_len, nh, hd, c.max_ctx, dt, st)); }
+    if (q_len == 1) {      // decode: RoPE + KV append + attention fused in one launch
+      ProfScope ps(h, st, C_ATTN);
+      RD_CHECK(rd_attention_decode(h->qkv, 3 * H, pos, h->cos, h->sin, kc, vc, h->keymask, h->ctx_len, h->att, B, nh, hd, c.max_ctx, dt, st));
+    } else {
+      { ProfScope ps(h, st, C_ROPE);
+        RD_CHECK(rd_rope_kv_store(h->qkv, pos, h->ctx_len, h->cos, h->sin, kc, vc, B, q_len, nh, hd, c.max_ctx, dt, st)); }
+      { ProfScope ps(h, st, C_ATTN);
+        RD_CHECK(rd_attention(h->qkv, 3 * H, kc, vc, h->keymask, h->ctx_len, h->att, B, q_len, nh, hd, c.max_ctx, dt, st)); }
+    }
     rd_epilogue eo{};
     eo.residual_dev = h->x; eo.ld_res = H; eo.res_mode = 1;
     RD_CHECK(linear(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, st));

@@ -21,6 +21,8 @@
 #include "common.cuh"
 
 bool rd_pdl_enabled();
+static int g_splitk_mode = 0;     // 0: cluster/DSMEM reduction when possible, 1: always the global workspace
+extern "C" int rd_linear_splitk_mode(int mode) { g_splitk_mode = mode; return RD_OK; }
 
 namespace {
 
@@ -40,15 +42,27 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a pipeline bug must surface as a launch failure with a message, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
+  long long t0 = 0;
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (!done && (++spins & 0x3FFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) {      // ~2 s at 2 GHz
+        printf("linear_tc_kernel: mbarrier wait timed out (tag %d, block %d,%d,%d, thread %d, parity %u)\n", tag, blockIdx.x,
+               blockIdx.y, blockIdx.z, threadIdx.x, parity);
+        __trap();
+      }
+    }
   } while (!done);
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t hint) {
@@ -75,6 +89,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
+}
+// read a float from the same smem offset of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+  uint32_t raddr;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+  return v;
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -116,6 +138,7 @@ struct TcParams {
   int M, N, K;
   int64_t ldo;
   int splits;
+  int cluster;           // 1: the splits of a tile form a thread-block cluster (1,1,splits), reduction over DSMEM
   float* ws_part;        // [splits][tiles][ACCS][NT][128] fp32
   uint32_t* ws_ctr;      // [tiles]
   uint64_t hint_w, hint_x;
@@ -161,6 +184,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int quad = warp & 3;                      // TMEM lane quadrant an epilogue warp may access
+  const int n_local = quad * 32 + lane;
+  const int n = n0 + n_local;
+  const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const int m_valid = min(NT, p.M - m0);
+  const int tiles = gridDim.x * gridDim.y;
+  const int tile_id = m_tile * gridDim.x + n_tile;
+  float* red = reinterpret_cast<float*>(smem);    // cluster split-K: partial tile parked in the pipeline smem
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -184,7 +215,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       for (int i = pre; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_wait(&empty_bar[s], ph ^ 1u, 1);
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         load_w(s, kb_begin + i);
         load_x(s, kb_begin + i);
@@ -197,7 +228,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&full_bar[s], ph, 2);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t b_addr = a_addr + Cfg::ACCS * Cfg::A_BYTES;
@@ -216,15 +247,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   } else {
     // ===================== epilogue (warps 2..5) =====================
     pdl_wait();
-    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
-    const int n_local = quad * 32 + lane;
-    const int n = n0 + n_local;
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait(tmem_full_bar, 0, 3);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int m_valid = min(NT, p.M - m0);
-    const int tiles = gridDim.x * gridDim.y;
-    const int tile_id = m_tile * gridDim.x + n_tile;
     if (p.splits == 1) {
       for (int c = 0; c < m_valid; c += 16) {
         uint32_t r[16], ru[16];
@@ -240,8 +264,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
           }
         }
       }
+    } else if (p.cluster) {
+      // split-K inside a thread-block cluster: park the fp32 partial tile in this CTA's (now idle) pipeline smem;
+      // after the cluster barrier every CTA reduces its own slice of the token columns over DSMEM.
+      for (int c = 0; c < m_valid; c += 16) {
+#pragma unroll
+        for (int a = 0; a < Cfg::ACCS; ++a) {
+          uint32_t r[16];
+          tc_ld16(taddr + a * NT + c, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c + j < m_valid) red[(a * NT + c + j) * BLOCK_N + n_local] = __uint_as_float(r[j]);
+        }
+      }
     } else {
-      // split-K: publish the fp32 partial tile, the last CTA of the tile reduces all splits in order
+      // split-K through a global workspace: publish the fp32 partial tile, the last CTA of the tile reduces all
+      // splits in fixed order
       float* part = p.ws_part + ((int64_t)split * tiles + tile_id) * (Cfg::ACCS * NT * BLOCK_N);
       for (int c = 0; c < m_valid; c += 16) {
 #pragma unroll
@@ -265,20 +304,55 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       if (*flag_smem) {
         __threadfence();
         if (n < p.N) {
-          for (int j = 0; j < m_valid; ++j) {
-            float acc = 0.f, accu = 0.f;
-            for (int s = 0; s < p.splits; ++s) {
+          for (int c = 0; c < m_valid; c += 8) {
+            float acc[8], accu[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[j] = 0.f; accu[j] = 0.f; }
+            for (int s = 0; s < p.splits; ++s) {       // 8 (16) independent loads in flight per split
               const float* ps = p.ws_part + ((int64_t)s * tiles + tile_id) * (Cfg::ACCS * NT * BLOCK_N);
-              acc += __ldcg(ps + (int64_t)j * BLOCK_N + n_local);
-              if (SWIGLU) accu += __ldcg(ps + ((int64_t)NT + j) * BLOCK_N + n_local);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (c + j < m_valid) {
+                  acc[j] += __ldcg(ps + (int64_t)(c + j) * BLOCK_N + n_local);
+                  if (SWIGLU) accu[j] += __ldcg(ps + ((int64_t)NT + c + j) * BLOCK_N + n_local);
+                }
+              }
             }
-            const int m = m0 + j;
-            out[(int64_t)m * p.ldo + n] = epilogue_elem<T>(p.epi, acc, accu, m, n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int m = m0 + c + j;
+              if (c + j < m_valid) out[(int64_t)m * p.ldo + n] = epilogue_elem<T>(p.epi, acc[j], accu[j], m, n);
+            }
           }
         }
       }
     }
     tc_fence_before();
+  }
+  if (p.cluster) {
+    // every thread of every CTA in the cluster: partial tiles are complete and visible cluster-wide
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp >= 2 && n < p.N) {
+      const uint32_t red_addr = smem_u32(red);
+      for (int j = split; j < m_valid; j += p.splits) {       // this CTA's slice of the token columns
+        float v[8], vu[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          v[s] = 0.f; vu[s] = 0.f;
+          if (s < p.splits) {
+            v[s] = ld_dsmem_f32(red_addr + (uint32_t)((j * BLOCK_N + n_local) * 4), (uint32_t)s);
+            if (SWIGLU) vu[s] = ld_dsmem_f32(red_addr + (uint32_t)(((NT + j) * BLOCK_N + n_local) * 4), (uint32_t)s);
+          }
+        }
+        float acc = 0.f, accu = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) { acc += v[s]; accu += vu[s]; }      // fixed split order: deterministic
+        const int m = m0 + j;
+        out[(int64_t)m * p.ldo + n] = epilogue_elem<T>(p.epi, acc, accu, m, n);
+      }
+    }
+    // nobody leaves (and frees its smem) while a peer may still be reading it
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
@@ -321,17 +395,42 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int
 
 int pick_nt(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256; }
 
-int pick_splits(int M, int N, int K) {
-  const int nt = pick_nt(M);
-  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N, m_tiles = (M + nt - 1) / nt;
-  const int kb = (K + BLOCK_K - 1) / BLOCK_K;
-  if (nt > 64 || n_tiles * m_tiles >= 256) return 1;
-  int s = (296 + n_tiles * m_tiles / 2) / (n_tiles * m_tiles);
-  const int smax = kb / 4 > 0 ? kb / 4 : 1;      // at least 4 k-blocks (32 KB of weights) per CTA
-  s = s < 1 ? 1 : s;
-  s = s > smax ? smax : s;
-  s = s > 16 ? 16 : s;
-  return s;
+// Max CTAs of this kernel that can be co-resident when launched as clusters of (1,1,cs) (cs = 1: plain launch).
+template <class T, int NT, bool SWIGLU>
+int resident_capacity(int cs) {
+  using Cfg = TcCfg<NT, SWIGLU>;
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cs < 1 || cs > 8) return 1;
+  if (cache[cs]) return cache[cs];
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1, 1, cs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)cs;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, linear_tc_kernel<T, NT, SWIGLU>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 148 / cs; }
+  cache[cs] = n * cs;
+  return cache[cs];
+}
+
+// Split-K factor for few-tile (decode) GEMMs.  The kernel is HBM-bound, so what matters is that (a) every CTA of the
+// grid is co-resident in ONE wave (equal shares of the stream finish together; a cluster size whose clusters do not
+// pack into the GPCs silently costs a second wave), (b) there are comfortably more CTAs than SMs pulling on HBM, and
+// (c) the split count is as small as that allows (less reduction work).
+template <class T, int NT, bool SWIGLU>
+int choose_splits(int tiles, int kb) {
+  if (NT > 64) return 1;                          // wide token tiles (prefill / conv): tensor-bound, many tiles
+  const int want = 185;                           // ~1.25 x 148 SMs
+  const int smax = kb / 4 > 0 ? (kb / 4 > 8 ? 8 : kb / 4) : 1;   // >= 4 k-blocks per CTA, portable cluster size <= 8
+  int best = 1, best_ctas = tiles;
+  for (int s = 1; s <= smax; ++s) {
+    const int ctas = tiles * s;
+    if (s > 1 && ctas > resident_capacity<T, NT, SWIGLU>(g_splitk_mode == 0 ? s : 1)) continue;
+    if (ctas >= want) return s;
+    if (ctas > best_ctas) { best = s; best_ctas = ctas; }
+  }
+  return best;
 }
 
 template <class T, int NT, bool SWIGLU>
@@ -347,20 +446,45 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
   RD_CHECK(make_map(&map_w, w, ldw, SWIGLU ? 2 * N : N, K, BLOCK_N, dtype));
   RD_CHECK(make_map(&map_x, x, ldx, M, K, NT, dtype));
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N, m_tiles = (M + NT - 1) / NT;
+  const int kb_total = (K + BLOCK_K - 1) / BLOCK_K;
+  if (splits <= 0) splits = choose_splits<T, NT, SWIGLU>(n_tiles * m_tiles, kb_total);
+  if (splits > kb_total) splits = kb_total;
+  if (splits > 8 && (ws == nullptr || g_splitk_mode == 0)) splits = 8;
+  if (splits > 16) splits = 16;
+  if (splits > 1 && ws == nullptr && g_splitk_mode != 0) splits = 1;
   TcParams p{};
   p.M = M; p.N = N; p.K = K; p.ldo = ldo; p.splits = splits; p.epi = epi;
   // decode: every weight byte is read once (evict-first), the small activation tile is shared by all CTAs (evict-last)
   p.hint_w = m_tiles == 1 ? HINT_EVICT_FIRST : HINT_EVICT_NORMAL;
   p.hint_x = m_tiles == 1 ? HINT_EVICT_LAST : HINT_EVICT_NORMAL;
-  if (splits > 1) {
+  // split-K reduction: thread-block cluster + DSMEM when the splits fit a portable cluster (<= 8) and the partial tile fits the
+  // pipeline smem; otherwise fp32 partials through the global workspace.
+  const bool use_cluster = splits > 1 && splits <= 8 && g_splitk_mode == 0 &&
+                           Cfg::ACCS * NT * BLOCK_N * 4 <= Cfg::STAGES * Cfg::STAGE_BYTES;
+  p.cluster = use_cluster ? 1 : 0;
+  if (splits > 1 && !use_cluster) {
     const int64_t part_bytes = (int64_t)splits * n_tiles * m_tiles * Cfg::ACCS * NT * BLOCK_N * 4;
-    const int64_t need = part_bytes + (int64_t)n_tiles * m_tiles * 4;
+    const int64_t need = part_bytes + ((int64_t)n_tiles * m_tiles * 4 + 255) / 256 * 256;
     RD_REQUIRE(ws != nullptr && ws_bytes >= need, "rd_linear: split-K workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
     p.ws_ctr = reinterpret_cast<uint32_t*>(ws);                                   // counters first (zero-initialised by the owner)
     p.ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((int64_t)n_tiles * m_tiles * 4 + 255) / 256 * 256);
   }
-  RD_CHECK_CUDA(rd_launch(linear_tc_kernel<T, NT, SWIGLU>, dim3(n_tiles, m_tiles, splits), dim3(TC_THREADS), Cfg::SMEM_BYTES, st,
-                          rd_pdl_enabled(), map_w, map_x, (T*)out, p));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_tiles, m_tiles, splits); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (rd_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (use_cluster) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = (unsigned)splits;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<T, NT, SWIGLU>, map_w, map_x, (T*)out, p));
   return RD_OK;
 }
 
@@ -391,11 +515,7 @@ int64_t rd_linear_tc_workspace_bytes(int M, int N, int K) {
 int rd_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
                  const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, cudaStream_t st) {
   const int nt = pick_nt(M);
-  int splits = g_force_splits > 0 ? g_force_splits : pick_splits(M, N, K);
-  const int kb = (K + BLOCK_K - 1) / BLOCK_K;
-  if (splits > kb) splits = kb;
-  if (splits > 16) splits = 16;
-  if (splits > 1 && ws == nullptr) splits = 1;
+  const int splits = g_force_splits > 0 ? g_force_splits : 0;     // 0: chosen per kernel variant from its occupancy
   const bool sw = epi.act == RD_ACT_SWIGLU;
   RD_DISPATCH_DTYPE(dtype, T, {
     if (sw) return dispatch_nt<T, true>(nt, x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, ws, ws_bytes, splits, st);

@@ -133,14 +133,18 @@ extern "C" int rd_rope_kv_store(void* qkv, const int32_t* pos, const int32_t* ct
 constexpr int ATT_THREADS = 128;
 constexpr int ATT_GROUPS = ATT_THREADS / 16;
 
-template <class T>
+// FUSED (decode, q_len == 1): the CTA first applies RoPE to its head's q and k, appends k,v to the cache at slot ctx
+// and keeps the three 128-vectors in shared memory, so the single-token step needs no separate rope/append launch.
+template <class T, bool FUSED>
 __global__ void __launch_bounds__(ATT_THREADS)
-attention_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __restrict__ kc, const T* __restrict__ vc,
+attention_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ kc, T* __restrict__ vc,
                  const uint8_t* __restrict__ keymask, const int32_t* __restrict__ ctx_len_p, T* __restrict__ out,
-                 int q_len, int nh, int cmax) {
+                 int q_len, int nh, int cmax, const int32_t* __restrict__ pos, const T* __restrict__ cos_t,
+                 const T* __restrict__ sin_t) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int HD = 128;
+  __shared__ float s_q[FUSED ? HD : 1], s_k[FUSED ? HD : 1], s_v[FUSED ? HD : 1];
   extern __shared__ float sc[];                 // scores / probabilities [c_tot]
   __shared__ float sred[ATT_THREADS / 32];
   __shared__ float spart[ATT_GROUPS][HD];
@@ -161,31 +165,70 @@ attention_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __restrict__ k
   const int jend = any ? (jcausal + 1) : c_tot;
 
   const int64_t m = (int64_t)b * q_len + i;
+  const T* kbase = kc + ((int64_t)b * nh + h) * cmax * HD;
+  const T* vbase = vc + ((int64_t)b * nh + h) * cmax * HD;
   float q[8];
-  {
+  if (FUSED) {
+    constexpr int half = HD / 2;
+    const int H = nh * HD;
+    const T* row = qkv + m * ldq;
+    const int64_t slot_off = (((int64_t)b * nh + h) * cmax + ctx) * HD;
+    if (tid < half) {
+      const int d = tid, p = pos[b];
+      const float c_lo = Tr<T>::f(cos_t[(int64_t)p * HD + d]), c_hi = Tr<T>::f(cos_t[(int64_t)p * HD + d + half]);
+      const float s_lo = Tr<T>::f(sin_t[(int64_t)p * HD + d]), s_hi = Tr<T>::f(sin_t[(int64_t)p * HD + d + half]);
+      float lo = Tr<T>::f(row[h * HD + d]), hi = Tr<T>::f(row[h * HD + d + half]);
+      s_q[d] = Tr<T>::rr(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));            // q*cos + rotate_half(q)*sin
+      s_q[d + half] = Tr<T>::rr(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
+      lo = Tr<T>::f(row[H + h * HD + d]); hi = Tr<T>::f(row[H + h * HD + d + half]);
+      const float k_lo = Tr<T>::rr(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
+      const float k_hi = Tr<T>::rr(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
+      s_k[d] = k_lo; s_k[d + half] = k_hi;
+      kc[slot_off + d] = Tr<T>::r(k_lo); kc[slot_off + d + half] = Tr<T>::r(k_hi);
+    } else {
+      const int d = tid - half;
+      const T v_lo = row[2 * H + h * HD + d], v_hi = row[2 * H + h * HD + d + half];
+      s_v[d] = Tr<T>::f(v_lo); s_v[d + half] = Tr<T>::f(v_hi);
+      vc[slot_off + d] = v_lo; vc[slot_off + d + half] = v_hi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = s_q[l16 * 8 + e];
+  } else {
     Vec8<T> qv = ld16(qkv + m * ldq + h * HD + l16 * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) q[e] = Tr<T>::f(qv.v[e]);
   }
-  const T* kbase = kc + ((int64_t)b * nh + h) * cmax * HD;
-  const T* vbase = vc + ((int64_t)b * nh + h) * cmax * HD;
-  const float inv_sqrt_d = 11.313708498984761f;  // math.sqrt(128)
+  // key/value row j: from the cache, except the row this CTA has just appended (not visible through the .nc path)
+  auto load_kv = [&](const T* base, const float* fresh, int j) {
+    Vec8<T> r;
+    if (FUSED && j == ctx) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r.v[e] = Tr<T>::r(fresh[l16 * 8 + e]);
+    } else {
+      r = ld_stream16(base + (int64_t)j * HD + l16 * 8);
+    }
+    return r;
+  };
+  const float sqrt_d = 11.313708498984761f;  // math.sqrt(128)
+  const unsigned hmask = 0xFFFFu << (lane & 16);
   for (int j0 = g; j0 < jend; j0 += ATT_GROUPS * 2) {
     const int j1 = j0 + ATT_GROUPS;
-    Vec8<T> k0 = ld_stream16(kbase + (int64_t)j0 * HD + l16 * 8);
-    Vec8<T> k1 = (j1 < jend) ? ld_stream16(kbase + (int64_t)j1 * HD + l16 * 8) : k0;
+    Vec8<T> k0 = load_kv(kbase, s_k, j0);
+    Vec8<T> k1 = (j1 < jend) ? load_kv(kbase, s_k, j1) : k0;
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { d0 = fmaf(q[e], Tr<T>::f(k0.v[e]), d0); d1 = fmaf(q[e], Tr<T>::f(k1.v[e]), d1); }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+    // the two 16-lane key groups of a warp may run different trip counts: shuffle within the half-warp only
+    for (int o = 8; o > 0; o >>= 1) { d0 += __shfl_xor_sync(hmask, d0, o); d1 += __shfl_xor_sync(hmask, d1, o); }
     if (l16 == 0) {
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int j = t ? j1 : j0;
         if (j < jend) {
           float s = Tr<T>::rr(t ? d1 : d0);                      // matmul output in the storage dtype
-          s = Tr<T>::rr(s / inv_sqrt_d);                         // / math.sqrt(head_dim)
+          s = Tr<T>::rr(s / sqrt_d);                             // / math.sqrt(head_dim)
           float madd = km[j] ? 0.f : lowest;                     // _expand_mask
           if (q_len > 1 && j > jcausal) madd = Tr<T>::rr(madd + lowest);   // + _make_causal_mask (may be -inf)
           s = Tr<T>::rr(s + madd);
@@ -216,8 +259,8 @@ attention_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __restrict__ k
   for (int j0 = g; j0 < jend; j0 += ATT_GROUPS * 2) {
     const int j1 = j0 + ATT_GROUPS;
     const bool has1 = j1 < jend;
-    Vec8<T> v0 = ld_stream16(vbase + (int64_t)j0 * HD + l16 * 8);
-    Vec8<T> v1 = has1 ? ld_stream16(vbase + (int64_t)j1 * HD + l16 * 8) : v0;
+    Vec8<T> v0 = load_kv(vbase, s_v, j0);
+    Vec8<T> v1 = has1 ? load_kv(vbase, s_v, j1) : v0;
     const float p0 = sc[j0], p1 = has1 ? sc[j1] : 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { acc[e] = fmaf(p0, Tr<T>::f(v0.v[e]), acc[e]); acc[e] = fmaf(p1, Tr<T>::f(v1.v[e]), acc[e]); }
@@ -240,9 +283,26 @@ extern "C" int rd_attention(const void* qkv, int64_t ldq, const void* kc, const 
   RD_REQUIRE(B > 0 && q_len > 0 && cmax > 0 && cmax * 4 <= 160 * 1024, "rd_attention: bad shape");
   RD_DISPATCH_DTYPE(dtype, T, {
     static bool attr_set = false;
-    if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
-    RD_CHECK_CUDA(rd_launch(attention_kernel<T>, dim3(q_len, nh, B), dim3(ATT_THREADS), (size_t)cmax * 4, (cudaStream_t)stream,
-                            rd_pdl_enabled(), (const T*)qkv, ldq, (const T*)kc, (const T*)vc, keymask, ctx_len, (T*)out, q_len, nh, cmax));
+    if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+    RD_CHECK_CUDA(rd_launch(attention_kernel<T, false>, dim3(q_len, nh, B), dim3(ATT_THREADS), (size_t)cmax * 4, (cudaStream_t)stream,
+                            rd_pdl_enabled(), (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, q_len, nh, cmax,
+                            (const int32_t*)nullptr, (const T*)nullptr, (const T*)nullptr));
+    return RD_OK;
+  });
+}
+
+// Single-token decode: RoPE + KV append + attention in one launch (rd_rope_kv_store + rd_attention with q_len == 1).
+extern "C" int rd_attention_decode(const void* qkv, int64_t ldq, const int32_t* pos, const void* cos_t, const void* sin_t,
+                                   void* kc, void* vc, const uint8_t* keymask, const int32_t* ctx_len, void* out, int B, int nh,
+                                   int hd, int cmax, int dtype, void* stream) {
+  RD_REQUIRE(hd == 128, "rd_attention_decode: head_dim must be 128 (Vicuna-7B); got %d", hd);
+  RD_REQUIRE(B > 0 && cmax > 0 && cmax * 4 <= 160 * 1024, "rd_attention_decode: bad shape");
+  RD_DISPATCH_DTYPE(dtype, T, {
+    static bool attr_set = false;
+    if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+    RD_CHECK_CUDA(rd_launch(attention_kernel<T, true>, dim3(1, nh, B), dim3(ATT_THREADS), (size_t)cmax * 4, (cudaStream_t)stream,
+                            rd_pdl_enabled(), (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, 1, nh, cmax, pos,
+                            (const T*)cos_t, (const T*)sin_t));
     return RD_OK;
   });
 }

@@ -104,6 +104,10 @@ class LlamaForCausalLM:
         self._h = None
         self._cap = (0, 0)
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self._graph_kernels: Dict[int, int] = {}
+        self._capture_launches = 0
+        self._replayed_kernels = 0
+        self._n_prompt_cached = 0
         self._cached_ids: Optional[torch.Tensor] = None     # host copy of the ids whose KV are in the cache
         self._img_w_packed = None
         self.algo = _lib.ALGO_AUTO
@@ -247,6 +251,9 @@ class LlamaForCausalLM:
             self._lib.rd_llm_destroy(self._h)
             self._h = None
         self._graphs = {}
+        self._graph_kernels = {}
+        self._capture_launches = 0
+        self._replayed_kernels = 0
         self._cap = (0, 0)
         self._cached_ids = None
 
@@ -448,13 +455,44 @@ class LlamaForCausalLM:
             return
         g = self._graphs.get(B)
         if g is None:
+            before = int(self._lib.rd_llm_launch_count(self._h))
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 _lib.check(self._lib.rd_llm_decode_step(self._h, _lib.current_stream()), "decode_step(capture)")
             _lib.check(self._lib.rd_llm_note_replayed_steps(self._h, -1), "note")   # capture recorded, did not run
             self._graphs[B] = g
+            self._graph_kernels[B] = int(self._lib.rd_llm_launch_count(self._h)) - before
+            self._capture_launches += self._graph_kernels[B]
         g.replay()
+        self._replayed_kernels += self._graph_kernels[B]
         _lib.check(self._lib.rd_llm_note_replayed_steps(self._h, 1), "note")
+
+    def launch_count(self) -> int:
+        """Kernels of libradialog_b200 launched so far (eager launches + kernels inside replayed CUDA graphs)."""
+        if self._h is None:
+            return 0
+        return int(self._lib.rd_llm_launch_count(self._h)) - self._capture_launches + self._replayed_kernels
+
+    @torch.no_grad()
+    def profile_decode_steps(self, B: int, T: int, steps: int = 8) -> Dict[str, Dict[str, float]]:
+        """Per-kernel-class device time of `steps` eager decode steps (CUDA events around every launch) at context ~T."""
+        from .synth import make_prompts
+        ids = make_prompts(B, seed=1)[:, :T].to(self.device).contiguous()
+        self.reserve(B, T + steps + 4)
+        st = _lib.current_stream()
+        _lib.check(self._lib.rd_llm_prefill(self._h, _lib.ptr(ids), None, B, T, None, 1, st), "prefill")
+        _lib.check(self._lib.rd_llm_decode_step(self._h, st), "decode_step")       # warm
+        torch.cuda.synchronize()
+        _lib.check(self._lib.rd_llm_profile(self._h, 1), "profile on")
+        for _ in range(steps):
+            _lib.check(self._lib.rd_llm_decode_step(self._h, st), "decode_step")
+        n = len(_lib.PROFILE_CLASSES)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        _lib.check(self._lib.rd_llm_profile_read(self._h, ms, cnt, n), "profile read")
+        _lib.check(self._lib.rd_llm_profile(self._h, 0), "profile off")
+        self._cached_ids = None
+        return {name: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, name in enumerate(_lib.PROFILE_CLASSES)}
 
     def _common_prefix(self, ids_host: torch.Tensor) -> int:
         """Longest prefix (same for all rows) of the new conversation whose KV entries are already cached and valid."""

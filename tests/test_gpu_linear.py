@@ -59,13 +59,17 @@ def run_linear(lib, x, w, M, N, K, dtype, algo, bias=None, act=0, residual=None,
     return out
 
 
-def assert_close_ulp(out, ref, dtype, what):
-    assert torch.isfinite(out.float()).all(), f"{what}: non-finite output"
+def assert_close_ulp(out, ref, dtype, what, mag=None):
+    """|out-ref| <= 2.5 ulp(magnitude) + 1e-5*max|ref| (the absolute floor covers results that cancel to ~0, where the
+    fp32 summation-order difference is larger than an ulp of the tiny result), and bit-equal on the vast majority.
+    `mag`: magnitude of the intermediate that carries the rounding (e.g. |residual|+|y| for a two-rounding epilogue)."""
+    assert torch.isfinite(out.float()).all(), f"{what}: non-finite / unwritten output"
     eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
-    scale = ref.float().abs().clamp_min(1e-3)
-    err = ((out.float() - ref.float()).abs() / scale)
-    # <= 2 ulp everywhere, and exact on the overwhelming majority
-    assert err.max().item() <= 2.5 * eps, f"{what}: max rel err {err.max().item():.3e} (> 2.5 ulp {2.5 * eps:.3e})"
+    r = ref.float()
+    tol = 2.5 * eps * (r.abs() if mag is None else mag.float().abs()) + 1e-5 * r.abs().max()
+    err = (out.float() - r).abs()
+    worst = (err - tol).max().item()
+    assert worst <= 0, f"{what}: error exceeds tolerance by {worst:.3e} (max abs err {err.max().item():.3e})"
     frac_exact = (out == ref).float().mean().item()
     assert frac_exact > 0.80, f"{what}: only {frac_exact:.3f} of elements bit-equal"
 
@@ -96,18 +100,22 @@ def test_tcgen05_plain(lib, cuda_dev, dtype, M):
         assert_close_ulp(out, ref_linear(x, w, dtype), dtype, f"tc M={M} N={N} K={K}")
 
 
-@pytest.mark.parametrize("splits", [1, 2, 3, 7])
-def test_tcgen05_split_k_is_deterministic_and_correct(lib, cuda_dev, splits):
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("splits", [1, 2, 3, 7, 8, 12])
+def test_tcgen05_split_k_is_deterministic_and_correct(lib, cuda_dev, splits, mode):
+    """mode 0: cluster + DSMEM reduction (splits <= 8), mode 1: global fp32 workspace."""
     dtype = torch.float16
     M, N, K = 32, 512, 4096
     ws = torch.zeros(64 << 20, dtype=torch.uint8, device=cuda_dev)
     x, w = make(M, N, K, dtype, cuda_dev, seed=7)
     lib.rd_linear_force_splits(splits)
+    lib.rd_linear_splitk_mode(mode)
     try:
         a = run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, ws=ws)
         b = run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, ws=ws)
     finally:
         lib.rd_linear_force_splits(0)
+        lib.rd_linear_splitk_mode(0)
     assert torch.equal(a, b), "split-K result changed between two launches"
     assert_close_ulp(a, ref_linear(x, w, dtype), dtype, f"tc split={splits}")
 
@@ -129,13 +137,14 @@ def test_epilogues(lib, cuda_dev, algo, dtype):
     # residual, both rounding modes
     for mode in (1, 2):
         out = run_linear(lib, x, w, M, N, K, dtype, algo, bias=bias if mode == 2 else None, residual=res, res_mode=mode, ws=ws)
-        assert_close_ulp(out, ref_linear(x, w, dtype, bias=bias if mode == 2 else None, residual=res, res_mode=mode), dtype,
-                         f"algo{algo} residual mode{mode}")
+        ref = ref_linear(x, w, dtype, bias=bias if mode == 2 else None, residual=res, res_mode=mode)
+        assert_close_ulp(out, ref, dtype, f"algo{algo} residual mode{mode}", mag=ref.float().abs() + res.float().abs())
     # LoRA side product
     lt = (torch.randn(M, 16, generator=g) * 0.3).to(dtype).to(cuda_dev)
     lb = (torch.randn(N, 16, generator=g) * 0.05).to(dtype).to(cuda_dev)
     out = run_linear(lib, x, w, M, N, K, dtype, algo, lora_t=lt, lora_b=lb, lora_scale=2.0, ws=ws)
-    assert_close_ulp(out, ref_linear(x, w, dtype, lora_t=lt, lora_b=lb, lora_scale=2.0), dtype, f"algo{algo} lora")
+    ref = ref_linear(x, w, dtype, lora_t=lt, lora_b=lb, lora_scale=2.0)
+    assert_close_ulp(out, ref, dtype, f"algo{algo} lora", mag=ref.float().abs() + 2.0 * (lt.float() @ lb.float().t()).abs())
     # SwiGLU (gate rows then up rows)
     x2, w2 = make(M, N, K, dtype, cuda_dev, seed=13, wrows=2 * N)
     out = run_linear(lib, x2, w2, M, N, K, dtype, algo, act=_lib.ACT_SWIGLU, ws=ws)
@@ -158,5 +167,6 @@ def test_vicuna_decode_shapes_tc_vs_gemv_vs_simt(lib, cuda_dev):
         gemv = run_linear(lib, x[:4].contiguous(), w, 4, N, K, dtype, _lib.ALGO_GEMV, act=act)
         eps = 2.0 ** -10
         for name, a, b in (("tc-simt", tc, simt), ("gemv-simt", gemv, simt[:4])):
+            assert torch.isfinite(a.float()).all() and torch.isfinite(b.float()).all(), f"{name} N={N} K={K}: unwritten output"
             err = (a.float() - b.float()).abs() / b.float().abs().clamp_min(1e-2)
             assert err.max().item() <= 4 * eps, f"{name} N={N} K={K}: {err.max().item():.3e}"

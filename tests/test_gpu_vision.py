@@ -65,7 +65,7 @@ def test_image_to_report_end_to_end(cuda_dev):
     (tie rule as in test_gpu_llm)."""
     from radialog_b200.llm import LlamaForCausalLM
     from radialog_b200.pipeline import ReportPipeline
-    from tests.test_gpu_llm import assert_ids_match
+    from parity_util import assert_ids_match
     vcfg = synth.tiny_vision_cfg(q_hidden=768, q_heads=12, q_intermediate=256, joint_feature_size=128)
     lcfg = synth.tiny_llama_cfg()
     vsd = synth.make_vision_weights(vcfg, seed=0)
