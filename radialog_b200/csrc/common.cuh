@@ -126,8 +126,19 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
 // acc: fp32 accumulator of out[m,n]; acc_up: accumulator of the paired up_proj row (SWIGLU only)
+// lora_b_row: optional register copy of lora_B[n, 0..lora_r) (lora_r <= 16) for callers whose thread owns one output
+// column n across many rows m (tcgen05 epilogue); nullptr = read it from global memory per element.
+constexpr int RD_MAX_LORA_REG = 16;
 template <class T>
-__device__ __forceinline__ T epilogue_elem(const EpiParams& p, float acc, float acc_up, int m, int n) {
+__device__ __forceinline__ void load_lora_b_row(const EpiParams& p, int n, float (&breg)[RD_MAX_LORA_REG]) {
+  const T* b = reinterpret_cast<const T*>(p.lora_b) + (int64_t)n * p.lora_r;
+#pragma unroll
+  for (int r = 0; r < RD_MAX_LORA_REG; ++r) breg[r] = r < p.lora_r ? Tr<T>::f(b[r]) : 0.f;
+}
+
+template <class T>
+__device__ __forceinline__ T epilogue_elem(const EpiParams& p, float acc, float acc_up, int m, int n,
+                                           const float* lora_b_row = nullptr) {
   float v = acc;
   if (p.bias) v += p.bias[n];
   float y;
@@ -144,9 +155,18 @@ __device__ __forceinline__ T epilogue_elem(const EpiParams& p, float acc, float 
   }
   if (p.lora_r > 0) {
     const T* t = reinterpret_cast<const T*>(p.lora_t) + (int64_t)m * p.lora_r;
-    const T* b = reinterpret_cast<const T*>(p.lora_b) + (int64_t)n * p.lora_r;
     float s = 0.f;
-    for (int r = 0; r < p.lora_r; ++r) s += Tr<T>::f(t[r]) * Tr<T>::f(b[r]);
+    if (lora_b_row != nullptr && p.lora_r == RD_MAX_LORA_REG) {
+      // lora_t row: two 128-bit loads, identical across the warp (same m) -> one L1 broadcast each
+      Vec8<T> t0 = ld16(t), t1 = ld16(t + 8);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) s += Tr<T>::f(t0.v[r]) * lora_b_row[r];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) s += Tr<T>::f(t1.v[r]) * lora_b_row[8 + r];
+    } else {
+      const T* b = reinterpret_cast<const T*>(p.lora_b) + (int64_t)n * p.lora_r;
+      for (int r = 0; r < p.lora_r; ++r) s += Tr<T>::f(t[r]) * Tr<T>::f(b[r]);
+    }
     y = Tr<T>::rr(y + Tr<T>::rr(p.lora_scale * Tr<T>::rr(s)));
   }
   if (p.residual) y = Tr<T>::rr(Tr<T>::f(reinterpret_cast<const T*>(p.residual)[(int64_t)m * p.ld_res + n]) + y);

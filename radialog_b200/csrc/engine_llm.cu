@@ -70,7 +70,7 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
   h->L.resize(cfg->layers);
   const int64_t H = cfg->hidden, I = cfg->inter, Bm = cfg->max_batch, C = cfg->max_ctx, e = 2;
   h->max_tokens = Bm * C;
-  h->vpad = (cfg->vocab + 7) / 8 * 8;
+  h->vpad = (cfg->vocab + 63) / 64 * 64;      // 128-byte row pitch: the epilogue's 64-byte warp stores stay sector aligned
   const int64_t Mt = h->max_tokens;
   int r = RD_OK;
   auto A = [&](char** p, int64_t bytes) { if (r == RD_OK) r = dalloc(p, bytes); };

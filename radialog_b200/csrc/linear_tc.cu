@@ -18,13 +18,25 @@
 // PDL: weight tiles never depend on the previous kernel, so the producer issues the first pipeline stages of W
 // before griddepcontrol.wait and only then loads the activations.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 bool rd_pdl_enabled();
+unsigned long long* rd_linear_trace_buffer();
+static int g_force_generic_epilogue = 0;   // test hook
+extern "C" int rd_linear_force_generic_epilogue(int on) { g_force_generic_epilogue = on; return RD_OK; }
 static int g_splitk_mode = 0;     // 0: cluster/DSMEM reduction when possible, 1: always the global workspace
 extern "C" int rd_linear_splitk_mode(int mode) { g_splitk_mode = mode; return RD_OK; }
 
 namespace {
+
+// The fused epilogue is called from several fully unrolled accumulator loops; inlining it there makes a ~24k-instruction
+// kernel whose straight-line epilogue runs at instruction-fetch latency (measured: ~250 ns per output element).  One
+// out-of-line copy keeps the epilogue resident in the instruction cache.
+template <class T>
+__device__ __noinline__ T epilogue_call(const EpiParams& p, float acc, float acc_up, int m, int n, const float* lora_b_row) {
+  return epilogue_elem<T>(p, acc, acc_up, m, n, lora_b_row);
+}
 
 constexpr int BLOCK_N = 128;   // weight rows per tile  (UMMA M)
 constexpr int BLOCK_K = 64;    // 64 x 2 B = 128 B = one swizzle-128B row
@@ -95,8 +107,16 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank
   uint32_t raddr;
   float v;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr));
   return v;
+}
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot) {
+  if (trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    trace[(size_t)cta * 16 + slot] = t;
+  }
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -117,6 +137,63 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int umma_m, int umma_
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue specialisation.  The generic fused epilogue (epilogue_elem) re-reads its kernel parameters through the
+// uniform datapath for every element, which measured ~250 ns per output element on the decode shapes; the hot
+// decode/prefill cases therefore get branch-free paths whose operands are hoisted into registers once per thread.
+// ------------------------------------------------------------------------------------------------
+enum { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_RES1 = 2, EPI_LORA16 = 3 };
+
+template <class T> struct EpiCtx {
+  T* outp;              // out + n
+  int64_t ldo;
+  const T* resp;        // residual + n            (EPI_RES1)
+  int64_t ld_res;
+  const T* lora_t;      // [M,16]                  (EPI_LORA16)
+  float lora_scale;
+  float b[16];          // lora_B[n, 0..16)        (EPI_LORA16)
+  const T* res_s;       // staged residual tile [NT][128] (nullptr = read global)
+  const T* lt_s;        // staged lora_t tile [NT][16]    (nullptr = read global)
+  int n_local;
+};
+
+template <class T, bool SWIGLU, int MODE>
+__device__ __forceinline__ void finish_store(const EpiParams& ep, const EpiCtx<T>& cx, float acc, float accu, int m, int n, int j) {
+  T y;
+  if (MODE == EPI_PLAIN) {
+    if (SWIGLU) {
+      const float g = Tr<T>::rr(acc), u = Tr<T>::rr(accu);
+      y = Tr<T>::r(Tr<T>::rr(silu_f(g)) * u);                           // T(T(silu(T(g))) * T(u))
+    } else {
+      y = Tr<T>::r(acc);
+    }
+  } else if (MODE == EPI_RES1) {
+    const float res = cx.res_s ? Tr<T>::f(cx.res_s[j * BLOCK_N + cx.n_local]) : Tr<T>::f(cx.resp[(int64_t)m * cx.ld_res]);
+    y = Tr<T>::r(res + Tr<T>::rr(acc));                                  // fp16 residual add after rounding Wx
+  } else if (MODE == EPI_LORA16) {
+    const T* trow = cx.lt_s ? cx.lt_s + j * 16 : cx.lora_t + (int64_t)m * 16;
+    const Vec8<T> t0 = ld16(trow), t1 = ld16(trow + 8);
+    float sdot = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sdot += Tr<T>::f(t0.v[r]) * cx.b[r];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sdot += Tr<T>::f(t1.v[r]) * cx.b[8 + r];
+    y = Tr<T>::r(Tr<T>::rr(acc) + Tr<T>::rr(cx.lora_scale * Tr<T>::rr(sdot)));
+  } else {
+    y = epilogue_elem<T>(ep, acc, accu, m, n, nullptr);
+  }
+  cx.outp[(int64_t)m * cx.ldo] = y;
+}
+
+#define EPI_DISPATCH(MODEVAR, ...)                                             \
+  switch (MODEVAR) {                                                           \
+    case EPI_PLAIN: { constexpr int MODE = EPI_PLAIN; __VA_ARGS__ } break;     \
+    case EPI_RES1: { constexpr int MODE = EPI_RES1; __VA_ARGS__ } break;       \
+    case EPI_LORA16: { constexpr int MODE = EPI_LORA16; __VA_ARGS__ } break;   \
+    default: { constexpr int MODE = EPI_GENERIC; __VA_ARGS__ } break;          \
+  }
+
 constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 template <int NT, bool SWIGLU> struct TcCfg {
@@ -126,11 +203,15 @@ template <int NT, bool SWIGLU> struct TcCfg {
   static constexpr int STAGE_BYTES = ACCS * A_BYTES + B_BYTES;
   // small-token (decode) tiles: keep two CTAs resident per SM so one CTA's prologue/epilogue hides behind the
   // other's weight stream; wide tiles take the whole SM.
-  static constexpr int SMEM_BUDGET = (NT <= 64) ? 108 * 1024 : 200 * 1024;
+  // decode tiles (NT <= 32, plain accumulator) stage the epilogue's residual / lora_t operands in smem while the
+  // weight stream runs, so the tail after the last MMA does not wait on global loads
+  static constexpr bool STAGE_EPI = (NT <= 32) && !SWIGLU;
+  static constexpr int EXTRA_BYTES = STAGE_EPI ? (NT * BLOCK_N * 2 + NT * 16 * 2) : 0;     // residual tile + lora_t tile
+  static constexpr int SMEM_BUDGET = (NT <= 64) ? (STAGE_EPI ? 100 * 1024 : 108 * 1024) : 200 * 1024;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = tmem_cols_for(ACCS * NT);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EXTRA_BYTES;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
@@ -138,15 +219,17 @@ struct TcParams {
   int M, N, K;
   int64_t ldo;
   int splits;
+  int epi_mode;          // EPI_*: which specialised epilogue applies
   int cluster;           // 1: the splits of a tile form a thread-block cluster (1,1,splits), reduction over DSMEM
   float* ws_part;        // [splits][tiles][ACCS][NT][128] fp32
   uint32_t* ws_ctr;      // [tiles]
   uint64_t hint_w, hint_x;
+  unsigned long long* trace;   // development aid: [cta][8] globaltimer stamps (nullptr = off)
   EpiParams epi;
 };
 
 template <class T, int NT, bool SWIGLU>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, (NT <= 64) ? 2 : 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, T* __restrict__ out,
                  const TcParams p) {
   using Cfg = TcCfg<NT, SWIGLU>;
@@ -168,6 +251,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   const int nkb = kb_end - kb_begin;
 
   pdl_launch_dependents();
+  if (threadIdx.x == 0) trace_stamp(p.trace, 0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
@@ -184,6 +268,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) trace_stamp(p.trace, 1);
   const int quad = warp & 3;                      // TMEM lane quadrant an epilogue warp may access
   const int n_local = quad * 32 + lane;
   const int n = n0 + n_local;
@@ -192,6 +277,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   const int tiles = gridDim.x * gridDim.y;
   const int tile_id = m_tile * gridDim.x + n_tile;
   float* red = reinterpret_cast<float*>(smem);    // cluster split-K: partial tile parked in the pipeline smem
+  EpiCtx<T> cx;                                   // epilogue operands hoisted into registers (epilogue warps only)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -211,6 +297,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         load_w(i, kb_begin + i);
       }
       pdl_wait();                                // activations were written by the previous kernel
+      trace_stamp(p.trace, 2);
       for (int i = 0; i < pre; ++i) load_x(i, kb_begin + i);
       for (int i = pre; i < nkb; ++i) {
         const int s = i % STAGES;
@@ -229,6 +316,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         mbar_wait(&full_bar[s], ph, 2);
+        if (i == 0) trace_stamp(p.trace, 3);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t b_addr = a_addr + Cfg::ACCS * Cfg::A_BYTES;
@@ -243,37 +331,72 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         tc_commit(&empty_bar[s]);                 // frees the smem stage once these MMAs have read it
       }
       tc_commit(tmem_full_bar);                   // accumulators complete
+      trace_stamp(p.trace, 4);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     pdl_wait();
+    cx.outp = out + n; cx.ldo = p.ldo;
+    cx.resp = reinterpret_cast<const T*>(p.epi.residual) + n; cx.ld_res = p.epi.ld_res;
+    cx.lora_t = reinterpret_cast<const T*>(p.epi.lora_t); cx.lora_scale = p.epi.lora_scale;
+    if (p.epi_mode == EPI_LORA16 && n < p.N) {
+      const T* brow = reinterpret_cast<const T*>(p.epi.lora_b) + (int64_t)n * 16;
+      const Vec8<T> b0 = ld16(brow), b1 = ld16(brow + 8);
+_Pragma("unroll")
+      for (int r = 0; r < 8; ++r) { cx.b[r] = Tr<T>::f(b0.v[r]); cx.b[8 + r] = Tr<T>::f(b1.v[r]); }
+    }
+    cx.res_s = nullptr; cx.lt_s = nullptr; cx.n_local = n_local;
+    if (Cfg::STAGE_EPI) {
+      // while the weight stream runs: pull the residual values this thread will add and the lora_t rows of the tile
+      T* res_s = reinterpret_cast<T*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+      T* lt_s = res_s + NT * BLOCK_N;
+      if (p.epi_mode == EPI_RES1 && n < p.N && (p.splits == 1 || p.cluster)) {
+        const int j0 = p.splits == 1 ? 0 : split, jstep = p.splits == 1 ? 1 : p.splits;
+        for (int jb = j0; jb < m_valid; jb += 8 * jstep) {
+          T tmp[8];
+_Pragma("unroll")
+          for (int t = 0; t < 8; ++t) { const int j = jb + t * jstep; if (j < m_valid) tmp[t] = cx.resp[(int64_t)(m0 + j) * cx.ld_res]; }
+_Pragma("unroll")
+          for (int t = 0; t < 8; ++t) { const int j = jb + t * jstep; if (j < m_valid) res_s[j * BLOCK_N + n_local] = tmp[t]; }
+        }
+        cx.res_s = res_s;
+      }
+      if (p.epi_mode == EPI_LORA16) {
+        const int e = threadIdx.x - 64;          // 128 epilogue threads, one 16-byte chunk each per round
+        for (int i = e; i < m_valid * 2; i += 128)
+          *reinterpret_cast<uint4*>(lt_s + i * 8) = *reinterpret_cast<const uint4*>(cx.lora_t + (int64_t)m0 * 16 + i * 8);
+        cx.lt_s = lt_s;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+    }
     mbar_wait(tmem_full_bar, 0, 3);
     tc_fence_after();
+    if (threadIdx.x == 64) trace_stamp(p.trace, 5);
     if (p.splits == 1) {
-      for (int c = 0; c < m_valid; c += 16) {
-        uint32_t r[16], ru[16];
-        tc_ld16(taddr + c, r);
-        if (SWIGLU) tc_ld16(taddr + NT + c, ru);
-        tc_wait_ld();
-        if (n < p.N) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m0 + c + j;
-            if (m < p.M)
-              out[(int64_t)m * p.ldo + n] = epilogue_elem<T>(p.epi, __uint_as_float(r[j]), SWIGLU ? __uint_as_float(ru[j]) : 0.f, m, n);
+      EPI_DISPATCH(p.epi_mode,
+        for (int c = 0; c < m_valid; c += 16) {
+          uint32_t r[16], ru[16];
+          tc_ld16(taddr + c, r);
+          if (SWIGLU) tc_ld16(taddr + NT + c, ru);
+          tc_wait_ld();
+          if (n < p.N) {
+_Pragma("unroll")
+            for (int j = 0; j < 16; ++j)
+              if (c + j < m_valid)
+                finish_store<T, SWIGLU, MODE>(p.epi, cx, __uint_as_float(r[j]), SWIGLU ? __uint_as_float(ru[j]) : 0.f, m0 + c + j, n, c + j);
           }
         }
-      }
+      )
     } else if (p.cluster) {
       // split-K inside a thread-block cluster: park the fp32 partial tile in this CTA's (now idle) pipeline smem;
       // after the cluster barrier every CTA reduces its own slice of the token columns over DSMEM.
       for (int c = 0; c < m_valid; c += 16) {
-#pragma unroll
+_Pragma("unroll")
         for (int a = 0; a < Cfg::ACCS; ++a) {
           uint32_t r[16];
           tc_ld16(taddr + a * NT + c, r);
           tc_wait_ld();
-#pragma unroll
+_Pragma("unroll")
           for (int j = 0; j < 16; ++j)
             if (c + j < m_valid) red[(a * NT + c + j) * BLOCK_N + n_local] = __uint_as_float(r[j]);
         }
@@ -283,12 +406,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       // splits in fixed order
       float* part = p.ws_part + ((int64_t)split * tiles + tile_id) * (Cfg::ACCS * NT * BLOCK_N);
       for (int c = 0; c < m_valid; c += 16) {
-#pragma unroll
+_Pragma("unroll")
         for (int a = 0; a < Cfg::ACCS; ++a) {
           uint32_t r[16];
           tc_ld16(taddr + a * NT + c, r);
           tc_wait_ld();
-#pragma unroll
+_Pragma("unroll")
           for (int j = 0; j < 16; ++j)
             if (c + j < m_valid) __stcg(part + ((int64_t)a * NT + c + j) * BLOCK_N + n_local, __uint_as_float(r[j]));
         }
@@ -304,57 +427,73 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       if (*flag_smem) {
         __threadfence();
         if (n < p.N) {
-          for (int c = 0; c < m_valid; c += 8) {
-            float acc[8], accu[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { acc[j] = 0.f; accu[j] = 0.f; }
-            for (int s = 0; s < p.splits; ++s) {       // 8 (16) independent loads in flight per split
-              const float* ps = p.ws_part + ((int64_t)s * tiles + tile_id) * (Cfg::ACCS * NT * BLOCK_N);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (c + j < m_valid) {
-                  acc[j] += __ldcg(ps + (int64_t)(c + j) * BLOCK_N + n_local);
-                  if (SWIGLU) accu[j] += __ldcg(ps + ((int64_t)NT + c + j) * BLOCK_N + n_local);
+          EPI_DISPATCH(p.epi_mode,
+            for (int c = 0; c < m_valid; c += 8) {
+              float acc[8], accu[8];
+_Pragma("unroll")
+              for (int j = 0; j < 8; ++j) { acc[j] = 0.f; accu[j] = 0.f; }
+              for (int s = 0; s < p.splits; ++s) {       // 8 (16) independent loads in flight per split
+                const float* ps = p.ws_part + ((int64_t)s * tiles + tile_id) * (Cfg::ACCS * NT * BLOCK_N);
+_Pragma("unroll")
+                for (int j = 0; j < 8; ++j) {
+                  if (c + j < m_valid) {
+                    acc[j] += __ldcg(ps + (int64_t)(c + j) * BLOCK_N + n_local);
+                    if (SWIGLU) accu[j] += __ldcg(ps + ((int64_t)NT + c + j) * BLOCK_N + n_local);
+                  }
                 }
               }
+_Pragma("unroll")
+              for (int j = 0; j < 8; ++j)
+                if (c + j < m_valid) finish_store<T, SWIGLU, MODE>(p.epi, cx, acc[j], accu[j], m0 + c + j, n, c + j);
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int m = m0 + c + j;
-              if (c + j < m_valid) out[(int64_t)m * p.ldo + n] = epilogue_elem<T>(p.epi, acc[j], accu[j], m, n);
-            }
-          }
+          )
         }
       }
     }
     tc_fence_before();
+    if (threadIdx.x == 64) trace_stamp(p.trace, 11);
   }
   if (p.cluster) {
     // every thread of every CTA in the cluster: partial tiles are complete and visible cluster-wide
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x == 64) trace_stamp(p.trace, 6);
     if (warp >= 2 && n < p.N) {
       const uint32_t red_addr = smem_u32(red);
-      for (int j = split; j < m_valid; j += p.splits) {       // this CTA's slice of the token columns
-        float v[8], vu[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          v[s] = 0.f; vu[s] = 0.f;
-          if (s < p.splits) {
-            v[s] = ld_dsmem_f32(red_addr + (uint32_t)((j * BLOCK_N + n_local) * 4), (uint32_t)s);
-            if (SWIGLU) vu[s] = ld_dsmem_f32(red_addr + (uint32_t)(((NT + j) * BLOCK_N + n_local) * 4), (uint32_t)s);
+      // this CTA's slice of the token columns: j = split, split + splits, ...; four columns per round so that their
+      // partials (<= 32 DSMEM loads, 64 with SwiGLU) are in flight together; summed in fixed split order.
+      EPI_DISPATCH(p.epi_mode,
+        for (int jb = split; jb < m_valid; jb += 4 * p.splits) {
+          float v[4][8], vu[4][8];
+_Pragma("unroll")
+          for (int t = 0; t < 4; ++t) {
+            const int j = jb + t * p.splits;
+_Pragma("unroll")
+            for (int s = 0; s < 8; ++s) {
+              v[t][s] = 0.f; vu[t][s] = 0.f;
+              if (j < m_valid && s < p.splits) {
+                v[t][s] = ld_dsmem_f32(red_addr + (uint32_t)((j * BLOCK_N + n_local) * 4), (uint32_t)s);
+                if (SWIGLU) vu[t][s] = ld_dsmem_f32(red_addr + (uint32_t)(((NT + j) * BLOCK_N + n_local) * 4), (uint32_t)s);
+              }
+            }
+          }
+_Pragma("unroll")
+          for (int t = 0; t < 4; ++t) {
+            const int j = jb + t * p.splits;
+            if (j < m_valid) {
+              float acc = 0.f, accu = 0.f;
+_Pragma("unroll")
+              for (int s = 0; s < 8; ++s) { acc += v[t][s]; accu += vu[t][s]; }
+              finish_store<T, SWIGLU, MODE>(p.epi, cx, acc, accu, m0 + j, n, j);
+            }
           }
         }
-        float acc = 0.f, accu = 0.f;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) { acc += v[s]; accu += vu[s]; }      // fixed split order: deterministic
-        const int m = m0 + j;
-        out[(int64_t)m * p.ldo + n] = epilogue_elem<T>(p.epi, acc, accu, m, n);
-      }
+      )
     }
     // nobody leaves (and frees its smem) while a peer may still be reading it
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
   __syncthreads();
+  if (threadIdx.x == 64) trace_stamp(p.trace, 7);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
@@ -395,23 +534,33 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int
 
 int pick_nt(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256; }
 
-// Max CTAs of this kernel that can be co-resident when launched as clusters of (1,1,cs) (cs = 1: plain launch).
+// Max CTAs of the decode-tile kernel that are co-resident when launched as clusters of (1,1,cs).  Measured on B200
+// (ncu launch__cluster_max_active with two ~110 KB CTAs per SM: 71 clusters of 4 = 284 CTAs; timing sweeps agree:
+// 258 CTAs in clusters of 3 run as one wave, 288 do not).  cudaOccupancyMaxActiveClusters under-reports here (it
+// answers as if one CTA fitted per SM), so the measured figure is used; RD_DEBUG_OCC=1 prints both.
 template <class T, int NT, bool SWIGLU>
 int resident_capacity(int cs) {
   using Cfg = TcCfg<NT, SWIGLU>;
   static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (cs < 1 || cs > 8) return 1;
   if (cache[cs]) return cache[cs];
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(1, 1, cs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)cs;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, linear_tc_kernel<T, NT, SWIGLU>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 148 / cs; }
-  cache[cs] = n * cs;
-  return cache[cs];
+  const int per_sm = (227 * 1024) / (Cfg::SMEM_BYTES + 1024);
+  const int model = per_sm >= 2 ? (284 / cs) * cs : (148 / cs) * cs;
+  if (getenv("RD_DEBUG_OCC")) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148, 1, cs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)cs;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t oe = cudaOccupancyMaxActiveClusters(&n, linear_tc_kernel<T, NT, SWIGLU>, &cfg);
+    cudaGetLastError();
+    fprintf(stderr, "radialog_b200: NT=%d swiglu=%d cluster %d: occupancy API %d clusters (%s), model %d CTAs\n", NT, (int)SWIGLU, cs, n,
+            cudaGetErrorString(oe), model);
+  }
+  cache[cs] = model;
+  return model;
 }
 
 // Split-K factor for few-tile (decode) GEMMs.  The kernel is HBM-bound, so what matters is that (a) every CTA of the
@@ -421,7 +570,7 @@ int resident_capacity(int cs) {
 template <class T, int NT, bool SWIGLU>
 int choose_splits(int tiles, int kb) {
   if (NT > 64) return 1;                          // wide token tiles (prefill / conv): tensor-bound, many tiles
-  const int want = 185;                           // ~1.25 x 148 SMs
+  const int want = 240;                           // ~1.6 CTAs per SM: measured sweet spot of the split sweep (profiles/)
   const int smax = kb / 4 > 0 ? (kb / 4 > 8 ? 8 : kb / 4) : 1;   // >= 4 k-blocks per CTA, portable cluster size <= 8
   int best = 1, best_ctas = tiles;
   for (int s = 1; s <= smax; ++s) {
@@ -454,6 +603,15 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
   if (splits > 1 && ws == nullptr && g_splitk_mode != 0) splits = 1;
   TcParams p{};
   p.M = M; p.N = N; p.K = K; p.ldo = ldo; p.splits = splits; p.epi = epi;
+  p.trace = rd_linear_trace_buffer();
+  {
+    const bool simple = epi.bias == nullptr && (epi.act == RD_ACT_NONE || (SWIGLU && epi.act == RD_ACT_SWIGLU));
+    p.epi_mode = EPI_GENERIC;
+    if (simple && epi.residual == nullptr && epi.lora_r == 0) p.epi_mode = EPI_PLAIN;
+    else if (!SWIGLU && simple && epi.residual != nullptr && epi.res_mode == 1 && epi.lora_r == 0) p.epi_mode = EPI_RES1;
+    else if (!SWIGLU && simple && epi.residual == nullptr && epi.lora_r == 16) p.epi_mode = EPI_LORA16;
+    if (g_force_generic_epilogue) p.epi_mode = EPI_GENERIC;
+  }
   // decode: every weight byte is read once (evict-first), the small activation tile is shared by all CTAs (evict-last)
   p.hint_w = m_tiles == 1 ? HINT_EVICT_FIRST : HINT_EVICT_NORMAL;
   p.hint_x = m_tiles == 1 ? HINT_EVICT_LAST : HINT_EVICT_NORMAL;
@@ -502,6 +660,15 @@ int dispatch_nt(int nt, const void* x, int64_t ldx, const void* w, int64_t ldw, 
 
 }  // namespace
 
+// development aid: per-CTA globaltimer stamps; with a non-zero stride every launch gets its own slab of the buffer
+static unsigned long long* g_trace = nullptr;
+static long long g_trace_stride = 0, g_trace_launch = 0;
+extern "C" int rd_linear_set_trace(void* buf) { g_trace = (unsigned long long*)buf; g_trace_stride = 0; g_trace_launch = 0; return RD_OK; }
+extern "C" int rd_linear_set_trace_strided(void* buf, long long stride_u64) {
+  g_trace = (unsigned long long*)buf; g_trace_stride = stride_u64; g_trace_launch = 0; return RD_OK;
+}
+extern "C" long long rd_linear_trace_launches() { return g_trace_launch; }
+unsigned long long* rd_linear_trace_buffer() { return g_trace ? g_trace + (g_trace_launch++) * g_trace_stride : nullptr; }
 static int g_force_splits = 0;   // test hook: 0 = heuristic
 extern "C" int rd_linear_force_splits(int s) { g_force_splits = s; return RD_OK; }
 

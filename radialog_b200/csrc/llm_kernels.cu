@@ -44,13 +44,26 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
   }
   if (lora_a == nullptr) return;
   __syncthreads();
-  for (int r = warp; r < lora_rows; r += 8) {                  // lora_A: Linear(H -> r), fp32 accumulate
+  // lora_A: Linear(H -> rows), fp32 accumulate.  The A rows are L2 resident; all chunks of a row are requested
+  // before the first is consumed (the loop used to run at one L2 round trip per 256 elements).
+  for (int r = warp; r < lora_rows; r += 8) {
     const T* ar = lora_a + (int64_t)r * H;
     float acc = 0.f;
-    for (int k = lane * 8; k < H; k += 32 * 8) {
-      Vec8<T> av = ld16(ar + k);
+    for (int k0 = lane * 8; k0 < H; k0 += 32 * 8 * 8) {
+      Vec8<T> av[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc = fmaf(Tr<T>::f(av.v[e]), srow[k + e], acc);
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * 256;
+        if (k < H) av[u] = ld16(ar + k);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * 256;
+        if (k < H) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc = fmaf(Tr<T>::f(av[u].v[e]), srow[k + e], acc);
+        }
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) lora_t[(int64_t)m * lora_rows + r] = Tr<T>::r(acc);
@@ -132,11 +145,12 @@ extern "C" int rd_rope_kv_store(void* qkv, const int32_t* pos, const int32_t* ct
 // ------------------------------------------------------------------------------------------------
 constexpr int ATT_THREADS = 128;
 constexpr int ATT_GROUPS = ATT_THREADS / 16;
+constexpr int ATT_U = 3;
 
 // FUSED (decode, q_len == 1): the CTA first applies RoPE to its head's q and k, appends k,v to the cache at slot ctx
 // and keeps the three 128-vectors in shared memory, so the single-token step needs no separate rope/append launch.
 template <class T, bool FUSED>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 7)
 attention_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ kc, T* __restrict__ vc,
                  const uint8_t* __restrict__ keymask, const int32_t* __restrict__ ctx_len_p, T* __restrict__ out,
                  int q_len, int nh, int cmax, const int32_t* __restrict__ pos, const T* __restrict__ cos_t,
@@ -157,9 +171,12 @@ attention_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ kc, T* 
   const uint8_t* km = keymask + (int64_t)b * cmax;
   const float lowest = Tr<T>::lowest();
 
-  int any = 0;
-  for (int j = tid; j <= jcausal; j += ATT_THREADS) any |= km[j];
-  any = __syncthreads_or(any);
+  int any = 1;                                  // decode: the token just selected always attends to itself
+  if (!FUSED) {
+    any = 0;
+    for (int j = tid; j <= jcausal; j += ATT_THREADS) any |= km[j];
+    any = __syncthreads_or(any);
+  }
   // rows with at least one visible key: masked keys past the causal limit contribute exp(min - max) == 0 exactly,
   // so they are skipped.  All-masked (left-pad) rows are evaluated literally over every key like the reference.
   const int jend = any ? (jcausal + 1) : c_tot;
@@ -212,32 +229,59 @@ attention_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ kc, T* 
   };
   const float sqrt_d = 11.313708498984761f;  // math.sqrt(128)
   const unsigned hmask = 0xFFFFu << (lane & 16);
-  for (int j0 = g; j0 < jend; j0 += ATT_GROUPS * 2) {
-    const int j1 = j0 + ATT_GROUPS;
-    Vec8<T> k0 = load_kv(kbase, s_k, j0);
-    Vec8<T> k1 = (j1 < jend) ? load_kv(kbase, s_k, j1) : k0;
-    float d0 = 0.f, d1 = 0.f;
+  // The KV sweep is latency bound (a few keys per 16-lane group): software-pipelined, ATT_U keys per group and
+  // iteration with the next batch's 128-bit loads already in flight while the current batch is reduced.
+  constexpr int STEP = ATT_GROUPS * ATT_U;
+  auto load_batch = [&](const T* base, const float* fresh, int jb, Vec8<T>(&dst)[ATT_U]) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { d0 = fmaf(q[e], Tr<T>::f(k0.v[e]), d0); d1 = fmaf(q[e], Tr<T>::f(k1.v[e]), d1); }
+    for (int u = 0; u < ATT_U; ++u) {
+      const int j = jb + u * ATT_GROUPS;
+      if (j < jend) dst[u] = load_kv(base, fresh, j);
+    }
+  };
+  {
+    Vec8<T> cur[ATT_U];
+    if (g < jend) load_batch(kbase, s_k, g, cur);
+    for (int jb = g; jb < jend; jb += STEP) {
+      Vec8<T> nxt[ATT_U];
+      if (jb + STEP < jend) load_batch(kbase, s_k, jb + STEP, nxt);
+      float d[ATT_U];
 #pragma unroll
-    // the two 16-lane key groups of a warp may run different trip counts: shuffle within the half-warp only
-    for (int o = 8; o > 0; o >>= 1) { d0 += __shfl_xor_sync(hmask, d0, o); d1 += __shfl_xor_sync(hmask, d1, o); }
-    if (l16 == 0) {
+      for (int u = 0; u < ATT_U; ++u) {
+        d[u] = 0.f;
+        if (jb + u * ATT_GROUPS < jend) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int j = t ? j1 : j0;
-        if (j < jend) {
-          float s = Tr<T>::rr(t ? d1 : d0);                      // matmul output in the storage dtype
-          s = Tr<T>::rr(s / sqrt_d);                             // / math.sqrt(head_dim)
-          float madd = km[j] ? 0.f : lowest;                     // _expand_mask
-          if (q_len > 1 && j > jcausal) madd = Tr<T>::rr(madd + lowest);   // + _make_causal_mask (may be -inf)
-          s = Tr<T>::rr(s + madd);
-          s = fmaxf(s, lowest);                                  // torch.max(attn_weights, finfo.min)
-          sc[j] = s;
+          for (int e = 0; e < 8; ++e) d[u] = fmaf(q[e], Tr<T>::f(cur[u].v[e]), d[u]);
         }
       }
+      // the two 16-lane key groups of a warp may run different trip counts: shuffle within the half-warp only
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < ATT_U; ++u) d[u] += __shfl_xor_sync(hmask, d[u], o);
+      }
+      if (l16 == 0) {
+#pragma unroll
+        for (int u = 0; u < ATT_U; ++u) {
+          const int j = jb + u * ATT_GROUPS;
+          if (j < jend) {
+            float s = Tr<T>::rr(d[u]);                             // matmul output in the storage dtype
+            s = Tr<T>::rr(s / sqrt_d);                             // / math.sqrt(head_dim)
+            float madd = km[j] ? 0.f : lowest;                     // _expand_mask
+            if (q_len > 1 && j > jcausal) madd = Tr<T>::rr(madd + lowest);   // + _make_causal_mask (may be -inf)
+            s = Tr<T>::rr(s + madd);
+            s = fmaxf(s, lowest);                                  // torch.max(attn_weights, finfo.min)
+            sc[j] = s;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < ATT_U; ++u) cur[u] = nxt[u];
     }
   }
+  // first batch of V rows is requested before the softmax so its latency hides behind the reductions
+  Vec8<T> vcur[ATT_U];
+  if (g < jend) load_batch(vbase, s_v, g, vcur);
   __syncthreads();
   float mx = -INFINITY;
   for (int j = tid; j < jend; j += ATT_THREADS) mx = fmaxf(mx, sc[j]);
@@ -256,14 +300,20 @@ attention_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ kc, T* 
   __syncthreads();
 
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int j0 = g; j0 < jend; j0 += ATT_GROUPS * 2) {
-    const int j1 = j0 + ATT_GROUPS;
-    const bool has1 = j1 < jend;
-    Vec8<T> v0 = load_kv(vbase, s_v, j0);
-    Vec8<T> v1 = has1 ? load_kv(vbase, s_v, j1) : v0;
-    const float p0 = sc[j0], p1 = has1 ? sc[j1] : 0.f;
+  for (int jb = g; jb < jend; jb += STEP) {
+    Vec8<T> vnxt[ATT_U];
+    if (jb + STEP < jend) load_batch(vbase, s_v, jb + STEP, vnxt);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { acc[e] = fmaf(p0, Tr<T>::f(v0.v[e]), acc[e]); acc[e] = fmaf(p1, Tr<T>::f(v1.v[e]), acc[e]); }
+    for (int u = 0; u < ATT_U; ++u) {
+      const int j = jb + u * ATT_GROUPS;
+      if (j < jend) {
+        const float pj = sc[j];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, Tr<T>::f(vcur[u].v[e]), acc[e]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ATT_U; ++u) vcur[u] = vnxt[u];
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) spart[g][l16 * 8 + e] = acc[e];

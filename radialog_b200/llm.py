@@ -408,7 +408,7 @@ class LlamaForCausalLM:
         ev1.record()
         gen_p, fin_p, logits_p, _, _ = self._state()
         Cmax, V = self._cap[1], self.cfg.vocab_size
-        vpad = (V + 7) // 8 * 8
+        vpad = (V + 63) // 64 * 64
         gen_t = self._wrap(gen_p, (self._cap[0], Cmax), torch.int64)
         fin_t = self._wrap(fin_p, (self._cap[0],), torch.int32)
         logits_t = self._wrap(logits_p, (self._cap[0], vpad), self.dtype)

@@ -168,5 +168,7 @@ def test_vicuna_decode_shapes_tc_vs_gemv_vs_simt(lib, cuda_dev):
         eps = 2.0 ** -10
         for name, a, b in (("tc-simt", tc, simt), ("gemv-simt", gemv, simt[:4])):
             assert torch.isfinite(a.float()).all() and torch.isfinite(b.float()).all(), f"{name} N={N} K={K}: unwritten output"
-            err = (a.float() - b.float()).abs() / b.float().abs().clamp_min(1e-2)
+            # SwiGLU multiplies two rounded values: an ulp of the larger factor can dominate a small product
+            floor = 5e-2 if act else 1e-2
+            err = (a.float() - b.float()).abs() / b.float().abs().clamp_min(floor)
             assert err.max().item() <= 4 * eps, f"{name} N={N} K={K}: {err.max().item():.3e}"
