@@ -328,7 +328,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU")
     ap.add_argument("--new-tokens", type=int, default=128)
     ap.add_argument("--dtype", default="bfloat16", choices=["float16", "bfloat16"])
-    ap.add_argument("--pdl", type=int, default=0)
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch between the kernels of a step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-b1", action="store_true", help="skip the batch-1 latency leg")
     args = ap.parse_args()

@@ -67,8 +67,8 @@ typedef struct rd_epilogue {
 /* out[M,N] = epilogue(x[M,K] . W[N,K]^T); row-major, leading dimensions in elements (multiples of 8).
  * Replaces every nn.Linear / 1x1 conv on the path (q/k/v/o/gate/up/down/lm_head: modeling_llama_imgemb.py:153-159,
  * 178-181,680; Q-Former denses: Qformer.py:128-130,282,352,367; img_proj_layer: test.py:295).
- * `algo`: 0 auto (M<=4 -> streaming GEMV; otherwise tcgen05 tensor-core tiles), 1 force GEMV (M<=4), 2 force
- * tcgen05, 3 SIMT validation kernel.  `ws_dev` is split-K workspace (may be NULL when algo picks no split;
+ * `algo`: 0 auto (= tcgen05 tensor-core tiles at every M), 1 streaming CUDA-core GEMV (M<=4), 2 tcgen05,
+ * 3 SIMT validation kernel.  `ws_dev` is split-K workspace (may be NULL when algo picks no split;
  * size from rd_linear_workspace_bytes).                                                                        */
 int rd_linear(const void* x_dev, int64_t ldx, const void* w_dev, int64_t ldw, void* out_dev, int64_t ldo,
               int M, int N, int K, const rd_epilogue* epi, int dtype, int algo, void* ws_dev, int64_t ws_bytes,
@@ -95,12 +95,15 @@ int rd_rmsnorm(const void* x_dev, const void* w_dev, void* out_dev, int M, int H
 int rd_layernorm(const void* x_dev, const float* gamma_dev, const float* beta_dev, void* out_dev, int M, int H,
                  float eps, int dtype, void* stream);
 
-/* apply_rotary_pos_emb (modeling_llama_imgemb.py:135-142) on q,k of qkv[M,3H] + KV-cache append (replaces the
- * torch.cat at :209-212).  Token m = b*q_len+i goes to cache slot ctx_len[0]+i.  q is rotated in place.
- * cos/sin: [max_pos, hd] storage dtype (tables of :97-109 cast as in :123-124).  Caches: [B, nh, cmax, hd].    */
-int rd_rope_kv_store(void* qkv_dev, const int32_t* pos_dev, const int32_t* ctx_len_dev, const void* cos_dev,
+/* apply_rotary_pos_emb (modeling_llama_imgemb.py:135-142) on q,k of the qkv buffer [M, ldq] + KV-cache append (replaces
+ * the torch.cat at :209-212).  Token m = b*q_len+i goes to cache slot ctx_len[0]+i.  q is rotated in place.
+ * cos/sin: [max_pos, hd] storage dtype (tables of :97-109 cast as in :123-124).  Caches: [B, nh, cmax, hd].
+ * peft LoRA (unmerged, finetune.py:167-173): if lora_b_dev != NULL the row also holds t = T(lora_A . x) in columns
+ * [3H, 3H+2r) (q's r values, then v's; produced by the QKV GEMM whose weight carries the lora_A rows) and
+ * q,v <- T( T(Wx) + T(lora_scale * T(lora_B . t)) ) before the rotation / append; lora_b_dev is [2H, r] (q rows, v rows). */
+int rd_rope_kv_store(void* qkv_dev, int64_t ldq, const int32_t* pos_dev, const int32_t* ctx_len_dev, const void* cos_dev,
                      const void* sin_dev, void* kcache_dev, void* vcache_dev, int B, int q_len, int nh, int hd,
-                     int cmax, int dtype, void* stream);
+                     int cmax, const void* lora_b_dev, int lora_r, float lora_scale, int dtype, void* stream);
 
 /* LlamaAttention core (modeling_llama_imgemb.py:216-234) for q_len new tokens per row against the cache:
  * fp16 scores, /sqrt(hd), + causal/padding mask, clamp to finfo.min, fp32 softmax rounded to the storage dtype,
@@ -110,10 +113,13 @@ int rd_attention(const void* qkv_dev, int64_t ldq, const void* kcache_dev, const
                  int hd, int cmax, int dtype, void* stream);
 
 /* Single-token decode: rd_rope_kv_store + rd_attention (q_len == 1) fused in one launch; pos_dev[B] are the position
- * ids of the new tokens, which are appended at cache slot ctx_len[0].                                            */
+ * ids of the new tokens, which are appended at cache slot ctx_len[0].  The KV sweep uses bulk asynchronous copies
+ * (cp.async.bulk + mbarrier) through a shared-memory ring.  ctx_lower_bound: host-known lower bound of ctx_len[0]
+ * (0 if unknown) — cache rows below it are requested before the programmatic-launch wait.  LoRA arguments as above. */
 int rd_attention_decode(const void* qkv_dev, int64_t ldq, const int32_t* pos_dev, const void* cos_dev, const void* sin_dev,
                         void* kcache_dev, void* vcache_dev, const uint8_t* keymask_dev, const int32_t* ctx_len_dev,
-                        void* out_dev, int B, int nh, int hd, int cmax, int dtype, void* stream);
+                        void* out_dev, int B, int nh, int hd, int cmax, int ctx_lower_bound, const void* lora_b_dev,
+                        int lora_r, float lora_scale, int dtype, void* stream);
 
 /* LlamaModel.forward splice (modeling_llama_imgemb.py:571-594, split_at_img :498-520): out[b,t,:] = img[b,t-p,:]
  * for t in [p,p+32) where p = first index of 32000 in row b (0 if none), else embed[ids[b,t]].  img may be NULL
@@ -145,14 +151,14 @@ typedef struct rd_llm_config {
 #define RD_W_IMG_PROJ_B 4  /* [H] fp32                        model.img_proj_layer.bias            */
 #define RD_W_ROPE_COS 5    /* [max_pos, hd]                                                        */
 #define RD_W_ROPE_SIN 6
-#define RD_W_QKV 10        /* [3H, H]  q_proj|k_proj|v_proj rows                                   */
+#define RD_W_QKV 10        /* [3H (+2r), H]  q_proj|k_proj|v_proj rows, then q lora_A and v lora_A rows when an adapter is loaded */
 #define RD_W_O 11          /* [H, H]                                                               */
 #define RD_W_GATE_UP 12    /* [2I, H]  gate_proj rows then up_proj rows                            */
 #define RD_W_DOWN 13       /* [H, I]                                                               */
 #define RD_W_LN1 14        /* [H] input_layernorm                                                  */
 #define RD_W_LN2 15        /* [H] post_attention_layernorm                                         */
-#define RD_W_LORA_A 16     /* [2r, H]  q lora_A rows then v lora_A rows                            */
-#define RD_W_LORA_B 17     /* [3H, 2r] block matrix: q rows use cols [0,r), v rows cols [r,2r)     */
+#define RD_W_LORA_A 16     /* unused by the engine (lora_A rides in RD_W_QKV); kept for ABI stability  */
+#define RD_W_LORA_B 17     /* [2H, r]  q lora_B rows then v lora_B rows                            */
 
 int rd_llm_create(const rd_llm_config* cfg, rd_llm** out);
 void rd_llm_destroy(rd_llm* h);

@@ -57,9 +57,9 @@ SIGNATURES = {
     "rd_linear_splitk_mode": (_i, [_i]),
     "rd_rmsnorm": (_i, [_p, _p, _p, _i, _i, _f, _p, _i, _p, _i, _p]),
     "rd_layernorm": (_i, [_p, _p, _p, _p, _i, _i, _f, _i, _p]),
-    "rd_rope_kv_store": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "rd_rope_kv_store": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _i, _p]),
     "rd_attention": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
-    "rd_attention_decode": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "rd_attention_decode": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _i, _p]),
     "rd_embed_splice": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "rd_llm_create": (_i, [C.POINTER(LlmConfig), C.POINTER(_p)]),
     "rd_llm_destroy": (None, [_p]),

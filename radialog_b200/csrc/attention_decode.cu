@@ -1,0 +1,286 @@
+// Single-token decode attention over the flat KV cache (q_len == 1), fused with RoPE and the KV append.
+// Replaces LlamaAttention.forward's cache torch.cat + two bmm + softmax (modeling_llama_imgemb.py:205-234) for the
+// decode step; rounding points as in llm_kernels.cu / SURVEY.md Appendix B.
+//
+// The K rows (and the V rows) of one (sequence, head) are one contiguous [ctx, 128] block of the cache, so the sweep is
+// done with bulk asynchronous copies (cp.async.bulk, the 1-D TMA path) through a ring of 32-key shared-memory buffers
+// with mbarrier completion instead of per-lane global loads: one elected thread keeps RING copies in flight, the rest of
+// the CTA computes from shared memory.  The first RING K chunks only cover cache rows written by EARLIER decode steps,
+// so they are requested before griddepcontrol.wait and stream in while the QKV GEMM of this layer is still finishing.
+// (Safety of that early read: programmatic launch depth is bounded to a few kernels by SM residency — every GEMM CTA
+// in between holds >100 KB of shared memory — while the writer of those rows is a whole decode step (>200 kernels)
+// back in the stream.  `prefetch_keys` is a host-known lower bound; chunks past the real context are read but ignored.)
+#include "common.cuh"
+
+bool rd_pdl_enabled();
+
+namespace {
+
+constexpr int HD = 128;
+constexpr int CH = 32;                     // keys per chunk: 32 x 256 B = 8 KB
+constexpr int CHUNK_BYTES = CH * HD * 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done, spins = 0;
+  long long t0 = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (!done && (++spins & 0x3FFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) { printf("attention_decode: mbarrier wait timed out (block %d,%d)\n", blockIdx.x, blockIdx.y); __trap(); }
+    }
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class T, int THREADS, int RING>
+__global__ void __launch_bounds__(THREADS)
+attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ kc, T* __restrict__ vc,
+                        const uint8_t* __restrict__ keymask, const int32_t* __restrict__ ctx_len_p, T* __restrict__ out, int nh,
+                        int cmax, const int32_t* __restrict__ pos, const T* __restrict__ cos_t, const T* __restrict__ sin_t,
+                        int prefetch_keys, const T* __restrict__ lora_b, int lora_r, float lora_scale) {
+  constexpr int GROUPS = THREADS / 16;
+  constexpr int WARPS = THREADS / 32;
+  extern __shared__ __align__(128) uint8_t smem[];
+  T* ring = reinterpret_cast<T*>(smem);                                   // [RING][CH][HD]
+  float* sc = reinterpret_cast<float*>(smem + RING * CHUNK_BYTES);        // [cmax + 1]
+  __shared__ __align__(8) uint64_t full_bar[RING];
+  __shared__ float s_q[HD], s_k[HD], s_v[HD];
+  __shared__ float sred[WARPS];
+  float (*spart)[HD] = reinterpret_cast<float (*)[HD]>(smem);            // reuses the ring once the sweep is over
+  static_assert(GROUPS * HD * 4 <= RING * CHUNK_BYTES, "spart must fit in the ring");
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = tid >> 4, l16 = tid & 15;
+  const T* kbase = kc + ((int64_t)b * nh + h) * cmax * HD;
+  const T* vbase = vc + ((int64_t)b * nh + h) * cmax * HD;
+
+  pdl_launch_dependents();
+  if (tid == 0) {
+    for (int i = 0; i < RING; ++i) mbar_init(&full_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // chunk sequence: K chunks 0..nK-1 then V chunks 0..nV-1; sequence entry s lives in ring slot s % RING
+  int n_pre = prefetch_keys / CH;
+  n_pre = n_pre > RING ? RING : n_pre;
+  if (tid == 0) {
+    for (int s = 0; s < n_pre; ++s) {            // cache rows of earlier steps: independent of the previous kernel
+      mbar_expect_tx(&full_bar[s], CHUNK_BYTES);
+      bulk_g2s(ring + (size_t)s * CH * HD, kbase + (size_t)s * CH * HD, CHUNK_BYTES, &full_bar[s]);
+    }
+  }
+  pdl_wait();
+
+  const int ctx = ctx_len_p[0];                  // cached keys; the new token goes to slot ctx
+  const int n_kv = (ctx + CH - 1) / CH;          // chunks that hold real keys
+  const int nK = n_kv > n_pre ? n_kv : n_pre;    // K entries of the sequence (prefetched-but-unused ones are skipped)
+  const int total = nK + n_kv;
+  int issued = n_pre;
+  auto issue = [&](int s) {                      // tid 0 only
+    const bool is_k = s < nK;
+    const int c = is_k ? s : s - nK;
+    int keys = ctx - c * CH;
+    keys = keys > CH ? CH : keys;
+    const int slot = s % RING;
+    const uint32_t bytes = (uint32_t)keys * HD * 2;
+    mbar_expect_tx(&full_bar[slot], bytes);
+    bulk_g2s(ring + (size_t)slot * CH * HD, (is_k ? kbase : vbase) + (size_t)c * CH * HD, bytes, &full_bar[slot]);
+  };
+  if (tid == 0) {
+    while (issued < total && issued < RING) { issue(issued); ++issued; }
+  }
+
+  // ---- RoPE of this head's q and k, KV append (modeling_llama_imgemb.py:135-142, 209-212) ----------------------------
+  {
+    constexpr int half = HD / 2;
+    const int H = nh * HD;
+    const T* row = qkv + (int64_t)b * ldq;
+    const int64_t slot_off = (((int64_t)b * nh + h) * cmax + ctx) * HD;
+    // peft LoRA (unmerged): the GEMM wrote t = T(lora_A . xn) after the 3H projection columns (q's r values, then v's)
+    auto lora = [&](float y, int n_row, const T* t) {
+      const T* brow = lora_b + (int64_t)n_row * lora_r;
+      float sdot = 0.f;
+      for (int i = 0; i < lora_r; ++i) sdot = fmaf(Tr<T>::f(brow[i]), Tr<T>::f(t[i]), sdot);
+      return Tr<T>::rr(y + Tr<T>::rr(lora_scale * Tr<T>::rr(sdot)));
+    };
+    if (tid < half) {
+      const int d = tid, p = pos[b];
+      const float c_lo = Tr<T>::f(cos_t[(int64_t)p * HD + d]), c_hi = Tr<T>::f(cos_t[(int64_t)p * HD + d + half]);
+      const float s_lo = Tr<T>::f(sin_t[(int64_t)p * HD + d]), s_hi = Tr<T>::f(sin_t[(int64_t)p * HD + d + half]);
+      float lo = Tr<T>::f(row[h * HD + d]), hi = Tr<T>::f(row[h * HD + d + half]);
+      if (lora_r > 0) { lo = lora(lo, h * HD + d, row + 3 * H); hi = lora(hi, h * HD + d + half, row + 3 * H); }
+      s_q[d] = Tr<T>::rr(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
+      s_q[d + half] = Tr<T>::rr(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
+      lo = Tr<T>::f(row[H + h * HD + d]); hi = Tr<T>::f(row[H + h * HD + d + half]);
+      const float k_lo = Tr<T>::rr(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
+      const float k_hi = Tr<T>::rr(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
+      s_k[d] = k_lo; s_k[d + half] = k_hi;
+      kc[slot_off + d] = Tr<T>::r(k_lo); kc[slot_off + d + half] = Tr<T>::r(k_hi);
+    } else if (tid < 2 * half) {
+      const int d = tid - half;
+      float v_lo = Tr<T>::f(row[2 * H + h * HD + d]), v_hi = Tr<T>::f(row[2 * H + h * HD + d + half]);
+      if (lora_r > 0) {
+        v_lo = lora(v_lo, H + h * HD + d, row + 3 * H + lora_r);
+        v_hi = lora(v_hi, H + h * HD + d + half, row + 3 * H + lora_r);
+      }
+      s_v[d] = v_lo; s_v[d + half] = v_hi;
+      vc[slot_off + d] = Tr<T>::r(v_lo); vc[slot_off + d + half] = Tr<T>::r(v_hi);
+    }
+  }
+  __syncthreads();
+  float q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q[e] = s_q[l16 * 8 + e];
+
+  const uint8_t* km = keymask + (int64_t)b * cmax;
+  const float lowest = Tr<T>::lowest();
+  const float sqrt_d = 11.313708498984761f;      // math.sqrt(128)
+  const unsigned hmask = 0xFFFFu << (lane & 16);
+  auto score_of = [&](float dot, int j) {          // modeling_llama_imgemb.py:216-230 (decode: padding mask only)
+    float s = Tr<T>::rr(dot);
+    s = Tr<T>::rr(s / sqrt_d);
+    s = Tr<T>::rr(s + (km[j] ? 0.f : lowest));
+    return fmaxf(s, lowest);
+  };
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+  for (int s = 0; s < total; ++s) {
+    const int slot = s % RING;
+    mbar_wait(&full_bar[slot], (uint32_t)(s / RING) & 1u);
+    const T* buf = ring + (size_t)slot * CH * HD;
+    if (s < nK) {
+      if (s < n_kv) {                              // ---- scores of this K chunk ----
+        int keys = ctx - s * CH;
+        keys = keys > CH ? CH : keys;
+        for (int jl = g; jl < CH; jl += GROUPS) {  // uniform trip count: the half-warp shuffles stay converged
+          float d = 0.f;
+          if (jl < keys) {
+            const Vec8<T> kk = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + l16 * 8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d = fmaf(q[e], Tr<T>::f(kk.v[e]), d);
+          }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
+          if (l16 == 0 && jl < keys) sc[s * CH + jl] = score_of(d, s * CH + jl);
+        }
+      }
+    } else {
+      const int c = s - nK;
+      if (c == 0) {                                // ---- first V chunk: finish the scores, softmax (fp32, rounded) ----
+        if (g == 0) {
+          float d = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d = fmaf(q[e], s_k[l16 * 8 + e], d);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
+          if (l16 == 0) sc[ctx] = score_of(d, ctx);
+        }
+        __syncthreads();
+        float mx = -INFINITY;
+        for (int j = tid; j <= ctx; j += THREADS) mx = fmaxf(mx, sc[j]);
+        mx = warp_max(mx);
+        if (lane == 0) sred[warp] = mx;
+        __syncthreads();
+        mx = sred[0];
+#pragma unroll
+        for (int w = 1; w < WARPS; ++w) mx = fmaxf(mx, sred[w]);
+        __syncthreads();
+        float sum = 0.f;
+        for (int j = tid; j <= ctx; j += THREADS) { const float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+        sum = warp_sum(sum);
+        if (lane == 0) sred[warp] = sum;
+        __syncthreads();
+        sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) sum += sred[w];
+        for (int j = tid; j <= ctx; j += THREADS) sc[j] = Tr<T>::rr(sc[j] / sum);     // softmax(fp32).to(dtype)
+        __syncthreads();
+      }
+      int keys = ctx - c * CH;
+      keys = keys > CH ? CH : keys;
+      for (int jl = g; jl < keys; jl += GROUPS) {  // ---- P.V of this V chunk ----
+        const Vec8<T> vv = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + l16 * 8);
+        const float pj = sc[c * CH + jl];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, Tr<T>::f(vv.v[e]), acc[e]);
+      }
+    }
+    __syncthreads();                               // everyone is done with this ring slot
+    if (tid == 0 && issued < total) { issue(issued); ++issued; }
+  }
+  if (n_kv == 0) {                                 // empty cache: the softmax over the single new key
+    if (g == 0) {
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(q[e], s_k[l16 * 8 + e], d);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
+      if (l16 == 0) sc[0] = Tr<T>::rr(1.0f);       // exp(s - s) / 1
+    }
+    __syncthreads();
+  }
+  if (g == 0) {                                    // the token just appended
+    const float pj = sc[ctx];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, s_v[l16 * 8 + e], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) spart[g][l16 * 8 + e] = acc[e];
+  __syncthreads();
+  if (tid < HD) {
+    float o = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < GROUPS; ++gg) o += spart[gg][tid];
+    out[(int64_t)b * (nh * HD) + h * HD + tid] = Tr<T>::r(o);
+  }
+}
+
+}  // namespace
+
+static int g_attn_prefetch = 1;      // test hook: 0 disables the pre-wait prefetch
+extern "C" int rd_attention_decode_set_prefetch(int on) { g_attn_prefetch = on; return RD_OK; }
+
+// Single-token decode: RoPE + KV append + attention in one launch (rd_rope_kv_store + rd_attention with q_len == 1).
+// ctx_lower_bound: a host-known lower bound of ctx_len[0] (0 if unknown); only used to size the early prefetch.
+extern "C" int rd_attention_decode(const void* qkv, int64_t ldq, const int32_t* pos, const void* cos_t, const void* sin_t,
+                                   void* kc, void* vc, const uint8_t* keymask, const int32_t* ctx_len, void* out, int B, int nh,
+                                   int hd, int cmax, int ctx_lower_bound, const void* lora_b, int lora_r, float lora_scale,
+                                   int dtype, void* stream) {
+  RD_REQUIRE(hd == 128, "rd_attention_decode: head_dim must be 128 (Vicuna-7B); got %d", hd);
+  RD_REQUIRE(B > 0 && nh > 0 && cmax > 0, "rd_attention_decode: bad shape");
+  const bool wide = (int64_t)B * nh <= 296;          // few (sequence, head) pairs: more threads per pair
+  const int ring = wide ? 4 : 3;                     // 128-thread CTAs: 7 resident per SM so that B=32 x 32 heads is one wave
+  const size_t smem = (size_t)ring * CHUNK_BYTES + ((size_t)(cmax + 1) * 4 + 127) / 128 * 128;
+  RD_REQUIRE(smem <= 200 * 1024, "rd_attention_decode: cmax %d too large", cmax);
+  const int pref = g_attn_prefetch ? (ctx_lower_bound < 0 ? 0 : ctx_lower_bound) : 0;
+  RD_DISPATCH_DTYPE(dtype, T, {
+    if (wide) {
+      RD_CHECK_CUDA(cudaFuncSetAttribute(attention_decode_kernel<T, 512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 512, 4>, dim3(nh, B), dim3(512), smem, (cudaStream_t)stream, rd_pdl_enabled(),
+                              (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
+                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale));
+    } else {
+      RD_CHECK_CUDA(cudaFuncSetAttribute(attention_decode_kernel<T, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 128, 3>, dim3(nh, B), dim3(128), smem, (cudaStream_t)stream, rd_pdl_enabled(),
+                              (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
+                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale));
+    }
+    return RD_OK;
+  });
+}

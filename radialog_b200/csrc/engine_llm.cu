@@ -6,7 +6,7 @@
 #include "common.cuh"
 
 extern "C" int rd_attention_decode(const void*, int64_t, const int32_t*, const void*, const void*, void*, void*, const uint8_t*,
-                                   const int32_t*, void*, int, int, int, int, int, void*);
+                                   const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
 extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const int32_t*, int, int, int, int, void*);
 extern "C" int rd_argmax_step(const void*, int64_t, int, int64_t*, int64_t*, int64_t, int32_t*, uint8_t*, int, int32_t*,
                               int32_t*, int32_t*, int32_t*, uint32_t*, int, int, int, int, int, int, void*);
@@ -74,7 +74,7 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
   const int64_t Mt = h->max_tokens;
   int r = RD_OK;
   auto A = [&](char** p, int64_t bytes) { if (r == RD_OK) r = dalloc(p, bytes); };
-  A(&h->x, Mt * H * e); A(&h->xn, Mt * H * e); A(&h->qkv, Mt * 3 * H * e); A(&h->att, Mt * H * e); A(&h->mid, Mt * I * e);
+  A(&h->x, Mt * H * e); A(&h->xn, Mt * H * e); A(&h->qkv, Mt * (3 * H + 2 * (cfg->lora_r > 0 ? cfg->lora_r : 0)) * e); A(&h->att, Mt * H * e); A(&h->mid, Mt * I * e);
   A(&h->xl, Bm * H * e); A(&h->logits, Bm * h->vpad * e); A(&h->img, Bm * 32 * H * e);
   A(&h->lora_t, Mt * 2 * (cfg->lora_r > 0 ? cfg->lora_r : 1) * e);
   h->kv_layer_bytes = Bm * C * H * e;
@@ -87,7 +87,7 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
   const int Ms[2] = {(int)Bm, 256};
   for (int mi = 0; mi < 2; ++mi) {
     int M = Ms[mi];
-    int64_t cand[5] = {rd_linear_tc_workspace_bytes(M, 3 * H, H), rd_linear_tc_workspace_bytes(M, H, H),
+    int64_t cand[5] = {rd_linear_tc_workspace_bytes(M, 3 * H + 64, H), rd_linear_tc_workspace_bytes(M, H, H),
                        rd_linear_tc_workspace_bytes(M, I, H), rd_linear_tc_workspace_bytes(M, H, I),
                        rd_linear_tc_workspace_bytes(M, cfg->vocab, H)};
     for (int i = 0; i < 5; ++i) ws = cand[i] > ws ? cand[i] : ws;
@@ -151,7 +151,7 @@ static int check_weights(rd_llm* h) {
   for (int l = 0; l < h->c.layers; ++l) {
     const LayerW& w = h->L[l];
     RD_REQUIRE(w.qkv && w.o && w.gate_up && w.down && w.ln1 && w.ln2, "rd_llm: weights of layer %d not set", l);
-    RD_REQUIRE(h->c.lora_r == 0 || (w.lora_a && w.lora_b), "rd_llm: LoRA weights of layer %d not set", l);
+    RD_REQUIRE(h->c.lora_r == 0 || w.lora_b, "rd_llm: LoRA weights of layer %d not set", l);
   }
   return RD_OK;
 }
@@ -190,19 +190,23 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     const LayerW& w = h->L[l];
     char* kc = h->kc + (int64_t)l * h->kv_layer_bytes;
     char* vc = h->vc + (int64_t)l * h->kv_layer_bytes;
+    // with an adapter, W_qkv carries the two lora_A blocks as 2r extra rows: the GEMM also yields t = T(lora_A . xn) in
+    // columns [3H, 3H+2r) of the qkv buffer; lora_B is applied where q and v are consumed (RoPE / attention kernels)
+    const int R2 = c.lora_r ? 2 * c.lora_r : 0;
+    const int64_t ldq = 3 * H + R2;
     { ProfScope ps(h, st, C_RMSNORM);
-      RD_CHECK(rd_rmsnorm(h->x, w.ln1, h->xn, M, H, c.rms_eps, c.lora_r ? w.lora_a : nullptr, 2 * c.lora_r, h->lora_t, dt, st)); }
-    rd_epilogue e{};
-    if (c.lora_r) { e.lora_t_dev = h->lora_t; e.lora_b_dev = w.lora_b; e.lora_r = 2 * c.lora_r; e.lora_scale = c.lora_scale; }
-    RD_CHECK(linear(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, 3 * H, M, 3 * H, H, &e, st));
+      RD_CHECK(rd_rmsnorm(h->x, w.ln1, h->xn, M, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
+    RD_CHECK(linear(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, st));
     if (q_len == 1) {      // decode: RoPE + KV append + attention fused in one launch
       ProfScope ps(h, st, C_ATTN);
-      RD_CHECK(rd_attention_decode(h->qkv, 3 * H, pos, h->cos, h->sin, kc, vc, h->keymask, h->ctx_len, h->att, B, nh, hd, c.max_ctx, dt, st));
+      RD_CHECK(rd_attention_decode(h->qkv, ldq, pos, h->cos, h->sin, kc, vc, h->keymask, h->ctx_len, h->att, B, nh, hd, c.max_ctx,
+                                   h->ctx_host, c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st));
     } else {
       { ProfScope ps(h, st, C_ROPE);
-        RD_CHECK(rd_rope_kv_store(h->qkv, pos, h->ctx_len, h->cos, h->sin, kc, vc, B, q_len, nh, hd, c.max_ctx, dt, st)); }
+        RD_CHECK(rd_rope_kv_store(h->qkv, ldq, pos, h->ctx_len, h->cos, h->sin, kc, vc, B, q_len, nh, hd, c.max_ctx,
+                                  c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st)); }
       { ProfScope ps(h, st, C_ATTN);
-        RD_CHECK(rd_attention(h->qkv, 3 * H, kc, vc, h->keymask, h->ctx_len, h->att, B, q_len, nh, hd, c.max_ctx, dt, st)); }
+        RD_CHECK(rd_attention(h->qkv, ldq, kc, vc, h->keymask, h->ctx_len, h->att, B, q_len, nh, hd, c.max_ctx, dt, st)); }
     }
     rd_epilogue eo{};
     eo.residual_dev = h->x; eo.ld_res = H; eo.res_mode = 1;

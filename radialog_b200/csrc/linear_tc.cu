@@ -143,7 +143,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int umma_m, int umma_
 // uniform datapath for every element, which measured ~250 ns per output element on the decode shapes; the hot
 // decode/prefill cases therefore get branch-free paths whose operands are hoisted into registers once per thread.
 // ------------------------------------------------------------------------------------------------
-enum { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_RES1 = 2, EPI_LORA16 = 3 };
+enum { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_RES1 = 2, EPI_LORA16 = 3, EPI_AFFINE = 4 };
 
 template <class T> struct EpiCtx {
   T* outp;              // out + n
@@ -153,13 +153,17 @@ template <class T> struct EpiCtx {
   const T* lora_t;      // [M,16]                  (EPI_LORA16)
   float lora_scale;
   float b[16];          // lora_B[n, 0..16)        (EPI_LORA16)
+  float bias_n;         // bias[n] (0 if none)      (EPI_AFFINE)
+  int act;              // RD_ACT_* held in a real register (EPI_AFFINE)
+  const T* res2p;       // residual + n for res_mode 2, or nullptr (EPI_AFFINE)
   const T* res_s;       // staged residual tile [NT][128] (nullptr = read global)
   const T* lt_s;        // staged lora_t tile [NT][16]    (nullptr = read global)
   int n_local;
 };
 
 template <class T, bool SWIGLU, int MODE>
-__device__ __forceinline__ void finish_store(const EpiParams& ep, const EpiCtx<T>& cx, float acc, float accu, int m, int n, int j) {
+__device__ __forceinline__ void finish_store(const EpiParams& ep, const EpiCtx<T>& cx, float acc, float accu, int m, int n, int j,
+                                             bool has_res = false, float res_pre = 0.f) {
   T y;
   if (MODE == EPI_PLAIN) {
     if (SWIGLU) {
@@ -169,7 +173,7 @@ __device__ __forceinline__ void finish_store(const EpiParams& ep, const EpiCtx<T
       y = Tr<T>::r(acc);
     }
   } else if (MODE == EPI_RES1) {
-    const float res = cx.res_s ? Tr<T>::f(cx.res_s[j * BLOCK_N + cx.n_local]) : Tr<T>::f(cx.resp[(int64_t)m * cx.ld_res]);
+    const float res = has_res ? res_pre : (cx.res_s ? Tr<T>::f(cx.res_s[j * BLOCK_N + cx.n_local]) : Tr<T>::f(cx.resp[(int64_t)m * cx.ld_res]));
     y = Tr<T>::r(res + Tr<T>::rr(acc));                                  // fp16 residual add after rounding Wx
   } else if (MODE == EPI_LORA16) {
     const T* trow = cx.lt_s ? cx.lt_s + j * 16 : cx.lora_t + (int64_t)m * 16;
@@ -180,6 +184,13 @@ __device__ __forceinline__ void finish_store(const EpiParams& ep, const EpiCtx<T
 #pragma unroll
     for (int r = 0; r < 8; ++r) sdot += Tr<T>::f(t1.v[r]) * cx.b[8 + r];
     y = Tr<T>::r(Tr<T>::rr(acc) + Tr<T>::rr(cx.lora_scale * Tr<T>::rr(sdot)));
+  } else if (MODE == EPI_AFFINE) {
+    // bias / ReLU / GELU / fp32 residual (convs, Q-Former, img_proj): operands live in registers, no parameter re-reads
+    float v = acc + cx.bias_n;
+    if (has_res) v += res_pre; else if (cx.res2p != nullptr) v += Tr<T>::f(cx.res2p[(int64_t)m * cx.ld_res]);
+    if (cx.act == RD_ACT_RELU) v = fmaxf(v, 0.0f);
+    else if (cx.act == RD_ACT_GELU) v = gelu_erf(v);
+    y = Tr<T>::r(v);
   } else {
     y = epilogue_elem<T>(ep, acc, accu, m, n, nullptr);
   }
@@ -191,6 +202,7 @@ __device__ __forceinline__ void finish_store(const EpiParams& ep, const EpiCtx<T
     case EPI_PLAIN: { constexpr int MODE = EPI_PLAIN; __VA_ARGS__ } break;     \
     case EPI_RES1: { constexpr int MODE = EPI_RES1; __VA_ARGS__ } break;       \
     case EPI_LORA16: { constexpr int MODE = EPI_LORA16; __VA_ARGS__ } break;   \
+    case EPI_AFFINE: { constexpr int MODE = EPI_AFFINE; __VA_ARGS__ } break;   \
     default: { constexpr int MODE = EPI_GENERIC; __VA_ARGS__ } break;          \
   }
 
@@ -339,6 +351,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     cx.outp = out + n; cx.ldo = p.ldo;
     cx.resp = reinterpret_cast<const T*>(p.epi.residual) + n; cx.ld_res = p.epi.ld_res;
     cx.lora_t = reinterpret_cast<const T*>(p.epi.lora_t); cx.lora_scale = p.epi.lora_scale;
+    cx.bias_n = 0.f; cx.act = RD_ACT_NONE; cx.res2p = nullptr;
+    if (p.epi_mode == EPI_AFFINE) {
+      if (p.epi.bias != nullptr && n < p.N) cx.bias_n = p.epi.bias[n];
+      // park act / residual pointer in ordinary registers (opaque moves) so the per-element code does not go back to the
+      // constant bank through the uniform datapath
+      int act_r = p.epi.act;
+      asm volatile("mov.b32 %0, %0;" : "+r"(act_r));
+      cx.act = act_r;
+      unsigned long long rp = (p.epi.residual != nullptr && p.epi.res_mode == 2) ? (unsigned long long)(cx.resp) : 0ull;
+      asm volatile("mov.b64 %0, %0;" : "+l"(rp));
+      cx.res2p = reinterpret_cast<const T*>(rp);
+    }
     if (p.epi_mode == EPI_LORA16 && n < p.N) {
       const T* brow = reinterpret_cast<const T*>(p.epi.lora_b) + (int64_t)n * 16;
       const Vec8<T> b0 = ld16(brow), b1 = ld16(brow + 8);
@@ -380,10 +404,18 @@ _Pragma("unroll")
           if (SWIGLU) tc_ld16(taddr + NT + c, ru);
           tc_wait_ld();
           if (n < p.N) {
+            // residual operands of the 16 columns are requested together, before the first one is consumed
+            const T* rsrc = (MODE == EPI_RES1 && cx.res_s == nullptr) ? cx.resp : ((MODE == EPI_AFFINE) ? cx.res2p : nullptr);
+            float resv[16];
+            if ((MODE == EPI_RES1 || MODE == EPI_AFFINE) && rsrc != nullptr) {
+_Pragma("unroll")
+              for (int j = 0; j < 16; ++j) resv[j] = (c + j < m_valid) ? Tr<T>::f(rsrc[(int64_t)(m0 + c + j) * cx.ld_res]) : 0.f;
+            }
 _Pragma("unroll")
             for (int j = 0; j < 16; ++j)
               if (c + j < m_valid)
-                finish_store<T, SWIGLU, MODE>(p.epi, cx, __uint_as_float(r[j]), SWIGLU ? __uint_as_float(ru[j]) : 0.f, m0 + c + j, n, c + j);
+                finish_store<T, SWIGLU, MODE>(p.epi, cx, __uint_as_float(r[j]), SWIGLU ? __uint_as_float(ru[j]) : 0.f, m0 + c + j, n, c + j,
+                                              (MODE == EPI_RES1 || MODE == EPI_AFFINE) && rsrc != nullptr, resv[j]);
           }
         }
       )
@@ -610,6 +642,7 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
     if (simple && epi.residual == nullptr && epi.lora_r == 0) p.epi_mode = EPI_PLAIN;
     else if (!SWIGLU && simple && epi.residual != nullptr && epi.res_mode == 1 && epi.lora_r == 0) p.epi_mode = EPI_RES1;
     else if (!SWIGLU && simple && epi.residual == nullptr && epi.lora_r == 16) p.epi_mode = EPI_LORA16;
+    else if (!SWIGLU && epi.lora_r == 0 && epi.act != RD_ACT_SWIGLU && (epi.residual == nullptr || epi.res_mode == 2)) p.epi_mode = EPI_AFFINE;
     if (g_force_generic_epilogue) p.epi_mode = EPI_GENERIC;
   }
   // decode: every weight byte is read once (evict-first), the small activation tile is shared by all CTAs (evict-last)

@@ -87,18 +87,47 @@ extern "C" int rd_rmsnorm(const void* x, const void* w, void* out, int M, int H,
 // RoPE + KV-cache append                                 modeling_llama_imgemb.py:128-142, 209-212
 // q_embed = (q*cos) + (rotate_half(q)*sin): three separately rounded ops; cache keeps post-RoPE K.
 // ------------------------------------------------------------------------------------------------
+// peft LoRA on q_proj / v_proj, applied here instead of in the QKV GEMM epilogue: the GEMM also produced
+// t = T(lora_A . xn) as 2r extra output columns (q's r values, then v's), and  y = T( T(Wx) + T(scale * T(lora_B . t)) ).
+template <class T>
+__device__ __forceinline__ float lora_add(float y, const T* __restrict__ brow, const float* t, int r, float scale) {
+  float s = 0.f;
+  if (r == 8) {                                   // the adapter rank of the reference (finetune.py:167): one 128-bit row
+    const Vec8<T> bv = ld16(brow);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(Tr<T>::f(bv.v[i]), t[i], s);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < r) s = fmaf(Tr<T>::f(brow[i]), t[i], s);
+  }
+  return Tr<T>::rr(y + Tr<T>::rr(scale * Tr<T>::rr(s)));
+}
+
 template <class T>
 __global__ void __launch_bounds__(256)
-rope_kv_store_kernel(T* __restrict__ qkv, const int32_t* __restrict__ pos, const int32_t* __restrict__ ctx_len,
+rope_kv_store_kernel(T* __restrict__ qkv, int64_t ldq, const int32_t* __restrict__ pos, const int32_t* __restrict__ ctx_len,
                      const T* __restrict__ cos_t, const T* __restrict__ sin_t, T* __restrict__ kc, T* __restrict__ vc,
-                     int q_len, int nh, int hd, int cmax) {
+                     int q_len, int nh, int hd, int cmax, const T* __restrict__ lora_b, int lora_r, float lora_scale) {
   pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.x, b = m / q_len, i = m % q_len;
   const int H = nh * hd, half = hd / 2;
   const int slot = ctx_len[0] + i;
   const int p = pos[m];
-  T* row = qkv + (int64_t)m * 3 * H;
+  T* row = qkv + (int64_t)m * ldq;
+  float tq[16], tv[16];                    // lora_A outputs of this token (only read when lora_r > 0)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { tq[i] = 0.f; tv[i] = 0.f; }
+  if (lora_r == 8) {
+    const Vec8<T> a = ld16(row + 3 * H), bb = ld16(row + 3 * H + 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tq[i] = Tr<T>::f(a.v[i]); tv[i] = Tr<T>::f(bb.v[i]); }
+  } else if (lora_r > 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < lora_r) { tq[i] = Tr<T>::f(row[3 * H + i]); tv[i] = Tr<T>::f(row[3 * H + lora_r + i]); }
+  }
   const T* cr = cos_t + (int64_t)p * hd;
   const T* sr = sin_t + (int64_t)p * hd;
   for (int idx = threadIdx.x; idx < nh * half; idx += blockDim.x) {
@@ -106,9 +135,14 @@ rope_kv_store_kernel(T* __restrict__ qkv, const int32_t* __restrict__ pos, const
     const float c_lo = Tr<T>::f(cr[d]), c_hi = Tr<T>::f(cr[d + half]);
     const float s_lo = Tr<T>::f(sr[d]), s_hi = Tr<T>::f(sr[d + half]);
     const int64_t cache_off = (((int64_t)b * nh + h) * cmax + slot) * hd;
+    const int n_lo = h * hd + d, n_hi = n_lo + half;
     {
       T* q = row + h * hd;
       float lo = Tr<T>::f(q[d]), hi = Tr<T>::f(q[d + half]);
+      if (lora_r > 0) {
+        lo = lora_add<T>(lo, lora_b + (int64_t)n_lo * lora_r, tq, lora_r, lora_scale);
+        hi = lora_add<T>(hi, lora_b + (int64_t)n_hi * lora_r, tq, lora_r, lora_scale);
+      }
       q[d] = Tr<T>::r(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
       q[d + half] = Tr<T>::r(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
     }
@@ -120,19 +154,27 @@ rope_kv_store_kernel(T* __restrict__ qkv, const int32_t* __restrict__ pos, const
     }
     {
       const T* v = row + 2 * H + h * hd;
-      vc[cache_off + d] = v[d];
-      vc[cache_off + d + half] = v[d + half];
+      float lo = Tr<T>::f(v[d]), hi = Tr<T>::f(v[d + half]);
+      if (lora_r > 0) {
+        lo = lora_add<T>(lo, lora_b + (int64_t)(H + n_lo) * lora_r, tv, lora_r, lora_scale);
+        hi = lora_add<T>(hi, lora_b + (int64_t)(H + n_hi) * lora_r, tv, lora_r, lora_scale);
+      }
+      vc[cache_off + d] = Tr<T>::r(lo);
+      vc[cache_off + d + half] = Tr<T>::r(hi);
     }
   }
 }
 
-extern "C" int rd_rope_kv_store(void* qkv, const int32_t* pos, const int32_t* ctx_len, const void* cos_t,
+extern "C" int rd_rope_kv_store(void* qkv, int64_t ldq, const int32_t* pos, const int32_t* ctx_len, const void* cos_t,
                                 const void* sin_t, void* kc, void* vc, int B, int q_len, int nh, int hd, int cmax,
-                                int dtype, void* stream) {
+                                const void* lora_b, int lora_r, float lora_scale, int dtype, void* stream) {
   RD_REQUIRE(B > 0 && q_len > 0 && hd % 2 == 0, "rd_rope_kv_store: bad shape");
+  RD_REQUIRE(lora_b == nullptr || (lora_r > 0 && lora_r <= 16), "rd_rope_kv_store: lora_r must be in [1,16] (got %d)", lora_r);
+  RD_REQUIRE(ldq >= 3 * (int64_t)nh * hd + 2 * (lora_b ? lora_r : 0), "rd_rope_kv_store: ldq %lld too small", (long long)ldq);
   RD_DISPATCH_DTYPE(dtype, T, {
     RD_CHECK_CUDA(rd_launch(rope_kv_store_kernel<T>, dim3(B * q_len), dim3(256), 0, (cudaStream_t)stream, rd_pdl_enabled(),
-                            (T*)qkv, pos, ctx_len, (const T*)cos_t, (const T*)sin_t, (T*)kc, (T*)vc, q_len, nh, hd, cmax));
+                            (T*)qkv, ldq, pos, ctx_len, (const T*)cos_t, (const T*)sin_t, (T*)kc, (T*)vc, q_len, nh, hd, cmax,
+                            (const T*)lora_b, lora_b ? lora_r : 0, lora_scale));
     return RD_OK;
   });
 }
@@ -337,22 +379,6 @@ extern "C" int rd_attention(const void* qkv, int64_t ldq, const void* kc, const 
     RD_CHECK_CUDA(rd_launch(attention_kernel<T, false>, dim3(q_len, nh, B), dim3(ATT_THREADS), (size_t)cmax * 4, (cudaStream_t)stream,
                             rd_pdl_enabled(), (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, q_len, nh, cmax,
                             (const int32_t*)nullptr, (const T*)nullptr, (const T*)nullptr));
-    return RD_OK;
-  });
-}
-
-// Single-token decode: RoPE + KV append + attention in one launch (rd_rope_kv_store + rd_attention with q_len == 1).
-extern "C" int rd_attention_decode(const void* qkv, int64_t ldq, const int32_t* pos, const void* cos_t, const void* sin_t,
-                                   void* kc, void* vc, const uint8_t* keymask, const int32_t* ctx_len, void* out, int B, int nh,
-                                   int hd, int cmax, int dtype, void* stream) {
-  RD_REQUIRE(hd == 128, "rd_attention_decode: head_dim must be 128 (Vicuna-7B); got %d", hd);
-  RD_REQUIRE(B > 0 && cmax > 0 && cmax * 4 <= 160 * 1024, "rd_attention_decode: bad shape");
-  RD_DISPATCH_DTYPE(dtype, T, {
-    static bool attr_set = false;
-    if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
-    RD_CHECK_CUDA(rd_launch(attention_kernel<T, true>, dim3(1, nh, B), dim3(ATT_THREADS), (size_t)cmax * 4, (cudaStream_t)stream,
-                            rd_pdl_enabled(), (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, 1, nh, cmax, pos,
-                            (const T*)cos_t, (const T*)sin_t));
     return RD_OK;
   });
 }

@@ -181,11 +181,7 @@ class LlamaForCausalLM:
             if m.has_lora:
                 aq, av = g(lora_prefix.format(i, "q_proj") + "lora_A.weight"), g(lora_prefix.format(i, "v_proj") + "lora_A.weight")
                 bq, bv = g(lora_prefix.format(i, "q_proj") + "lora_B.weight"), g(lora_prefix.format(i, "v_proj") + "lora_B.weight")
-                lw["lora_a"] = torch.cat([aq, av], 0).contiguous()                     # [2r, H]
-                lb = torch.zeros(3 * H, 2 * r, device=dev, dtype=dt)                   # block matrix, k rows stay zero
-                lb[:H, :r] = bq
-                lb[2 * H:, r:] = bv
-                lw["lora_b"] = lb
+                self._pack_lora(lw, aq, av, bq, bv)
             m.layers_w.append(lw)
         if "model.img_proj_layer.weight" in sd:
             lin = nn.Linear(cfg.qformer_hidden, H)
@@ -194,6 +190,14 @@ class LlamaForCausalLM:
             m.img_proj_layer = lin.to(dev)
         self._destroy_engine()
         return self
+
+    def _pack_lora(self, lw, aq, av, bq, bv):
+        """Unmerged LoRA in the engine layout: the two lora_A blocks ride as 2r extra rows of the fused QKV weight (the GEMM
+        then also produces t = lora_A . x), lora_B [2H, r] is applied where q and v are consumed."""
+        H3 = 3 * self.cfg.hidden_size
+        lw["qkv"] = torch.cat([lw["qkv"][:H3], aq, av], 0).contiguous()
+        lw["lora_b"] = torch.cat([bq, bv], 0).contiguous()
+        lw.pop("lora_a", None)
 
     def load_adapter(self, adapter_sd: Dict[str, torch.Tensor]):
         """peft adapter_model.bin: lora_A/lora_B of q_proj,v_proj and img_proj_layer (finetune.py:139-145)."""
@@ -208,12 +212,8 @@ class LlamaForCausalLM:
         m = self.model
         for i, lw in enumerate(m.layers_w):
             p = f"base_model.model.model.layers.{i}.self_attn."
-            aq, av = merged[p + "q_proj.lora_A.weight"].to(dev, dt), merged[p + "v_proj.lora_A.weight"].to(dev, dt)
-            lw["lora_a"] = torch.cat([aq, av], 0).contiguous()
-            lb = torch.zeros(3 * H, 2 * r, device=dev, dtype=dt)
-            lb[:H, :r] = merged[p + "q_proj.lora_B.weight"].to(dev, dt)
-            lb[2 * H:, r:] = merged[p + "v_proj.lora_B.weight"].to(dev, dt)
-            lw["lora_b"] = lb
+            self._pack_lora(lw, merged[p + "q_proj.lora_A.weight"].to(dev, dt), merged[p + "v_proj.lora_A.weight"].to(dev, dt),
+                            merged[p + "q_proj.lora_B.weight"].to(dev, dt), merged[p + "v_proj.lora_B.weight"].to(dev, dt))
         m.has_lora = True
         if "model.img_proj_layer.weight" in merged:
             lin = nn.Linear(cfg.qformer_hidden, H)

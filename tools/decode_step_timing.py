@@ -22,8 +22,10 @@ NEW = int(os.environ.get("NEW", "64"))
 for B in [int(b) for b in os.environ.get("BS", "32,1").split(",")]:
     prompts = synth.make_prompts(B, seed=4321).to(dev)
     img = torch.randn(B, 32, 768, device=dev) * 0.5
-    for graph in (True, False):
-        for pdl in (0, 1):
+    for algo in ([0, 1, 2] if B <= 4 else [0]):
+      llm.set_algo(algo)
+      for graph, pdl in ((True, 1), (False, 1), (True, 0)):
+        if True:
             lib.rd_set_pdl(pdl)
             llm.use_cuda_graph = graph
             llm._graphs = {}
@@ -31,5 +33,5 @@ for B in [int(b) for b in os.environ.get("BS", "32,1").split(",")]:
             torch.cuda.synchronize()
             llm.generate(prompts, img_embeds=img, max_new_tokens=NEW, suppress_eos=True)
             s = llm.last_stats
-            print(f"B={B:3d} graph={int(graph)} pdl={pdl}: prefill {s['prefill_ms']:.1f} ms, decode {s['decode_ms'] / (NEW - 1):.3f} ms/step", flush=True)
+            print(f"B={B:3d} algo={algo} graph={int(graph)} pdl={pdl}: prefill {s['prefill_ms']:.1f} ms, decode {s['decode_ms'] / (NEW - 1):.3f} ms/step", flush=True)
 lib.rd_set_pdl(0)
