@@ -165,6 +165,9 @@ void rd_llm_destroy(rd_llm* h);
 int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* ptr_dev);
 /* GEMM path: 0 auto, 1 GEMV, 2 tcgen05, 3 SIMT (validation) */
 int rd_llm_set_algo(rd_llm* h, int algo);
+/* Decode step: bytes of W_qkv / W_o / W_gate|up that the (latency-bound, HBM-idle) norm and attention kernels pull into
+ * the 126 MB L2 with cp.async.bulk.prefetch ahead of the GEMM that streams them; 0,0,0 turns it off. */
+int rd_llm_set_l2_prefetch(rd_llm* h, long long qkv_bytes, long long o_bytes, long long gate_up_bytes);
 
 /* Start generation: clears the KV cache, infers attention_mask = (ids != pad) and position_ids = cumsum-1
  * (prepare_inputs_for_generation, modeling_llama_imgemb.py:795-836), runs the prefill forward over ids[B,T] with

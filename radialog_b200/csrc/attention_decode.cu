@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(THREADS)
 attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ kc, T* __restrict__ vc,
                         const uint8_t* __restrict__ keymask, const int32_t* __restrict__ ctx_len_p, T* __restrict__ out, int nh,
                         int cmax, const int32_t* __restrict__ pos, const T* __restrict__ cos_t, const T* __restrict__ sin_t,
-                        int prefetch_keys, const T* __restrict__ lora_b, int lora_r, float lora_scale) {
+                        int prefetch_keys, const T* __restrict__ lora_b, int lora_r, float lora_scale,
+                        const void* pf0, long long pf0_bytes, const void* pf1, long long pf1_bytes) {
   constexpr int GROUPS = THREADS / 16;
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -70,6 +71,11 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
   const T* vbase = vc + ((int64_t)b * nh + h) * cmax * HD;
 
   pdl_launch_dependents();
+  {                     // weights of the next GEMMs -> L2 while this latency-bound kernel leaves HBM idle
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x, n_ctas = gridDim.x * gridDim.y;
+    l2_prefetch_slice(pf0, pf0_bytes, cta, n_ctas, tid, THREADS);
+    l2_prefetch_slice(pf1, pf1_bytes, cta, n_ctas, tid, THREADS);
+  }
   if (tid == 0) {
     for (int i = 0; i < RING; ++i) mbar_init(&full_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -253,6 +259,12 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
 
 }  // namespace
 
+static const void* g_pf0 = nullptr; static long long g_pf0_bytes = 0;
+static const void* g_pf1 = nullptr; static long long g_pf1_bytes = 0;
+// weights the next rd_attention_decode launch should pull into L2 (consumed by that launch)
+extern "C" int rd_attention_decode_set_l2_prefetch(const void* p0, long long b0, const void* p1, long long b1) {
+  g_pf0 = p0; g_pf0_bytes = b0; g_pf1 = p1; g_pf1_bytes = b1; return RD_OK;
+}
 static int g_attn_prefetch = 1;      // test hook: 0 disables the pre-wait prefetch
 extern "C" int rd_attention_decode_set_prefetch(int on) { g_attn_prefetch = on; return RD_OK; }
 
@@ -274,13 +286,14 @@ extern "C" int rd_attention_decode(const void* qkv, int64_t ldq, const int32_t* 
       RD_CHECK_CUDA(cudaFuncSetAttribute(attention_decode_kernel<T, 512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 512, 4>, dim3(nh, B), dim3(512), smem, (cudaStream_t)stream, rd_pdl_enabled(),
                               (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
-                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale));
+                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes));
     } else {
       RD_CHECK_CUDA(cudaFuncSetAttribute(attention_decode_kernel<T, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 128, 3>, dim3(nh, B), dim3(128), smem, (cudaStream_t)stream, rd_pdl_enabled(),
                               (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
-                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale));
+                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes));
     }
+    g_pf0 = nullptr; g_pf1 = nullptr; g_pf0_bytes = 0; g_pf1_bytes = 0;
     return RD_OK;
   });
 }

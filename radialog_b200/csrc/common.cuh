@@ -107,6 +107,23 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// L2 prefetch of a slice of an upcoming weight matrix (cp.async.bulk.prefetch.L2): the small latency-bound kernels between
+// two GEMMs leave HBM idle; they use that time to pull the next GEMM's weights into the 126 MB L2.  CTA `cta` of `n_ctas`
+// requests its share of [ptr, ptr+bytes), spread over its threads in 16 KB requests; nothing waits on them.
+__device__ __forceinline__ void l2_prefetch_slice(const void* ptr, long long bytes, int cta, int n_ctas, int tid, int n_threads) {
+  if (ptr == nullptr || bytes <= 0) return;
+  const long long per = ((bytes + n_ctas - 1) / n_ctas + 127) / 128 * 128;     // this CTA's share
+  const long long off = (long long)cta * per;
+  if (off >= bytes) return;
+  const long long len = (bytes - off < per ? bytes - off : per) / 16 * 16;
+  const char* base = reinterpret_cast<const char*>(ptr) + off;
+  constexpr long long CHUNK = 16384;                                             // one request per thread and round
+  for (long long o = (long long)tid * CHUNK; o < len; o += (long long)n_threads * CHUNK) {
+    const unsigned sz = (unsigned)(len - o < CHUNK ? len - o : CHUNK);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + o), "r"(sz) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // shared epilogue (rd_linear): see include/radialog_b200.h for the rounding contract
 // ------------------------------------------------------------------------------------------------

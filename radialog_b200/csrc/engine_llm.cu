@@ -2,11 +2,14 @@
 // transformers 4.28.1 as a native runtime: flat pre-allocated KV cache (replaces the
 // per-step torch.cat at :209-212), device-resident generation state, one host call per decode step that is
 // CUDA-graph capturable.
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 
 extern "C" int rd_attention_decode(const void*, int64_t, const int32_t*, const void*, const void*, void*, void*, const uint8_t*,
                                    const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
+extern "C" int rd_rmsnorm_prefetch(const void*, const void*, void*, int, int, float, const void*, long long, int, void*);
+extern "C" int rd_attention_decode_set_l2_prefetch(const void*, long long, const void*, long long);
 extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const int32_t*, int, int, int, int, void*);
 extern "C" int rd_argmax_step(const void*, int64_t, int, int64_t*, int64_t*, int64_t, int32_t*, uint8_t*, int, int32_t*,
                               int32_t*, int32_t*, int32_t*, uint32_t*, int, int, int, int, int, int, void*);
@@ -25,6 +28,10 @@ struct rd_llm {
   const float* img_b = nullptr;
   int algo = 0;
   int esz = 2;
+  // L2 weight prefetch from the norm / attention kernels: mechanism kept, OFF by default (A/B runs on B200 showed no
+  // gain at B=32 beyond run-to-run noise and a loss at B=1, where the norm kernel is a single CTA)
+  bool l2_prefetch = false;
+  long long pf_qkv = 0, pf_o = 0, pf_gu = 0;
   int64_t max_tokens = 0;
   int vpad = 0;
   // device buffers
@@ -140,6 +147,14 @@ extern "C" int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* p) 
   return RD_OK;
 }
 
+// bytes of W_qkv / W_o / W_gate|up to prefetch into L2 from the norm / attention kernels of a decode step (0,0,0 = off)
+extern "C" int rd_llm_set_l2_prefetch(rd_llm* h, long long qkv_bytes, long long o_bytes, long long gate_up_bytes) {
+  RD_REQUIRE(h, "rd_llm_set_l2_prefetch: null handle");
+  h->pf_qkv = qkv_bytes; h->pf_o = o_bytes; h->pf_gu = gate_up_bytes;
+  h->l2_prefetch = qkv_bytes > 0 || o_bytes > 0 || gate_up_bytes > 0;
+  return RD_OK;
+}
+
 extern "C" int rd_llm_set_algo(rd_llm* h, int algo) {
   RD_REQUIRE(h && algo >= 0 && algo <= 3, "rd_llm_set_algo: bad argument");
   h->algo = algo;
@@ -194,11 +209,15 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     // columns [3H, 3H+2r) of the qkv buffer; lora_B is applied where q and v are consumed (RoPE / attention kernels)
     const int R2 = c.lora_r ? 2 * c.lora_r : 0;
     const int64_t ldq = 3 * H + R2;
+    const bool decode = q_len == 1 && h->l2_prefetch;
+    const long long qkv_bytes = (long long)(3 * H + R2) * H * 2, o_bytes = (long long)H * H * 2, gu_bytes = (long long)2 * I * H * 2;
     { ProfScope ps(h, st, C_RMSNORM);
-      RD_CHECK(rd_rmsnorm(h->x, w.ln1, h->xn, M, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
+      // decode: the norm kernels are latency bound and leave HBM idle -> they pull the next GEMM's weights into L2
+      RD_CHECK(rd_rmsnorm_prefetch(h->x, w.ln1, h->xn, M, H, c.rms_eps, decode ? w.qkv : nullptr, decode ? std::min(qkv_bytes, h->pf_qkv) : 0, dt, st)); }
     RD_CHECK(linear(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, st));
     if (q_len == 1) {      // decode: RoPE + KV append + attention fused in one launch
       ProfScope ps(h, st, C_ATTN);
+      if (decode) rd_attention_decode_set_l2_prefetch(w.o, std::min(o_bytes, h->pf_o), w.gate_up, std::min(gu_bytes, h->pf_gu));
       RD_CHECK(rd_attention_decode(h->qkv, ldq, pos, h->cos, h->sin, kc, vc, h->keymask, h->ctx_len, h->att, B, nh, hd, c.max_ctx,
                                    h->ctx_host, c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st));
     } else {

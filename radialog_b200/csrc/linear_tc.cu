@@ -491,17 +491,19 @@ _Pragma("unroll")
     if (threadIdx.x == 64) trace_stamp(p.trace, 6);
     if (warp >= 2 && n < p.N) {
       const uint32_t red_addr = smem_u32(red);
-      // this CTA's slice of the token columns: j = split, split + splits, ...; four columns per round so that their
-      // partials (<= 32 DSMEM loads, 64 with SwiGLU) are in flight together; summed in fixed split order.
+      // this CTA's slice of the token columns: j = split, split + splits, ...; RT columns per round so that their partials
+      // are in flight together over DSMEM; summed in fixed split order.
+      constexpr int RT = SWIGLU ? 4 : 8;       // token columns per round (register budget: RT x 8 partials, x2 with SwiGLU)
       EPI_DISPATCH(p.epi_mode,
-        for (int jb = split; jb < m_valid; jb += 4 * p.splits) {
-          float v[4][8], vu[4][8];
+        for (int jb = split; jb < m_valid; jb += RT * p.splits) {
+          float v[RT][8], vu[SWIGLU ? RT : 1][8];
 _Pragma("unroll")
-          for (int t = 0; t < 4; ++t) {
+          for (int t = 0; t < RT; ++t) {
             const int j = jb + t * p.splits;
 _Pragma("unroll")
             for (int s = 0; s < 8; ++s) {
-              v[t][s] = 0.f; vu[t][s] = 0.f;
+              v[t][s] = 0.f;
+              if (SWIGLU) vu[t][s] = 0.f;
               if (j < m_valid && s < p.splits) {
                 v[t][s] = ld_dsmem_f32(red_addr + (uint32_t)((j * BLOCK_N + n_local) * 4), (uint32_t)s);
                 if (SWIGLU) vu[t][s] = ld_dsmem_f32(red_addr + (uint32_t)(((NT + j) * BLOCK_N + n_local) * 4), (uint32_t)s);
@@ -509,12 +511,12 @@ _Pragma("unroll")
             }
           }
 _Pragma("unroll")
-          for (int t = 0; t < 4; ++t) {
+          for (int t = 0; t < RT; ++t) {
             const int j = jb + t * p.splits;
             if (j < m_valid) {
               float acc = 0.f, accu = 0.f;
 _Pragma("unroll")
-              for (int s = 0; s < 8; ++s) { acc += v[t][s]; accu += vu[t][s]; }
+              for (int s = 0; s < 8; ++s) { acc += v[t][s]; if (SWIGLU) accu += vu[t][s]; }
               finish_store<T, SWIGLU, MODE>(p.epi, cx, acc, accu, m0 + j, n, j);
             }
           }

@@ -11,8 +11,9 @@ bool rd_pdl_enabled();
 template <class T>
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ out, int H, float eps,
-               const T* __restrict__ lora_a, int lora_rows, T* __restrict__ lora_t) {
+               const T* __restrict__ lora_a, int lora_rows, T* __restrict__ lora_t, const void* pf_ptr, long long pf_bytes) {
   pdl_launch_dependents();
+  l2_prefetch_slice(pf_ptr, pf_bytes, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x);     // weights: no dependency on x
   pdl_wait();
   extern __shared__ float srow[];      // H floats
   __shared__ float sred[8];
@@ -70,17 +71,27 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
   }
 }
 
-extern "C" int rd_rmsnorm(const void* x, const void* w, void* out, int M, int H, float eps, const void* lora_a,
-                          int lora_rows, void* lora_t, int dtype, void* stream) {
+static int rmsnorm_impl(const void* x, const void* w, void* out, int M, int H, float eps, const void* lora_a,
+                        int lora_rows, void* lora_t, const void* pf_ptr, long long pf_bytes, int dtype, void* stream) {
   RD_REQUIRE(M > 0 && H > 0 && H % 8 == 0, "rd_rmsnorm: bad shape M=%d H=%d", M, H);
   RD_REQUIRE(H * 4 <= 200 * 1024, "rd_rmsnorm: H=%d too large", H);
   RD_DISPATCH_DTYPE(dtype, T, {
     static bool attr_set = false;
     if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(rmsnorm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
     RD_CHECK_CUDA(rd_launch(rmsnorm_kernel<T>, dim3(M), dim3(256), (size_t)H * 4, (cudaStream_t)stream, rd_pdl_enabled(),
-                            (const T*)x, (const T*)w, (T*)out, H, eps, (const T*)lora_a, lora_rows, (T*)lora_t));
+                            (const T*)x, (const T*)w, (T*)out, H, eps, (const T*)lora_a, lora_rows, (T*)lora_t, pf_ptr, pf_bytes));
     return RD_OK;
   });
+}
+
+extern "C" int rd_rmsnorm(const void* x, const void* w, void* out, int M, int H, float eps, const void* lora_a,
+                          int lora_rows, void* lora_t, int dtype, void* stream) {
+  return rmsnorm_impl(x, w, out, M, H, eps, lora_a, lora_rows, lora_t, nullptr, 0, dtype, stream);
+}
+// rd_rmsnorm that also pulls [pf_ptr, pf_ptr+pf_bytes) (the next GEMM's weights) into L2 while it runs
+extern "C" int rd_rmsnorm_prefetch(const void* x, const void* w, void* out, int M, int H, float eps, const void* pf_ptr,
+                                   long long pf_bytes, int dtype, void* stream) {
+  return rmsnorm_impl(x, w, out, M, H, eps, nullptr, 0, nullptr, pf_ptr, pf_bytes, dtype, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -182,3 +182,25 @@ def test_dicom_and_use_img_side_channels(cuda_dev, tmp_path, monkeypatch):
     direct1 = model.generate(prompts[:1], img_embeds=img[:1].to(cuda_dev), max_new_tokens=4, suppress_eos=True).cpu()
     via_file = model.generate(prompts[:1], use_img=True, max_new_tokens=4, suppress_eos=True).cpu()
     assert torch.equal(via_file, direct1)
+
+
+def test_sixteen_image_set_token_id_equality_real_width(cuda_dev):
+    """north_star: greedy token-ID equality on a fixed 16-image synthetic set.  Full-width model (H=4096, 32 heads,
+    I=11008, V=32001, LoRA) truncated to 2 layers so the CPU oracle finishes in about a minute; the image tokens come
+    from the full ResNet-50 + Q-Former vision stage of the product path.  Ids must equal the oracle's except at steps
+    where the oracle's own top-2 margin is a tie (< 3 ulp)."""
+    from radialog_b200.vision import Blip2Qformer
+    dtype = torch.float16
+    cfg = synth.LlamaCfg(num_hidden_layers=2)
+    model, orc, _ = build(cfg, dtype, cuda_dev)
+    vcfg = synth.VisionCfg()
+    vsd = synth.make_vision_weights(vcfg, seed=0)
+    imgs = synth.make_images(16, seed=1234)
+    vis = Blip2Qformer.from_state_dict(vcfg, vsd, torch_dtype=dtype, device=cuda_dev, max_batch=16)
+    q_out, _ = vis.forward_image(imgs.to(cuda_dev))
+    prompts = synth.make_prompts(16, seed=4321, ragged=True)
+    n_new = 16
+    out = model.generate(prompts.to(cuda_dev), img_embeds=q_out, max_new_tokens=n_new, suppress_eos=True).cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    o_ids, o_scores = orc.generate(prompts, q_out.cpu(), n_new, suppress_eos=True, return_scores=True)
+    assert_ids_match(out, o_ids, o_scores, prompts.shape[1], dtype, "16-image set", min_exact_rows=0.75)
