@@ -249,6 +249,9 @@ def run_own_arm(args):
         t = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
+        nl = torch.tensor([float(n_launch)], device=dev, dtype=torch.float64)
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)          # whole-job launch count
+        n_launch = int(nl.item())
 
     # ---- roofline of the dominant kernel + whole decode step (rank 0) ----------------------------------------------------------------
     out = None
