@@ -165,6 +165,11 @@ void rd_llm_destroy(rd_llm* h);
 int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* ptr_dev);
 /* GEMM path: 0 auto, 1 GEMV, 2 tcgen05, 3 SIMT (validation) */
 int rd_llm_set_algo(rd_llm* h, int algo);
+/* Single-token decode steps with B <= 32 run ALL decoder layers in one persistent kernel (one CTA per SM, weights of
+ * every phase streamed through one TMA ring, stream-K work split, grid barriers between phases; csrc/decode_mega.cu).
+ * on = 1 (default) / 0 = one kernel per op.  Same rounding contract either way (LlamaDecoderLayer.forward,
+ * modeling_llama_imgemb.py:266-318).  Call outside stream capture.                                              */
+int rd_llm_set_mega(rd_llm* h, int on);
 /* Decode step: bytes of W_qkv / W_o / W_gate|up that the (latency-bound, HBM-idle) norm and attention kernels pull into
  * the 126 MB L2 with cp.async.bulk.prefetch ahead of the GEMM that streams them; 0,0,0 turns it off. */
 int rd_llm_set_l2_prefetch(rd_llm* h, long long qkv_bytes, long long o_bytes, long long gate_up_bytes);

@@ -1,0 +1,876 @@
+// Persistent decode-layer kernel: ALL transformer layers of one single-token decode step in ONE launch (sm_100a).
+//
+// Replaces, for q_len == 1 and B <= 32, the per-layer launch sequence of engine_llm.cu
+//   rmsnorm -> QKV GEMM -> RoPE+append+attention -> O GEMM(+res) -> rmsnorm -> gate|up GEMM(+SwiGLU) -> down GEMM(+res)
+// (LlamaDecoderLayer.forward, modeling_llama_imgemb.py:266-318; rounding points of SURVEY.md Appendix B unchanged).
+//
+// Why: a decode step is HBM-bound (13.2 GB of weights per step), and with one kernel per op every launch boundary
+// drains the weight stream (prologue + split-K tail ~10 us per GEMM, profiles/ncu_s2_linear.md).  Here one CTA per SM
+// stays resident for the whole step and a dedicated producer thread streams the weight tiles of ALL phases and layers
+// through one TMA ring; it never waits for anything except a free ring slot, so the HBM pipe stays busy across phase
+// boundaries while the consumers synchronise.
+//
+//   warp 0     : weight producer   (cp.async.bulk.tensor 2D, 128B swizzle, evict-first) - runs ahead across phases/layers
+//   warp 1     : tcgen05.mma issuer (UMMA 128 x 32, fp32 accumulators in TMEM, 4 accumulator buffers)
+//   warp 2     : activation producer (TMA of the [32 x 64] token tiles, gated on the grid barrier of the previous phase)
+//   warps 4-11 : workers: RMSNorm applied to the token tiles in shared memory, GEMM epilogues (tcgen05.ld, stream-K
+//                fix-up, residual add, SwiGLU, sum-of-squares partials for the next RMSNorm), RoPE + KV append + attention.
+//
+// Work split: every GEMM phase is cut "stream-K" style: the (weight tile, k-block) units of the phase are dealt to the
+// CTAs in equal contiguous runs (host-built table), so all SMs pull the same number of weight bytes whatever the tile
+// count (96 / 32 / 86 / 32 tiles vs 148 SMs).  A tile whose k range is shared by several CTAs is reduced through an
+// fp32 workspace in L2 by the LAST CTA to finish it, in fixed split order (deterministic).  Phases are separated by a
+// grid barrier (one atomic counter); 5 per layer.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+#include "decode_mega.h"
+#include "tc_ptx.cuh"
+
+bool rd_pdl_enabled();
+
+namespace {
+using namespace tcptx;
+
+constexpr int TILE_N = 128;            // weight rows per tile (UMMA M)
+constexpr int BK = 64;                 // k-block: 64 x 2 B = one 128-byte swizzle row
+constexpr int NT = 32;                 // token columns (UMMA N)
+constexpr int UK = 16;
+constexpr int W_SLOT = TILE_N * BK * 2;   // 16 KB
+constexpr int X_SLOT = NT * BK * 2;       // 4 KB
+constexpr int SW = 8;                  // weight ring slots (128 KB)
+constexpr int SX = 20;                 // token-tile ring slots (80 KB); doubles as the attention scratch
+constexpr int NACC = 4, ACC_COLS = 64, TMEM_COLS = 256;
+constexpr int WORK_WARPS = 8, WORKERS = WORK_WARPS * 32, THREADS = 128 + WORKERS;
+constexpr int MAX_G = 160, MAX_SEG = 4, MAX_SPLIT = 8;
+constexpr int PART_STRIDE = 2 * NT * TILE_N;      // floats per (tile, split) slab of the stream-K workspace
+constexpr int ATT_WARP_BYTES = SX * X_SLOT / WORK_WARPS;     // 10 KB: [scores / partial acc 2 KB][chunk 4 KB][chunk 4 KB]
+constexpr int ATT_CH = 16;             // keys per bulk-copy chunk (16 x 256 B = 4 KB)
+constexpr int ATT_MAX_CTX = 1023;      // scores of one (sequence, head) live in 2 KB of shared memory as 2-byte values
+static_assert(ATT_WARP_BYTES == 2048 + 2 * ATT_CH * 256, "attention scratch layout");
+
+constexpr int SMEM_RING = SW * W_SLOT + SX * X_SLOT;
+constexpr int N_BARS = 2 * SW + 3 * SX + 2 * NACC + 2 * WORK_WARPS;
+constexpr int SMEM_MISC = N_BARS * 8 + 16 + 32 * 4 + 4 * 32 * 4 + WORK_WARPS * 2 * 4;
+constexpr int SMEM_BYTES = SMEM_RING + 1024 + ((SMEM_MISC + 127) / 128) * 128;
+
+enum { G_QKV = 0, G_O = 1, G_GU = 2, G_DN = 3 };
+
+struct Seg { int tile, kb0, kb1, split, nsplits, pad0, pad1, pad2; };
+struct Sched {
+  int nseg[4][MAX_G];
+  Seg seg[4][MAX_G][MAX_SEG];
+};
+
+struct LayerDev {
+  const void *ln1, *ln2, *lora_b;
+  void *kc, *vc;
+};
+
+struct MegaParams {
+  const CUtensorMap* wmaps;     // [layers][4]
+  const LayerDev* lay;          // [layers]
+  const Sched* sched;
+  void *x, *qkv, *att, *mid;
+  float* ws;                    // stream-K partials [tile][MAX_SPLIT][PART_STRIDE]
+  float* ssq;                   // [H/128][32] sum-of-squares partials of the residual stream
+  uint32_t* sync;               // [0] grid-barrier counter, [1] exit counter, [32..] per-tile arrival counters
+  const uint8_t* keymask;
+  const int32_t *ctx_len, *pos;
+  const void *cos_t, *sin_t;
+  int B, H, I, nh, n_qkv, ldq, cmax, lora_r, l0, l1, G, att_P;
+  float lora_scale, eps;
+};
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); }
+__device__ __forceinline__ void team_bar(int team, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ void grid_wait(const uint32_t* ctr, uint32_t target, int tag) {
+  if (target == 0) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (ld_acquire_gpu(ctr) < target) {
+    if ((++spins & 0xFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 6000000000ll) {
+        printf("decode_mega: grid barrier timed out (tag %d, block %d, target %u, have %u)\n", tag, blockIdx.x, target, ld_acquire_gpu(ctr));
+        __trap();
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int phase_epoch(int l_rel, int g) { return 5 * l_rel + (g == G_QKV ? 0 : g == G_O ? 2 : g == G_GU ? 3 : 4); }
+
+template <class T> __device__ __forceinline__ T ldcg_t(const T* p) {
+  const unsigned short u = __ldcg(reinterpret_cast<const unsigned short*>(p));
+  return *reinterpret_cast<const T*>(&u);
+}
+template <class T> __device__ __forceinline__ Vec8<T> ldcg16(const T* p) {
+  Vec8<T> r;
+  *reinterpret_cast<uint4*>(&r) = __ldcg(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// attention of one decode step for this CTA's (sequence, head) items: RoPE + KV append + softmax(QK^T).V with the
+// reference's rounding points (modeling_llama_imgemb.py:205-234; same arithmetic as attention_decode.cu).  A team of
+// P warps shares one item: K/V chunks round-robin over the team, scores in the team leader's scratch.
+// ------------------------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void attention_items(const MegaParams& p, const LayerDev& L, int cta, int ww, int lane, uint8_t* scratch,
+                                                uint64_t* att_bar, float* s_red, uint32_t& seq) {
+  constexpr int HD = 128;
+  const int P = p.att_P, team = ww / P, pw = ww % P, teams = WORK_WARPS / P;
+  const int g2 = lane >> 4, l16 = lane & 15;
+  const unsigned hmask = 0xFFFFu << (lane & 16);
+  T* sc = reinterpret_cast<T*>(scratch + (size_t)(team * P) * ATT_WARP_BYTES);
+  float* pacc = reinterpret_cast<float*>(scratch + (size_t)ww * ATT_WARP_BYTES);
+  uint8_t* cbuf = scratch + (size_t)ww * ATT_WARP_BYTES + 2048;
+  uint64_t* bar = att_bar + ww * 2;
+  const int nh = p.nh, H = p.H, cmax = p.cmax, lora_r = p.lora_r;
+  const T* kc = reinterpret_cast<const T*>(L.kc);
+  const T* vc = reinterpret_cast<const T*>(L.vc);
+  const T* lora_b = reinterpret_cast<const T*>(L.lora_b);
+  const T* cos_t = reinterpret_cast<const T*>(p.cos_t);
+  const T* sin_t = reinterpret_cast<const T*>(p.sin_t);
+  const int ctx = p.ctx_len[0];
+  const int nK = (ctx + ATT_CH - 1) / ATT_CH;
+  const int n_my = nK > pw ? (nK - pw + P - 1) / P : 0;
+  const float lowest = Tr<T>::lowest();
+  const float sqrt_d = 11.313708498984761f;
+  const int nitems = p.B * nh;
+
+  for (int item = team * p.G + cta; item < nitems; item += teams * p.G) {
+    const int b = item / nh, h = item % nh;
+    const T* kbase = kc + ((int64_t)b * nh + h) * cmax * HD;
+    const T* vbase = vc + ((int64_t)b * nh + h) * cmax * HD;
+    auto issue = [&](int s) {                    // lane 0: chunk s of this warp's K-then-V sequence
+      const bool is_k = s < n_my;
+      const int c = pw + (is_k ? s : s - n_my) * P;
+      int keys = ctx - c * ATT_CH;
+      keys = keys > ATT_CH ? ATT_CH : keys;
+      const uint32_t q = seq + (uint32_t)s;
+      uint64_t* bb = bar + (q & 1u);
+      mbar_expect_tx(bb, (uint32_t)keys * HD * 2);
+      bulk_g2s(cbuf + (q & 1u) * (ATT_CH * HD * 2), (is_k ? kbase : vbase) + (size_t)c * ATT_CH * HD, (uint32_t)keys * HD * 2, bb);
+    };
+    if (lane == 0) {
+      if (2 * n_my > 0) issue(0);
+      if (2 * n_my > 1) issue(1);
+    }
+    // ---- RoPE of q (every warp of the team), of k and the LoRA'd v (team leader), KV append ----------------------
+    const T* row = reinterpret_cast<const T*>(p.qkv) + (int64_t)b * p.ldq;
+    const int D = l16 * 8, Dp = D ^ 64;
+    const bool lo_half = D < 64;
+    const int ppos = p.pos[b];
+    float tq[16], tv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { tq[i] = 0.f; tv[i] = 0.f; }
+    if (lora_r > 0) {
+      for (int i = 0; i < lora_r; ++i) { tq[i] = Tr<T>::f(ldcg_t(row + 3 * H + i)); tv[i] = Tr<T>::f(ldcg_t(row + 3 * H + lora_r + i)); }
+    }
+    auto lora = [&](float y, int n_row, const float* t) {
+      const T* brow = lora_b + (int64_t)n_row * lora_r;
+      float sdot = 0.f;
+      for (int i = 0; i < lora_r; ++i) sdot = fmaf(Tr<T>::f(brow[i]), t[i], sdot);
+      return Tr<T>::rr(y + Tr<T>::rr(p.lora_scale * Tr<T>::rr(sdot)));
+    };
+    const Vec8<T> cv = ld16(cos_t + (int64_t)ppos * HD + D), sv = ld16(sin_t + (int64_t)ppos * HD + D);
+    float q[8], kn[8], vn[8];
+    {
+      const Vec8<T> own = ldcg16(row + h * HD + D), oth = ldcg16(row + h * HD + Dp);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float a = Tr<T>::f(own.v[e]), o = Tr<T>::f(oth.v[e]);
+        if (lora_r > 0) { a = lora(a, h * HD + D + e, tq); o = lora(o, h * HD + Dp + e, tq); }
+        const float c = Tr<T>::f(cv.v[e]), s = Tr<T>::f(sv.v[e]);
+        q[e] = Tr<T>::rr(Tr<T>::rr(a * c) + Tr<T>::rr((lo_half ? -o : o) * s));
+      }
+    }
+    if (pw == 0) {
+      const Vec8<T> own = ldcg16(row + H + h * HD + D), oth = ldcg16(row + H + h * HD + Dp);
+      const Vec8<T> vv = ldcg16(row + 2 * H + h * HD + D);
+      Vec8<T> ko, vo;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float a = Tr<T>::f(own.v[e]), o = Tr<T>::f(oth.v[e]);
+        const float c = Tr<T>::f(cv.v[e]), s = Tr<T>::f(sv.v[e]);
+        kn[e] = Tr<T>::rr(Tr<T>::rr(a * c) + Tr<T>::rr((lo_half ? -o : o) * s));
+        float v = Tr<T>::f(vv.v[e]);
+        if (lora_r > 0) v = lora(v, H + h * HD + D + e, tv);
+        vn[e] = v;
+        ko.v[e] = Tr<T>::r(kn[e]); vo.v[e] = Tr<T>::r(v);
+      }
+      if (g2 == 0) {
+        const int64_t slot_off = (((int64_t)b * nh + h) * cmax + ctx) * HD + D;
+        *reinterpret_cast<uint4*>(reinterpret_cast<T*>(L.kc) + slot_off) = *reinterpret_cast<const uint4*>(&ko);
+        *reinterpret_cast<uint4*>(reinterpret_cast<T*>(L.vc) + slot_off) = *reinterpret_cast<const uint4*>(&vo);
+      }
+    }
+    const uint8_t* km = p.keymask + (int64_t)b * cmax;
+    auto score_of = [&](float dot, int j) {      // modeling_llama_imgemb.py:216-230 (decode: padding mask only)
+      float s = Tr<T>::rr(dot);
+      s = Tr<T>::rr(s / sqrt_d);
+      s = Tr<T>::rr(s + (km[j] ? 0.f : lowest));
+      return fmaxf(s, lowest);
+    };
+    // ---- scores of this warp's K chunks ------------------------------------------------------------------------------
+    float lmax = -INFINITY;
+    for (int s = 0; s < n_my; ++s) {
+      const uint32_t qi = seq + (uint32_t)s;
+      mbar_wait(bar + (qi & 1u), (qi >> 1) & 1u, 40);
+      const T* buf = reinterpret_cast<const T*>(cbuf + (qi & 1u) * (ATT_CH * HD * 2));
+      const int c = pw + s * P;
+      int keys = ctx - c * ATT_CH;
+      keys = keys > ATT_CH ? ATT_CH : keys;
+#pragma unroll 2
+      for (int jl = g2; jl < ATT_CH; jl += 2) {  // uniform trip count: the half-warp shuffles stay converged
+        float d = 0.f;
+        if (jl < keys) {
+          const Vec8<T> kk = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + D);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d = fmaf(q[e], Tr<T>::f(kk.v[e]), d);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
+        if (jl < keys) {
+          const float svv = score_of(d, c * ATT_CH + jl);
+          if (l16 == 0) sc[c * ATT_CH + jl] = Tr<T>::r(svv);
+          lmax = fmaxf(lmax, svv);
+        }
+      }
+      __syncwarp();
+      if (lane == 0 && s + 2 < 2 * n_my) issue(s + 2);
+    }
+    if (pw == 0) {                               // the token just appended
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(q[e], kn[e], d);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
+      const float svv = score_of(d, ctx);
+      if (lane == 0) sc[ctx] = Tr<T>::r(svv);
+      lmax = fmaxf(lmax, svv);
+    }
+    lmax = warp_max(lmax);
+    float mx = lmax;
+    if (P > 1) {
+      if (lane == 0) s_red[ww * 2] = lmax;
+      team_bar(team, P * 32);
+      mx = s_red[(team * P) * 2];
+      for (int i = 1; i < P; ++i) mx = fmaxf(mx, s_red[(team * P + i) * 2]);
+    } else {
+      __syncwarp();
+    }
+    // ---- softmax denominator (fp32), modeling_llama_imgemb.py:233 ----------------------------------------------------
+    float lsum = 0.f;
+    for (int j = pw * 32 + lane; j <= ctx; j += P * 32) lsum += expf(Tr<T>::f(sc[j]) - mx);
+    lsum = warp_sum(lsum);
+    float sum = lsum;
+    if (P > 1) {
+      if (lane == 0) s_red[ww * 2 + 1] = lsum;
+      team_bar(team, P * 32);
+      sum = 0.f;
+      for (int i = 0; i < P; ++i) sum += s_red[(team * P + i) * 2 + 1];
+    }
+    // ---- P.V over this warp's V chunks -------------------------------------------------------------------------------
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = n_my; s < 2 * n_my; ++s) {
+      const uint32_t qi = seq + (uint32_t)s;
+      mbar_wait(bar + (qi & 1u), (qi >> 1) & 1u, 41);
+      const T* buf = reinterpret_cast<const T*>(cbuf + (qi & 1u) * (ATT_CH * HD * 2));
+      const int c = pw + (s - n_my) * P;
+      int keys = ctx - c * ATT_CH;
+      keys = keys > ATT_CH ? ATT_CH : keys;
+      for (int jl = g2; jl < keys; jl += 2) {
+        const Vec8<T> vv = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + D);
+        const float pj = Tr<T>::rr(expf(Tr<T>::f(sc[c * ATT_CH + jl]) - mx) / sum);      // softmax(fp32).to(dtype)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, Tr<T>::f(vv.v[e]), acc[e]);
+      }
+      __syncwarp();
+      if (lane == 0 && s + 2 < 2 * n_my) issue(s + 2);
+    }
+    if (pw == 0 && g2 == 0) {
+      const float pj = Tr<T>::rr(expf(Tr<T>::f(sc[ctx]) - mx) / sum);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vn[e], acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += __shfl_down_sync(0xffffffffu, acc[e], 16);
+    if (P > 1) {
+      if (pw != 0 && lane < 16) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pacc[D + e] = acc[e];
+      }
+      team_bar(team, P * 32);
+      if (pw == 0 && lane < 16) {
+        for (int i = 1; i < P; ++i) {
+          const float* pa = reinterpret_cast<const float*>(scratch + (size_t)(team * P + i) * ATT_WARP_BYTES);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += pa[D + e];
+        }
+      }
+    }
+    if (pw == 0 && lane < 16) {
+      Vec8<T> o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o.v[e] = Tr<T>::r(acc[e]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.att) + (int64_t)b * H + h * HD + D) = *reinterpret_cast<const uint4*>(&o);
+    }
+    seq += (uint32_t)(2 * n_my);
+    if (P > 1) team_bar(team, P * 32);           // partial accumulators / scores are free for the next item
+    else __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(THREADS, 1)
+decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_att,
+                   const __grid_constant__ CUtensorMap map_mid, const MegaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* wring = smem;
+  uint8_t* xring = smem + SW * W_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_RING);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = w_full + SW;
+  uint64_t* x_full = w_empty + SW;
+  uint64_t* x_empty = x_full + SX;
+  uint64_t* xn_full = x_empty + SX;
+  uint64_t* acc_full = xn_full + SX;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint64_t* att_bar = acc_empty + NACC;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(att_bar + 2 * WORK_WARPS);
+  uint32_t* s_flag = tmem_ptr_smem + 1;
+  float* s_rstd = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_ssq = s_rstd + 32;            // [4][32]
+  float* s_red = s_ssq + 4 * 32;         // [WORK_WARPS][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+  const int KB_H = p.H / BK, KB_I = p.I / BK;
+  const Sched* __restrict__ sched = p.sched;
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < SX; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&xn_full[i], WORKERS); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], WORKERS); }
+    for (int i = 0; i < 2 * WORK_WARPS; ++i) mbar_init(&att_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== weight producer: never waits on anything but a free ring slot =====================
+    if (lane == 0) {
+      uint32_t wi = 0;
+      for (int l = p.l0; l < p.l1; ++l) {
+        for (int g = 0; g < 4; ++g) {
+          const CUtensorMap* map = p.wmaps + l * 4 + g;
+          const int ns = sched->nseg[g][cta];
+          for (int s = 0; s < ns; ++s) {
+            const Seg sg = sched->seg[g][cta][s];
+            const int row = sg.tile * TILE_N;
+            for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+              const int reps = g == G_GU ? 2 : 1;
+              for (int r = 0; r < reps; ++r) {
+                const uint32_t slot = wi % SW;
+                mbar_wait(&w_empty[slot], ((wi / SW) & 1u) ^ 1u, 1);
+                mbar_expect_tx(&w_full[slot], W_SLOT);
+                tma_load_2d(wring + slot * W_SLOT, map, &w_full[slot], kb * BK, r == 0 ? row : p.I + row, HINT_EVICT_FIRST);
+                ++wi;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(Tr<T>::umma_fmt, TILE_N, NT);
+      uint32_t wi = 0, xi = 0, sc = 0, xn_par = 0;
+      for (int l = p.l0; l < p.l1; ++l) {
+        for (int g = 0; g < 4; ++g) {
+          const bool norm = (g == G_QKV || g == G_GU), gu = (g == G_GU);
+          const int ns = sched->nseg[g][cta];
+          for (int s = 0; s < ns; ++s) {
+            const Seg sg = sched->seg[g][cta][s];
+            const uint32_t a = sc % NACC;
+            mbar_wait(&acc_empty[a], ((sc / NACC) & 1u) ^ 1u, 2);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + a * ACC_COLS;
+            for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+              const uint32_t ws0 = wi % SW;
+              mbar_wait(&w_full[ws0], (wi / SW) & 1u, 3);
+              ++wi;
+              uint32_t ws1 = 0;
+              if (gu) {
+                ws1 = wi % SW;
+                mbar_wait(&w_full[ws1], (wi / SW) & 1u, 4);
+                ++wi;
+              }
+              const uint32_t xs = xi % SX;
+              if (norm) {
+                mbar_wait(&xn_full[xs], (xn_par >> xs) & 1u, 5);
+                xn_par ^= 1u << xs;
+              } else {
+                mbar_wait(&x_full[xs], (xi / SX) & 1u, 6);
+              }
+              ++xi;
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(wring + ws0 * W_SLOT);
+              const uint32_t u_addr = smem_u32(wring + ws1 * W_SLOT);
+              const uint32_t b_addr = smem_u32(xring + xs * X_SLOT);
+              const uint64_t da = make_smem_desc(a_addr), du = make_smem_desc(u_addr), db = make_smem_desc(b_addr);
+#pragma unroll
+              for (int k = 0; k < BK / UK; ++k) {
+                const uint32_t accf = (kb > sg.kb0 || k > 0) ? 1u : 0u;
+                const uint64_t koff = (uint64_t)((k * UK * 2) >> 4);
+                tc_mma_f16(d0, da + koff, db + koff, idesc, accf);
+                if (gu) tc_mma_f16(d0 + NT, du + koff, db + koff, idesc, accf);
+              }
+              tc_commit(&w_empty[ws0]);
+              if (gu) tc_commit(&w_empty[ws1]);
+              tc_commit(&x_empty[xs]);
+            }
+            tc_commit(&acc_full[a]);
+            ++sc;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== activation producer =====================
+    if (lane == 0) {
+      pdl_wait();
+      uint32_t xi = 0;
+      for (int l = p.l0; l < p.l1; ++l) {
+        for (int g = 0; g < 4; ++g) {
+          const int ns = sched->nseg[g][cta];
+          if (ns == 0) continue;
+          grid_wait(p.sync, (uint32_t)phase_epoch(l - p.l0, g) * (uint32_t)p.G, 10 + g);
+          fence_proxy_async_all();
+          const CUtensorMap* map = (g == G_QKV || g == G_GU) ? &map_x : (g == G_O ? &map_att : &map_mid);
+          for (int s = 0; s < ns; ++s) {
+            const Seg sg = sched->seg[g][cta][s];
+            for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+              const uint32_t slot = xi % SX;
+              mbar_wait(&x_empty[slot], ((xi / SX) & 1u) ^ 1u, 7);
+              mbar_expect_tx(&x_full[slot], X_SLOT);
+              tma_load_2d(xring + slot * X_SLOT, map, &x_full[slot], kb * BK, 0, HINT_EVICT_LAST);
+              ++xi;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== workers =====================
+    pdl_wait();
+    const int ww = warp - 4, wtid = threadIdx.x - 128;
+    const int quad = warp & 3;
+    const int col0 = ww >= 4 ? 16 : 0;
+    const int n_local = quad * 32 + lane;
+    const int B = p.B, H = p.H;
+    T* xg = reinterpret_cast<T*>(p.x);
+    uint32_t xi = 0, sc = 0, att_seq = 0, epoch = 0;
+    uint32_t* tile_ctr = p.sync + 32;
+
+    for (int l = p.l0; l < p.l1; ++l) {
+      const LayerDev L = p.lay[l];
+      for (int ph = 0; ph < 5; ++ph) {
+        // wait for the previous phase of the whole grid
+        if (wtid == 0) grid_wait(p.sync, epoch * (uint32_t)p.G, 20 + ph);
+        worker_bar();
+        if (ph == 1) {
+          attention_items<T>(p, L, cta, ww, lane, xring, att_bar, s_red, att_seq);
+        } else {
+          const int g = ph == 0 ? G_QKV : ph - 1;
+          const bool norm = (g == G_QKV || g == G_GU), gu = (g == G_GU);
+          const int ns = sched->nseg[g][cta];
+          int n_x = 0;
+          for (int s = 0; s < ns; ++s) n_x += sched->seg[g][cta][s].kb1 - sched->seg[g][cta][s].kb0;
+          if (norm && ns > 0) {
+            // ---- RMSNorm statistics: rstd[j] = rsqrt(mean(x_j^2) + eps), fp32 (modeling_llama_imgemb.py:85-93) ----
+            if (g == G_QKV && l == p.l0) {
+              for (int j = ww; j < B; j += WORK_WARPS) {
+                float ss = 0.f;
+                for (int k = lane * 8; k < H; k += 256) {
+                  const Vec8<T> v = ldcg16(xg + (int64_t)j * H + k);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) { const float f = Tr<T>::f(v.v[e]); ss = fmaf(f, f, ss); }
+                }
+                ss = warp_sum(ss);
+                if (lane == 0) s_rstd[j] = 1.0f / sqrtf(ss / (float)H + p.eps);
+              }
+            } else if (wtid < B) {
+              float tot = 0.f;
+              const int nt = H / TILE_N;
+              for (int t = 0; t < nt; ++t) tot += __ldcg(p.ssq + t * 32 + wtid);
+              s_rstd[wtid] = 1.0f / sqrtf(tot / (float)H + p.eps);
+            }
+            worker_bar();
+            // ---- normalise the token tiles in place: xn = T(w * T(x * rstd)) ----
+            const T* lnw = reinterpret_cast<const T*>(g == G_QKV ? L.ln1 : L.ln2);
+            const int r = wtid >> 3, pc = wtid & 7, c = pc ^ (r & 7);
+            const float rs = r < B ? s_rstd[r] : 0.f;
+            for (int s = 0; s < ns; ++s) {
+              const Seg sg = sched->seg[g][cta][s];
+              for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+                const uint32_t slot = xi % SX;
+                mbar_wait(&x_full[slot], (xi / SX) & 1u, 30);
+                ++xi;
+                if (r < B) {
+                  uint4* cp = reinterpret_cast<uint4*>(xring + slot * X_SLOT + r * 128 + pc * 16);
+                  uint4 raw = *cp;
+                  const Vec8<T> xv = *reinterpret_cast<const Vec8<T>*>(&raw);
+                  const Vec8<T> wv = ld16(lnw + kb * BK + c * 8);
+                  Vec8<T> o;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float y = Tr<T>::rr(Tr<T>::f(xv.v[e]) * rs);
+                    o.v[e] = Tr<T>::r(Tr<T>::f(wv.v[e]) * y);
+                  }
+                  *cp = *reinterpret_cast<const uint4*>(&o);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&xn_full[slot]);
+              }
+            }
+          } else {
+            xi += (uint32_t)n_x;
+          }
+          // ---- epilogues of this CTA's segments ----
+          for (int s = 0; s < ns; ++s) {
+            const Seg sg = sched->seg[g][cta][s];
+            const uint32_t a = sc % NACC;
+            mbar_wait(&acc_full[a], (sc / NACC) & 1u, 31);
+            ++sc;
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + a * ACC_COLS + col0 + ((uint32_t)(quad * 32) << 16);
+            uint32_t r0[16], r1[16];
+            tc_ld16(taddr, r0);
+            if (gu) tc_ld16(taddr + NT, r1);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&acc_empty[a]);
+            float acc[16], accu[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { acc[j] = __uint_as_float(r0[j]); accu[j] = gu ? __uint_as_float(r1[j]) : 0.f; }
+            bool finalise = true;
+            if (sg.nsplits > 1) {
+              float* part = p.ws + ((int64_t)sg.tile * MAX_SPLIT + sg.split) * PART_STRIDE;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (col0 + j < B) {
+                  __stcg(part + (col0 + j) * TILE_N + n_local, acc[j]);
+                  if (gu) __stcg(part + (NT + col0 + j) * TILE_N + n_local, accu[j]);
+                }
+              }
+              __threadfence();
+              worker_bar();
+              if (wtid == 0) {
+                const uint32_t prev = atomicAdd(tile_ctr + sg.tile, 1u);
+                const uint32_t last = (prev == (uint32_t)sg.nsplits - 1) ? 1u : 0u;
+                if (last) tile_ctr[sg.tile] = 0;          // re-arm for the next phase that uses this tile index
+                *s_flag = last;
+              }
+              worker_bar();
+              finalise = *s_flag != 0;
+              if (finalise) {
+                __threadfence();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { acc[j] = 0.f; accu[j] = 0.f; }
+                for (int sp = 0; sp < sg.nsplits; ++sp) {       // fixed split order: deterministic
+                  const float* ps = p.ws + ((int64_t)sg.tile * MAX_SPLIT + sp) * PART_STRIDE;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    if (col0 + j < B) {
+                      acc[j] += __ldcg(ps + (col0 + j) * TILE_N + n_local);
+                      if (gu) accu[j] += __ldcg(ps + (NT + col0 + j) * TILE_N + n_local);
+                    }
+                  }
+                }
+              }
+              worker_bar();                               // s_flag may be rewritten by the next segment
+            }
+            if (finalise) {
+              const int n = sg.tile * TILE_N + n_local;
+              if (g == G_QKV) {
+                if (n < p.n_qkv) {
+                  T* o = reinterpret_cast<T*>(p.qkv) + n;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (col0 + j < B) o[(int64_t)(col0 + j) * p.ldq] = Tr<T>::r(acc[j]);
+                }
+              } else if (g == G_GU) {
+                if (n < p.I) {
+                  T* o = reinterpret_cast<T*>(p.mid) + n;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    if (col0 + j < B) {
+                      const float gg = Tr<T>::rr(acc[j]), uu = Tr<T>::rr(accu[j]);
+                      o[(int64_t)(col0 + j) * p.I] = Tr<T>::r(Tr<T>::rr(silu_f(gg)) * uu);     // T(T(silu(T(g))) * T(u))
+                    }
+                  }
+                }
+              } else {
+                // o_proj / down_proj: residual add in the storage dtype + sum of squares of the new residual stream
+                float res[16], yy[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) res[j] = (col0 + j < B && n < H) ? Tr<T>::f(ldcg_t(xg + (int64_t)(col0 + j) * H + n)) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  yy[j] = 0.f;
+                  if (col0 + j < B && n < H) {
+                    const T y = Tr<T>::r(res[j] + Tr<T>::rr(acc[j]));
+                    xg[(int64_t)(col0 + j) * H + n] = y;
+                    const float f = Tr<T>::f(y);
+                    yy[j] = f * f;
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float t = warp_sum(yy[j]);
+                  if (lane == 0) s_ssq[quad * 32 + col0 + j] = t;
+                }
+                worker_bar();
+                if (wtid < B) __stcg(p.ssq + sg.tile * 32 + wtid, s_ssq[wtid] + s_ssq[32 + wtid] + s_ssq[64 + wtid] + s_ssq[96 + wtid]);
+                worker_bar();
+              }
+            }
+          }
+        }
+        // arrive at the grid barrier that closes this phase
+        worker_bar();
+        if (wtid == 0) {
+          __threadfence();
+          atomicAdd(p.sync, 1u);
+        }
+        ++epoch;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+  if (threadIdx.x == 0) {
+    // the last CTA to leave re-arms the counters for the next launch (nobody polls them any more)
+    const uint32_t prev = atomicAdd(p.sync + 1, 1u);
+    if (prev == (uint32_t)p.G - 1) {
+      p.sync[0] = 0;
+      p.sync[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+int make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int box_rows, int dtype) {
+  PFN_encodeTiled enc = get_encode();
+  RD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == RD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                   gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RD_REQUIRE(r == CUDA_SUCCESS, "decode_mega: cuTensorMapEncodeTiled failed (%d) ptr=%p ld=%lld rows=%d K=%d", (int)r, ptr, (long long)ld, rows, K);
+  return RD_OK;
+}
+
+// Deal the (tile, k-block) units of one GEMM phase to `G` CTAs in contiguous, equal runs.  Returns false if the split
+// would need more than MAX_SEG segments per CTA or MAX_SPLIT contributors per tile.
+bool build_phase(Sched* sc, int g, int tiles, int kb, int G, int G_all) {
+  for (int c = 0; c < G_all; ++c) sc->nseg[g][c] = 0;
+  const long long U = (long long)tiles * kb;
+  std::vector<int> per_tile(tiles, 0);
+  for (int c = 0; c < G; ++c) {
+    long long u0 = U * c / G, u1 = U * (c + 1) / G;
+    while (u0 < u1) {
+      const int t = (int)(u0 / kb), k0 = (int)(u0 % kb);
+      const int k1 = (int)((u1 - u0) < (kb - k0) ? k0 + (u1 - u0) : kb);
+      int& n = sc->nseg[g][c];
+      if (n >= MAX_SEG) return false;
+      Seg& s = sc->seg[g][c][n++];
+      s.tile = t; s.kb0 = k0; s.kb1 = k1; s.split = per_tile[t]++; s.nsplits = 0;
+      u0 += k1 - k0;
+    }
+  }
+  for (int t = 0; t < tiles; ++t) if (per_tile[t] > MAX_SPLIT) return false;
+  for (int c = 0; c < G; ++c)
+    for (int i = 0; i < sc->nseg[g][c]; ++i) sc->seg[g][c][i].nsplits = per_tile[sc->seg[g][c][i].tile];
+  return true;
+}
+
+}  // namespace
+
+struct rd_mega {
+  MegaCreate c;
+  int G = 0, n_qkv = 0;
+  CUtensorMap* wmaps = nullptr;
+  LayerDev* lay = nullptr;
+  Sched* sched = nullptr;
+  float *ws = nullptr, *ssq = nullptr;
+  uint32_t* sync = nullptr;
+};
+
+const char* rd_mega_unsupported_reason(const MegaCreate* c) {
+  if (!c) return "null config";
+  if (c->H % 128 != 0) return "hidden size is not a multiple of 128";
+  if (c->I % 64 != 0) return "intermediate size is not a multiple of 64";
+  if (c->H / c->nh != 128) return "head_dim != 128";
+  if (c->lora_r > 16) return "lora_r > 16";
+  if (c->cmax > ATT_MAX_CTX + 1) return "max_ctx > 1024";
+  if (c->H / 128 > 480) return "hidden size too large";
+  return nullptr;
+}
+
+int rd_mega_create(const MegaCreate* c, const MegaLayerDesc* layers, rd_mega** out) {
+  RD_REQUIRE(c && layers && out, "rd_mega_create: null argument");
+  const char* why = rd_mega_unsupported_reason(c);
+  RD_REQUIRE(why == nullptr, "rd_mega_create: %s", why);
+  int dev = 0, sms = 0;
+  RD_CHECK_CUDA(cudaGetDevice(&dev));
+  RD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  rd_mega* m = new rd_mega();
+  m->c = *c;
+  m->G = sms < MAX_G ? sms : MAX_G;
+  if (const char* e = getenv("RD_MEGA_CTAS")) { const int g = atoi(e); if (g > 0 && g < m->G) m->G = g; }
+  m->n_qkv = 3 * c->H + 2 * c->lora_r;
+  const int H = c->H, I = c->I;
+  // schedule
+  std::vector<Sched> hs(1);
+  Sched* sc = &hs[0];
+  memset(sc, 0, sizeof(Sched));
+  const int tiles[4] = {(m->n_qkv + TILE_N - 1) / TILE_N, H / TILE_N, (I + TILE_N - 1) / TILE_N, H / TILE_N};
+  const int kbs[4] = {H / BK, H / BK, H / BK, I / BK};
+  int max_tiles = 0;
+  for (int g = 0; g < 4; ++g) {
+    max_tiles = tiles[g] > max_tiles ? tiles[g] : max_tiles;
+    const long long U = (long long)tiles[g] * kbs[g];
+    int Gp = (int)(U / 8 > 0 ? U / 8 : 1);          // at least ~8 k-blocks per active CTA
+    Gp = Gp > m->G ? m->G : Gp;
+    while (Gp > 1 && !build_phase(sc, g, tiles[g], kbs[g], Gp, m->G)) --Gp;
+    if (Gp == 1 && !build_phase(sc, g, tiles[g], kbs[g], 1, m->G)) {
+      delete m;
+      rd_set_error("rd_mega_create: cannot schedule GEMM phase %d (%d tiles x %d k-blocks)", g, tiles[g], kbs[g]);
+      return RD_ERR_UNSUPPORTED;
+    }
+  }
+  // tensor maps of the weights
+  std::vector<CUtensorMap> hm((size_t)c->layers * 4);
+  std::vector<LayerDev> hl(c->layers);
+  for (int l = 0; l < c->layers; ++l) {
+    const MegaLayerDesc& d = layers[l];
+    int r = make_map(&hm[l * 4 + G_QKV], d.qkv, H, m->n_qkv, H, TILE_N, c->dtype);
+    if (r == RD_OK) r = make_map(&hm[l * 4 + G_O], d.o, H, H, H, TILE_N, c->dtype);
+    if (r == RD_OK) r = make_map(&hm[l * 4 + G_GU], d.gate_up, H, 2 * I, H, TILE_N, c->dtype);
+    if (r == RD_OK) r = make_map(&hm[l * 4 + G_DN], d.down, I, H, I, TILE_N, c->dtype);
+    if (r != RD_OK) { delete m; return r; }
+    hl[l].ln1 = d.ln1; hl[l].ln2 = d.ln2; hl[l].lora_b = d.lora_b; hl[l].kc = d.kc; hl[l].vc = d.vc;
+  }
+  auto fail = [&](cudaError_t e) { rd_set_error("rd_mega_create: CUDA error %s", cudaGetErrorString(e)); rd_mega_destroy(m); return RD_ERR_CUDA; };
+  cudaError_t e;
+  if ((e = cudaMalloc((void**)&m->wmaps, hm.size() * sizeof(CUtensorMap))) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpy(m->wmaps, hm.data(), hm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void**)&m->lay, hl.size() * sizeof(LayerDev))) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpy(m->lay, hl.data(), hl.size() * sizeof(LayerDev), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void**)&m->sched, sizeof(Sched))) != cudaSuccess) return fail(e);
+  if ((e = cudaMemcpy(m->sched, sc, sizeof(Sched), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
+  const size_t ws_bytes = (size_t)max_tiles * MAX_SPLIT * PART_STRIDE * 4;
+  if ((e = cudaMalloc((void**)&m->ws, ws_bytes)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc((void**)&m->ssq, (size_t)(H / TILE_N) * 32 * 4)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(m->ssq, 0, (size_t)(H / TILE_N) * 32 * 4)) != cudaSuccess) return fail(e);
+  const size_t sync_bytes = (size_t)(32 + max_tiles + 32) * 4;
+  if ((e = cudaMalloc((void**)&m->sync, sync_bytes)) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(m->sync, 0, sync_bytes)) != cudaSuccess) return fail(e);
+  *out = m;
+  return RD_OK;
+}
+
+void rd_mega_destroy(rd_mega* m) {
+  if (!m) return;
+  void* ptrs[] = {m->wmaps, m->lay, m->sched, m->ws, m->ssq, m->sync};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete m;
+}
+
+template <class T>
+static int launch_mega(rd_mega* m, const MegaStep* s, cudaStream_t st) {
+  const MegaCreate& c = m->c;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RD_CHECK_CUDA(cudaFuncSetAttribute(decode_mega_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap map_x, map_att, map_mid;
+  RD_CHECK(make_map(&map_x, s->x, c.H, s->B, c.H, NT, c.dtype));
+  RD_CHECK(make_map(&map_att, s->att, c.H, s->B, c.H, NT, c.dtype));
+  RD_CHECK(make_map(&map_mid, s->mid, c.I, s->B, c.I, NT, c.dtype));
+  MegaParams p{};
+  p.wmaps = m->wmaps; p.lay = m->lay; p.sched = m->sched;
+  p.x = s->x; p.qkv = s->qkv; p.att = s->att; p.mid = s->mid;
+  p.ws = m->ws; p.ssq = m->ssq; p.sync = m->sync;
+  p.keymask = s->keymask; p.ctx_len = s->ctx_len; p.pos = s->pos; p.cos_t = s->cos; p.sin_t = s->sin;
+  p.B = s->B; p.H = c.H; p.I = c.I; p.nh = c.nh; p.n_qkv = m->n_qkv; p.ldq = m->n_qkv; p.cmax = c.cmax; p.lora_r = c.lora_r;
+  p.l0 = s->layer_begin; p.l1 = s->layer_end; p.G = m->G;
+  p.lora_scale = c.lora_scale; p.eps = c.eps;
+  // warps per (sequence, head): as many as keeps every item in one round
+  const int items = s->B * c.nh;
+  int P = 8;
+  while (P > 1 && (WORK_WARPS / P) * m->G < items) P >>= 1;
+  p.att_P = P;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(m->G); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = rd_pdl_enabled() ? 1 : 0;
+  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T>, map_x, map_att, map_mid, p));
+  return RD_OK;
+}
+
+int rd_mega_launch(rd_mega* m, const MegaStep* s, cudaStream_t st) {
+  RD_REQUIRE(m && s, "rd_mega_launch: null argument");
+  RD_REQUIRE(s->B > 0 && s->B <= NT && s->B <= m->c.max_batch, "rd_mega_launch: B=%d out of range (1..%d)", s->B, NT);
+  RD_REQUIRE(s->layer_begin >= 0 && s->layer_begin < s->layer_end && s->layer_end <= m->c.layers, "rd_mega_launch: bad layer range");
+  RD_DISPATCH_DTYPE(m->c.dtype, T, { return launch_mega<T>(m, s, st); });
+}

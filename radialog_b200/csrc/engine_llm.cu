@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
+#include "decode_mega.h"
 
 extern "C" int rd_attention_decode(const void*, int64_t, const int32_t*, const void*, const void*, void*, void*, const uint8_t*,
                                    const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
@@ -14,7 +15,7 @@ extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const i
 extern "C" int rd_argmax_step(const void*, int64_t, int, int64_t*, int64_t*, int64_t, int32_t*, uint8_t*, int, int32_t*,
                               int32_t*, int32_t*, int32_t*, uint32_t*, int, int, int, int, int, int, void*);
 
-enum { C_RMSNORM = 0, C_QKV, C_ROPE, C_ATTN, C_O, C_GATEUP, C_DOWN, C_LMHEAD, C_ARGMAX, C_EMBED, C_NCLASS };
+enum { C_RMSNORM = 0, C_QKV, C_ROPE, C_ATTN, C_O, C_GATEUP, C_DOWN, C_LMHEAD, C_ARGMAX, C_EMBED, C_MEGA, C_NCLASS };
 
 struct LayerW {
   const void *qkv = nullptr, *o = nullptr, *gate_up = nullptr, *down = nullptr, *ln1 = nullptr, *ln2 = nullptr,
@@ -28,6 +29,9 @@ struct rd_llm {
   const float* img_b = nullptr;
   int algo = 0;
   int esz = 2;
+  // persistent decode-layer kernel (decode_mega.cu): 1 = use it whenever the shape allows (B <= 32), 0 = per-op kernels
+  int mega_mode = 1;
+  rd_mega* mega = nullptr;
   // L2 weight prefetch from the norm / attention kernels: mechanism kept, OFF by default (A/B runs on B200 showed no
   // gain at B=32 beyond run-to-run noise and a loss at B=1, where the norm kernel is a single CTA)
   bool l2_prefetch = false;
@@ -112,12 +116,14 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
                   h->pos, h->pos_cur, h->npos, h->finished, h->ctx_len, h->n_gen, h->done_ctr, h->cur_tok, h->gen};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
+  rd_mega_destroy(h->mega);
   delete h;
 }
 
 extern "C" int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* p) {
   RD_REQUIRE(h && p, "rd_llm_set_weight: null argument");
   RD_REQUIRE(((uintptr_t)p & 15) == 0, "rd_llm_set_weight: pointer for slot %d must be 16-byte aligned", slot);
+  if (h->mega) { rd_mega_destroy(h->mega); h->mega = nullptr; }      // its tensor maps point at the old weights
   if (slot < 10) {
     switch (slot) {
       case RD_W_EMBED: h->embed = p; break;
@@ -195,6 +201,44 @@ static int linear(rd_llm* h, int cls, const void* x, int64_t ldx, const void* w,
   int algo = h->algo;
   if (algo == 1 && M > 4) algo = 3;     // forced-GEMV validation mode falls back to SIMT for wide batches
   return rd_linear(x, ldx, w, ldw, out, ldo, M, N, K, e, h->c.dtype, algo, h->ws, h->ws_bytes, st);
+}
+
+static MegaCreate mega_config(const rd_llm* h) {
+  const rd_llm_config& c = h->c;
+  MegaCreate mc{};
+  mc.H = c.hidden; mc.I = c.inter; mc.nh = c.heads; mc.layers = c.layers; mc.lora_r = c.lora_r > 0 ? c.lora_r : 0; mc.dtype = c.dtype;
+  mc.max_batch = c.max_batch; mc.cmax = c.max_ctx; mc.lora_scale = c.lora_scale; mc.eps = c.rms_eps;
+  return mc;
+}
+
+// whether single-token steps of B rows go through the persistent kernel
+static bool mega_wanted(const rd_llm* h, int B) {
+  if (!h->mega_mode || h->algo != 0 || B > 32) return false;
+  const MegaCreate mc = mega_config(h);
+  return rd_mega_unsupported_reason(&mc) == nullptr;
+}
+
+// builds the persistent kernel's tables (tensor maps of all layer weights, work schedule); allocates, so it must not
+// run inside a stream capture - prefill / extend call it ahead of the first decode step
+static int mega_ensure(rd_llm* h) {
+  if (h->mega) return RD_OK;
+  const MegaCreate mc = mega_config(h);
+  std::vector<MegaLayerDesc> d(h->c.layers);
+  for (int l = 0; l < h->c.layers; ++l) {
+    const LayerW& w = h->L[l];
+    d[l].qkv = w.qkv; d[l].o = w.o; d[l].gate_up = w.gate_up; d[l].down = w.down; d[l].ln1 = w.ln1; d[l].ln2 = w.ln2;
+    d[l].lora_b = h->c.lora_r ? w.lora_b : nullptr;
+    d[l].kc = h->kc + (int64_t)l * h->kv_layer_bytes; d[l].vc = h->vc + (int64_t)l * h->kv_layer_bytes;
+  }
+  return rd_mega_create(&mc, d.data(), &h->mega);
+}
+
+static int run_layers_mega(rd_llm* h, int B, const int32_t* pos, cudaStream_t st) {
+  ProfScope ps(h, st, C_MEGA);
+  MegaStep s{};
+  s.x = h->x; s.qkv = h->qkv; s.att = h->att; s.mid = h->mid; s.keymask = h->keymask; s.ctx_len = h->ctx_len; s.pos = pos;
+  s.cos = h->cos; s.sin = h->sin; s.B = B; s.layer_begin = 0; s.layer_end = h->c.layers;
+  return rd_mega_launch(h->mega, &s, st);
 }
 
 // layers over M = B*q_len tokens whose embeddings are in h->x; positions in `pos`
@@ -286,6 +330,7 @@ static int extend_impl(rd_llm* h, const int64_t* ids, const void* img_embeds, in
   }
   { ProfScope ps(h, st, C_EMBED);
     RD_CHECK(rd_embed_splice(ids, h->embed, img_rows, h->x, B, T, H, c.vocab, dt, st)); }
+  if (mega_wanted(h, B)) RD_CHECK(mega_ensure(h));
   RD_CHECK(run_layers(h, B, T, h->pos, st));
   RD_CHECK(head_and_select(h, B, T, all_logits, st));
   h->ctx_host += T;
@@ -343,10 +388,20 @@ extern "C" int rd_llm_decode_step(rd_llm* h, void* stream) {
   const rd_llm_config& c = h->c;
   { ProfScope ps(h, st, C_EMBED);
     RD_CHECK(rd_embed_splice(h->cur_tok, h->embed, nullptr, h->x, h->B, 1, c.hidden, c.vocab, c.dtype, st)); }
-  RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
+  if (mega_wanted(h, h->B) && h->mega != nullptr) RD_CHECK(run_layers_mega(h, h->B, h->pos_cur, st));
+  else RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
   RD_CHECK(head_and_select(h, h->B, 1, nullptr, st));
   h->ctx_host += 1;
   h->n_generated += 1;
+  return RD_OK;
+}
+
+// 1 (default): single-token steps with B <= 32 run all layers in the persistent kernel of decode_mega.cu; 0: per-op kernels.
+// Call it outside stream capture (switching it on may allocate the kernel's tables).
+extern "C" int rd_llm_set_mega(rd_llm* h, int on) {
+  RD_REQUIRE(h, "rd_llm_set_mega: null handle");
+  h->mega_mode = on ? 1 : 0;
+  if (h->mega_mode && h->mega == nullptr && h->B > 0 && mega_wanted(h, h->B) && check_weights(h) == RD_OK) return mega_ensure(h);
   return RD_OK;
 }
 

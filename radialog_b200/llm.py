@@ -111,6 +111,7 @@ class LlamaForCausalLM:
         self._cached_ids: Optional[torch.Tensor] = None     # host copy of the ids whose KV are in the cache
         self._img_w_packed = None
         self.algo = _lib.ALGO_AUTO
+        self.mega = True
         self.use_cuda_graph = True
         self.last_stats: Dict[str, float] = {}
 
@@ -291,6 +292,7 @@ class LlamaForCausalLM:
             for key, t in lw.items():
                 _lib.check(sw(h, i, slots[key], _lib.ptr(t)), f"set_weight layer {i} {key}")
         _lib.check(self._lib.rd_llm_set_algo(h, self.algo), "set_algo")
+        _lib.check(self._lib.rd_llm_set_mega(h, 1 if self.mega else 0), "set_mega")
 
     def _bind_img_proj(self):
         lin = self.model.img_proj_layer
@@ -308,6 +310,13 @@ class LlamaForCausalLM:
         self._graphs = {}
         if self._h is not None:
             _lib.check(self._lib.rd_llm_set_algo(self._h, algo), "set_algo")
+
+    def set_mega(self, on: bool):
+        """Single-token steps through the persistent all-layers kernel (default) or one kernel per op."""
+        self.mega = bool(on)
+        self._graphs = {}
+        if self._h is not None:
+            _lib.check(self._lib.rd_llm_set_mega(self._h, 1 if on else 0), "set_mega")
 
     def _state(self):
         gen, fin, logits, hidden = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
