@@ -31,7 +31,9 @@ UNIT = "reports/s"
 T_PROMPT = 64
 W_DEC_BYTES = 13_214_695_424          # decode-step weight bytes (V=32001, 2-byte weights)
 KV_BYTES_PER_TOKEN = 524_288           # per sequence per cached token, 32 layers
-GATE_UP_BYTES = 2 * 2 * 11008 * 4096   # dominant kernel: fused gate|up weights per launch
+GATE_UP_BYTES = 2 * 2 * 11008 * 4096   # fused gate|up weights per launch (per-op path)
+LAYER_W_BYTES = 32 * 202_383_360 * 2   # the 32 decoder layers' weights, 2-byte (12,952,535,040 B)
+PROFILE_STEPS = 8
 
 
 def peaks():
@@ -257,9 +259,7 @@ def run_own_arm(args):
     out = None
     if rank == 0:
         hbm_peak, peak_src = peaks()
-        prof = llm.profile_decode_steps(B, T_PROMPT, steps=8)
-        gu_ms = prof["gate_up"]["ms"] / max(1, prof["gate_up"]["launches"])
-        gu_gbs = GATE_UP_BYTES / (gu_ms * 1e-3) / 1e9
+        roof, prof, per_op = dominant_kernel_roofline(llm, B, hbm_peak, peak_src)
         dec_ms = sum(s["decode_ms"] for s in stats) / len(stats) / (NEW - 1)
         c_mid = T_PROMPT + NEW // 2
         step_bytes = W_DEC_BYTES + B * KV_BYTES_PER_TOKEN * (c_mid + 1)
@@ -277,13 +277,12 @@ def run_own_arm(args):
             "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": imgs_host.numel() * 4 + prompts_host.numel() * 8,
                     "d2h_bytes_per_step": int(seqs.numel() * 8)},
             "gpu_launches": int(n_launch),
-            "roofline": {"kernel": "linear_tc_kernel<NT=32,SWIGLU> (gate|up projection, decode)" if B > 4 else "gemv_kernel (gate|up, decode)",
-                         "bound": "hbm", "achieved": gu_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gu_gbs / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "how": "CUDA events around each eager launch, 8 decode steps x 32 layers, after the timed region"},
+            "roofline": roof,
             "decode_step": {"ms": dec_ms, "algorithmic_bytes": step_bytes, "achieved_gbs": step_gbs, "frac_of_hbm_peak": step_gbs / hbm_peak,
                             "tokens_per_s": B / (dec_ms * 1e-3)},
             "phases_ms": {k: sum(s[k] for s in stats) / len(stats) for k in ("vision_ms", "prefill_ms", "decode_ms")},
-            "kernel_classes_ms_per_decode_step": {k: v["ms"] / 8 for k, v in prof.items()},
+            "kernel_classes_ms_per_decode_step": {k: v["ms"] / PROFILE_STEPS for k, v in prof.items()},
+            "per_op_path": per_op,
         }
     if world > 1:
         dist.barrier()
@@ -297,6 +296,33 @@ def run_own_arm(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(llm, B, hbm_peak, peak_src):
+    """Dominant kernel = decode_mega_kernel: ONE launch runs the 32 decoder layers of a decode step.  Algorithmic bytes
+    per launch = layer weights + B x (KV read of c cached tokens + KV write); duration = CUDA events around
+    each eager launch (the engine records them on the launching stream).  Also times the one-kernel-per-op path."""
+    prof = llm.profile_decode_steps(B, T_PROMPT, steps=PROFILE_STEPS)
+    n = max(1, prof["mega"]["launches"])
+    mega_ms = prof["mega"]["ms"] / n
+    c_mean = T_PROMPT + 1 + (PROFILE_STEPS - 1) / 2.0          # cached tokens seen by the profiled steps
+    mega_bytes = LAYER_W_BYTES + B * KV_BYTES_PER_TOKEN * (c_mean + 1)
+    gbs = mega_bytes / (mega_ms * 1e-3) / 1e9 if mega_ms > 0 else 0.0
+    roof = {"kernel": f"decode_mega_kernel (all 32 decoder layers of one decode step, B={B}, ctx~{int(c_mean)})", "bound": "hbm",
+            "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": int(mega_bytes), "ms_per_launch": mega_ms,
+            "how": f"CUDA events around each eager launch, {PROFILE_STEPS} decode steps, after the timed region"}
+    llm.set_mega(False)
+    try:
+        pp = llm.profile_decode_steps(B, T_PROMPT, steps=PROFILE_STEPS)
+    finally:
+        llm.set_mega(True)
+    gu_ms = pp["gate_up"]["ms"] / max(1, pp["gate_up"]["launches"])
+    per_op = {"note": "same steps with one kernel per op (rd_llm_set_mega(0)); eager launches, events around each",
+              "gate_up_gbs": GATE_UP_BYTES / (gu_ms * 1e-3) / 1e9 if gu_ms > 0 else None,
+              "gate_up_frac": GATE_UP_BYTES / (gu_ms * 1e-3) / 1e9 / hbm_peak if gu_ms > 0 else None,
+              "kernel_classes_ms_per_decode_step": {k: v["ms"] / PROFILE_STEPS for k, v in pp.items()}}
+    return roof, prof, per_op
 
 
 def bench_b1(pipe, llm, dev, new_tokens, hbm_peak):
@@ -315,11 +341,11 @@ def bench_b1(pipe, llm, dev, new_tokens, hbm_peak):
     ms = e0.elapsed_time(e1)
     dec_ms = pipe.last_stats["decode_ms"] / (new_tokens - 1)
     step_bytes = W_DEC_BYTES + KV_BYTES_PER_TOKEN * (T_PROMPT + new_tokens // 2 + 1)
-    prof = llm.profile_decode_steps(1, T_PROMPT, steps=8)
-    gu_ms = prof["gate_up"]["ms"] / max(1, prof["gate_up"]["launches"])
+    roof, _, per_op = dominant_kernel_roofline(llm, 1, hbm_peak, "")
     return {"reports_per_s": 1e3 / ms, "ms_per_report": ms, "decode_ms_per_token": dec_ms,
             "decode_step_gbs": step_bytes / (dec_ms * 1e-3) / 1e9, "decode_step_frac_of_hbm_peak": step_bytes / (dec_ms * 1e-3) / 1e9 / hbm_peak,
-            "gemv_gate_up_gbs": GATE_UP_BYTES / (gu_ms * 1e-3) / 1e9, "gemv_gate_up_frac": GATE_UP_BYTES / (gu_ms * 1e-3) / 1e9 / hbm_peak}
+            "mega_kernel_gbs": roof["achieved"], "mega_kernel_frac": roof["frac"],
+            "gemv_gate_up_gbs": per_op["gate_up_gbs"], "gemv_gate_up_frac": per_op["gate_up_frac"]}
 
 
 def main():

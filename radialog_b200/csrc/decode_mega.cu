@@ -42,23 +42,31 @@ constexpr int W_SLOT = TILE_N * BK * 2;   // 16 KB
 constexpr int X_SLOT = NT * BK * 2;       // 4 KB
 constexpr int SW = 8;                  // weight ring slots (128 KB)
 constexpr int SX = 20;                 // token-tile ring slots (80 KB); doubles as the attention scratch
-constexpr int NACC = 4, ACC_COLS = 64, TMEM_COLS = 256;
+// Accumulation chains: tcgen05.mma into ONE accumulator is a dependent chain, and at N = 32 an MMA is so short that the
+// chain runs at pipeline latency (~125 ns per MMA measured, 0.5 us per k-block).  Each segment therefore accumulates its
+// four k-steps per k-block into FOUR independent 32-column accumulators (gate|up: two each), summed in the epilogue.
+constexpr int NCHAIN = 4;
+constexpr int NACC = 2, ACC_COLS = NCHAIN * NT, TMEM_COLS = NACC * ACC_COLS;
 constexpr int WORK_WARPS = 8, WORKERS = WORK_WARPS * 32, THREADS = 128 + WORKERS;
-constexpr int MAX_G = 160, MAX_SEG = 4, MAX_SPLIT = 8;
+constexpr int MAX_G = 160, MAX_SEG = 2, MAX_SPLIT = 8;     // MAX_SEG <= NACC: a phase never waits for its own epilogues
 constexpr int PART_STRIDE = 2 * NT * TILE_N;      // floats per (tile, split) slab of the stream-K workspace
 constexpr int ATT_WARP_BYTES = SX * X_SLOT / WORK_WARPS;     // 10 KB: [scores / partial acc 2 KB][chunk 4 KB][chunk 4 KB]
 constexpr int ATT_CH = 16;             // keys per bulk-copy chunk (16 x 256 B = 4 KB)
 constexpr int ATT_MAX_CTX = 1023;      // scores of one (sequence, head) live in 2 KB of shared memory as 2-byte values
 static_assert(ATT_WARP_BYTES == 2048 + 2 * ATT_CH * 256, "attention scratch layout");
 
+struct Seg { int tile, kb0, kb1, split, nsplits, pad0, pad1, pad2; };
 constexpr int SMEM_RING = SW * W_SLOT + SX * X_SLOT;
-constexpr int N_BARS = 2 * SW + 3 * SX + 2 * NACC + 2 * WORK_WARPS;
-constexpr int SMEM_MISC = N_BARS * 8 + 16 + 32 * 4 + 4 * 32 * 4 + WORK_WARPS * 2 * 4;
+constexpr int CONS_R = 32;               // ring of "k-block consumed" barriers (one tcgen05.commit per k-block group frees its W and X slots)
+constexpr int N_BARS = SW + CONS_R + 2 * SX + 2 * NACC + 2 * WORK_WARPS;
+static_assert(CONS_R > SX && CONS_R > SW, "consumed-barrier ring must be longer than both operand rings");
+struct CtaSched { int nseg[4]; Seg seg[4][MAX_SEG]; };
+constexpr int LNW_KB = 64;                // k-blocks of RMSNorm weights staged per phase (8 KB)
+constexpr int SMEM_MISC = LNW_KB * BK * 2 + N_BARS * 8 + 16 + 32 * 4 + 8 * 32 * 4 + WORK_WARPS * 2 * 4 + (int)sizeof(CtaSched) + 64 + SW * 4;
 constexpr int SMEM_BYTES = SMEM_RING + 1024 + ((SMEM_MISC + 127) / 128) * 128;
 
 enum { G_QKV = 0, G_O = 1, G_GU = 2, G_DN = 3 };
 
-struct Seg { int tile, kb0, kb1, split, nsplits, pad0, pad1, pad2; };
 struct Sched {
   int nseg[4][MAX_G];
   Seg seg[4][MAX_G][MAX_SEG];
@@ -69,8 +77,12 @@ struct LayerDev {
   void *kc, *vc;
 };
 
+constexpr int MAX_LAYERS = 48;
+// Tensor maps of every layer's weights travel as a __grid_constant__ kernel parameter (constant bank): TMA issue from a
+// descriptor in plain global memory measured ~0.8 us per cp.async.bulk.tensor (one L2/DRAM round trip per instruction).
+struct WeightMaps { CUtensorMap m[MAX_LAYERS * 4]; };
+
 struct MegaParams {
-  const CUtensorMap* wmaps;     // [layers][4]
   const LayerDev* lay;          // [layers]
   const Sched* sched;
   void *x, *qkv, *att, *mid;
@@ -80,10 +92,27 @@ struct MegaParams {
   const uint8_t* keymask;
   const int32_t *ctx_len, *pos;
   const void *cos_t, *sin_t;
-  int B, H, I, nh, n_qkv, ldq, cmax, lora_r, l0, l1, G, att_P;
+  int B, H, I, nh, n_qkv, ldq, cmax, lora_r, l0, l1, G, att_P, sw, dbg, cb;
   float lora_scale, eps;
+  unsigned long long* trace;    // development aid: [cta][layer][phase 0..4][8] globaltimer stamps (nullptr = off)
 };
 
+__device__ __forceinline__ void trace_stamp(const MegaParams& p, int l, int ph, int ev) {
+  if (p.trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(((size_t)blockIdx.x * (p.l1 - p.l0) + (l - p.l0)) * 5 + ph) * 8 + ev] = t;
+  }
+}
+__device__ __forceinline__ int phase_of_g(int g) { return g == 0 ? 0 : g + 1; }
+
+// One lane polls the mbarrier, the rest of the warp waits at the warp barrier: hundreds of threads spinning on
+// mbarrier.try_wait saturate the SM's synchronisation unit and slow every other barrier operation of the CTA
+// (measured: the MMA issue loop ran at ~0.7 us per k-block with 256 workers polling one accumulator barrier).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int tag, int lane) {
+  if (lane == 0) mbar_wait(bar, parity, tag);
+  __syncwarp();
+}
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); }
 __device__ __forceinline__ void team_bar(int team, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(threads) : "memory");
@@ -172,13 +201,27 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
     float tq[16], tv[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { tq[i] = 0.f; tv[i] = 0.f; }
-    if (lora_r > 0) {
-      for (int i = 0; i < lora_r; ++i) { tq[i] = Tr<T>::f(ldcg_t(row + 3 * H + i)); tv[i] = Tr<T>::f(ldcg_t(row + 3 * H + lora_r + i)); }
+    if (lora_r == 8) {                           // the adapter rank of the reference (finetune.py:167): 128-bit rows
+      const Vec8<T> a = ldcg16(row + 3 * H), bb = ldcg16(row + 3 * H + 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { tq[i] = Tr<T>::f(a.v[i]); tv[i] = Tr<T>::f(bb.v[i]); }
+    } else if (lora_r > 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < lora_r) { tq[i] = Tr<T>::f(ldcg_t(row + 3 * H + i)); tv[i] = Tr<T>::f(ldcg_t(row + 3 * H + lora_r + i)); }
     }
     auto lora = [&](float y, int n_row, const float* t) {
       const T* brow = lora_b + (int64_t)n_row * lora_r;
       float sdot = 0.f;
-      for (int i = 0; i < lora_r; ++i) sdot = fmaf(Tr<T>::f(brow[i]), t[i], sdot);
+      if (lora_r == 8) {
+        const Vec8<T> bv = ld16(brow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sdot = fmaf(Tr<T>::f(bv.v[i]), t[i], sdot);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < lora_r) sdot = fmaf(Tr<T>::f(brow[i]), t[i], sdot);
+      }
       return Tr<T>::rr(y + Tr<T>::rr(p.lora_scale * Tr<T>::rr(sdot)));
     };
     const Vec8<T> cv = ld16(cos_t + (int64_t)ppos * HD + D), sv = ld16(sin_t + (int64_t)ppos * HD + D);
@@ -224,7 +267,7 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
     float lmax = -INFINITY;
     for (int s = 0; s < n_my; ++s) {
       const uint32_t qi = seq + (uint32_t)s;
-      mbar_wait(bar + (qi & 1u), (qi >> 1) & 1u, 40);
+      mbar_wait_warp(bar + (qi & 1u), (qi >> 1) & 1u, 40, lane);
       const T* buf = reinterpret_cast<const T*>(cbuf + (qi & 1u) * (ATT_CH * HD * 2));
       const int c = pw + s * P;
       int keys = ctx - c * ATT_CH;
@@ -283,7 +326,7 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int s = n_my; s < 2 * n_my; ++s) {
       const uint32_t qi = seq + (uint32_t)s;
-      mbar_wait(bar + (qi & 1u), (qi >> 1) & 1u, 41);
+      mbar_wait_warp(bar + (qi & 1u), (qi >> 1) & 1u, 41, lane);
       const T* buf = reinterpret_cast<const T*>(cbuf + (qi & 1u) * (ATT_CH * HD * 2));
       const int c = pw + (s - n_my) * P;
       int keys = ctx - c * ATT_CH;
@@ -334,35 +377,42 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
 template <class T>
 __global__ void __launch_bounds__(THREADS, 1)
 decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_att,
-                   const __grid_constant__ CUtensorMap map_mid, const MegaParams p) {
+                   const __grid_constant__ CUtensorMap map_mid, const __grid_constant__ WeightMaps wmaps, const MegaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wring = smem;
   uint8_t* xring = smem + SW * W_SLOT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_RING);
+  uint8_t* s_lnw = smem + SMEM_RING;                     // [LNW_KB][64] RMSNorm weights of this CTA's k-blocks (norm phases)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_RING + LNW_KB * BK * 2);
   uint64_t* w_full = bars;
-  uint64_t* w_empty = w_full + SW;
-  uint64_t* x_full = w_empty + SW;
-  uint64_t* x_empty = x_full + SX;
-  uint64_t* xn_full = x_empty + SX;
+  uint64_t* cons = w_full + SW;
+  uint64_t* x_full = cons + CONS_R;
+  uint64_t* xn_full = x_full + SX;
   uint64_t* acc_full = xn_full + SX;
   uint64_t* acc_empty = acc_full + NACC;
   uint64_t* att_bar = acc_empty + NACC;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(att_bar + 2 * WORK_WARPS);
   uint32_t* s_flag = tmem_ptr_smem + 1;
   float* s_rstd = reinterpret_cast<float*>(tmem_ptr_smem + 4);
-  float* s_ssq = s_rstd + 32;            // [4][32]
-  float* s_red = s_ssq + 4 * 32;         // [WORK_WARPS][2]
+  float* s_ssq = s_rstd + 32;            // [8][32]
+  float* s_red = s_ssq + 8 * 32;         // [WORK_WARPS][2]
+  CtaSched* sched = reinterpret_cast<CtaSched*>(s_red + WORK_WARPS * 2 + 2);      // this CTA's slice of the work table
+  uint32_t* s_wkb = reinterpret_cast<uint32_t*>(sched + 1);                       // [SW] k-block that consumes the tile in each W slot
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
   const int KB_H = p.H / BK, KB_I = p.I / BK;
-  const Sched* __restrict__ sched = p.sched;
 
   pdl_launch_dependents();
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + 4 * MAX_SEG) {
+    const int g = (threadIdx.x - 128) / MAX_SEG, i = (threadIdx.x - 128) % MAX_SEG;
+    sched->seg[g][i] = p.sched->seg[g][cta][i];
+    if (i == 0) sched->nseg[g] = p.sched->nseg[g][cta];
+  }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < SX; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); mbar_init(&xn_full[i], WORKERS); }
+    for (int i = 0; i < SW; ++i) mbar_init(&w_full[i], 1);
+    for (int i = 0; i < CONS_R; ++i) mbar_init(&cons[i], 1);
+    for (int i = 0; i < SX; ++i) { mbar_init(&x_full[i], 1); mbar_init(&xn_full[i], 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], WORKERS); }
     for (int i = 0; i < 2 * WORK_WARPS; ++i) mbar_init(&att_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -377,107 +427,148 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // The three control warps run their loops warp-uniformly (all 32 lanes, uniform registers) and elect one lane only for
+  // the asynchronous instruction itself: a lane-0-only loop makes ptxas wrap every UTCHMMA / UTMALDG operand in a
+  // waterfall (ELECT / R2UR.BROADCAST / BRA) and the serial instruction stream of the MMA loop, not HBM, set the pace
+  // (measured ~2000 cycles per k-block against a budget of 700).
   if (warp == 0) {
     // ===================== weight producer: never waits on anything but a free ring slot =====================
-    if (lane == 0) {
-      uint32_t wi = 0;
-      for (int l = p.l0; l < p.l1; ++l) {
-        for (int g = 0; g < 4; ++g) {
-          const CUtensorMap* map = p.wmaps + l * 4 + g;
-          const int ns = sched->nseg[g][cta];
-          for (int s = 0; s < ns; ++s) {
-            const Seg sg = sched->seg[g][cta][s];
-            const int row = sg.tile * TILE_N;
-            for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-              const int reps = g == G_GU ? 2 : 1;
-              for (int r = 0; r < reps; ++r) {
-                const uint32_t slot = wi % SW;
-                mbar_wait(&w_empty[slot], ((wi / SW) & 1u) ^ 1u, 1);
-                mbar_expect_tx(&w_full[slot], W_SLOT);
-                tma_load_2d(wring + slot * W_SLOT, map, &w_full[slot], kb * BK, r == 0 ? row : p.I + row, HINT_EVICT_FIRST);
-                ++wi;
+    uint32_t slot = 0, ki = 0, filled = 0;
+    bool first = true;
+    for (int l = p.l0; l < p.l1; ++l) {
+      for (int g = 0; g < 4; ++g) {
+        const CUtensorMap* map = &wmaps.m[l * 4 + g];
+        const int ns = sched->nseg[g];
+        first = true;
+        for (int s = 0; s < ns; ++s) {
+          const Seg sg = sched->seg[g][s];
+          const int row = sg.tile * TILE_N;
+          for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+            const int reps = g == G_GU ? 2 : 1;
+            for (int r = 0; r < reps; ++r) {
+              if (filled >= SW) {                 // the slot's previous tile must have been read by its MMAs
+                const uint32_t old = s_wkb[slot];
+                mbar_wait(&cons[old & (CONS_R - 1)], (old / CONS_R) & 1u, 1);
+              } else {
+                ++filled;
               }
+              __syncwarp();
+              if (elect_one()) {
+                s_wkb[slot] = ki;
+                if (first) trace_stamp(p, l, phase_of_g(g), 7);
+                if (p.dbg & 2) {
+                  mbar_arrive(&w_full[slot]);     // diagnostic: no weight traffic
+                } else {
+                  mbar_expect_tx(&w_full[slot], W_SLOT);
+                  tma_load_2d(wring + slot * W_SLOT, map, &w_full[slot], kb * BK, r == 0 ? row : p.I + row, HINT_EVICT_FIRST);
+                }
+              }
+              __syncwarp();
+              first = false;
+              if (++slot == SW) slot = 0;
             }
+            ++ki;
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(Tr<T>::umma_fmt, TILE_N, NT);
-      uint32_t wi = 0, xi = 0, sc = 0, xn_par = 0;
-      for (int l = p.l0; l < p.l1; ++l) {
-        for (int g = 0; g < 4; ++g) {
-          const bool norm = (g == G_QKV || g == G_GU), gu = (g == G_GU);
-          const int ns = sched->nseg[g][cta];
-          for (int s = 0; s < ns; ++s) {
-            const Seg sg = sched->seg[g][cta][s];
-            const uint32_t a = sc % NACC;
-            mbar_wait(&acc_empty[a], ((sc / NACC) & 1u) ^ 1u, 2);
-            tc_fence_after();
-            const uint32_t d0 = tmem_base + a * ACC_COLS;
-            for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-              const uint32_t ws0 = wi % SW;
-              mbar_wait(&w_full[ws0], (wi / SW) & 1u, 3);
-              ++wi;
-              uint32_t ws1 = 0;
-              if (gu) {
-                ws1 = wi % SW;
-                mbar_wait(&w_full[ws1], (wi / SW) & 1u, 4);
-                ++wi;
-              }
-              const uint32_t xs = xi % SX;
-              if (norm) {
-                mbar_wait(&xn_full[xs], (xn_par >> xs) & 1u, 5);
-                xn_par ^= 1u << xs;
-              } else {
-                mbar_wait(&x_full[xs], (xi / SX) & 1u, 6);
-              }
-              ++xi;
-              tc_fence_after();
-              const uint32_t a_addr = smem_u32(wring + ws0 * W_SLOT);
-              const uint32_t u_addr = smem_u32(wring + ws1 * W_SLOT);
-              const uint32_t b_addr = smem_u32(xring + xs * X_SLOT);
-              const uint64_t da = make_smem_desc(a_addr), du = make_smem_desc(u_addr), db = make_smem_desc(b_addr);
-#pragma unroll
-              for (int k = 0; k < BK / UK; ++k) {
-                const uint32_t accf = (kb > sg.kb0 || k > 0) ? 1u : 0u;
-                const uint64_t koff = (uint64_t)((k * UK * 2) >> 4);
-                tc_mma_f16(d0, da + koff, db + koff, idesc, accf);
-                if (gu) tc_mma_f16(d0 + NT, du + koff, db + koff, idesc, accf);
-              }
-              tc_commit(&w_empty[ws0]);
-              if (gu) tc_commit(&w_empty[ws1]);
-              tc_commit(&x_empty[xs]);
+    constexpr uint32_t idesc = make_idesc(Tr<T>::umma_fmt, TILE_N, NT);
+    const uint64_t dw0 = make_smem_desc(smem_u32(wring)), dx0 = make_smem_desc(smem_u32(xring));
+    uint32_t ws = 0, wph = 0, xs = 0, xph = 0, sc = 0, xn_par = 0, ci = 0;
+    for (int l = p.l0; l < p.l1; ++l) {
+      for (int g = 0; g < 4; ++g) {
+        const bool norm = (g == G_QKV || g == G_GU), gu = (g == G_GU);
+        const int ns = sched->nseg[g];
+        for (int s = 0; s < ns; ++s) {
+          const Seg sg = sched->seg[g][s];
+          const uint32_t a = sc % NACC;
+          mbar_wait(&acc_empty[a], ((sc / NACC) & 1u) ^ 1u, 2);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + a * ACC_COLS;
+          for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+            const uint32_t ws0 = ws;
+            mbar_wait(&w_full[ws0], wph, 3);
+            if (++ws == SW) { ws = 0; wph ^= 1u; }
+            uint32_t ws1 = ws0;
+            if (gu) {
+              ws1 = ws;
+              mbar_wait(&w_full[ws1], wph, 4);
+              if (++ws == SW) { ws = 0; wph ^= 1u; }
             }
-            tc_commit(&acc_full[a]);
-            ++sc;
+            if (norm) {
+              mbar_wait(&xn_full[xs], (xn_par >> xs) & 1u, 5);
+              xn_par ^= 1u << xs;
+            } else {
+              mbar_wait(&x_full[xs], xph, 6);
+            }
+            tc_fence_after();
+            const uint64_t da = dw0 + (uint64_t)(ws0 * (W_SLOT >> 4)), du = dw0 + (uint64_t)(ws1 * (W_SLOT >> 4));
+            const uint64_t db = dx0 + (uint64_t)(xs * (X_SLOT >> 4));
+            const uint32_t accf = kb > sg.kb0 ? 1u : 0u;
+            __syncwarp();
+            if (elect_one()) {
+              if (s == 0 && kb == sg.kb0) trace_stamp(p, l, phase_of_g(g), 4);
+              if (!(p.dbg & 4)) {
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k) {
+                  const uint64_t koff = (uint64_t)((k * UK * 2) >> 4);
+                  if (gu) {          // chains: gate k even/odd -> columns 0 / 32, up -> 64 / 96
+                    const uint32_t af = (accf || k >= 2) ? 1u : 0u;
+                    tc_mma_f16(d0 + (k & 1) * NT, da + koff, db + koff, idesc, af);
+                    tc_mma_f16(d0 + (2 + (k & 1)) * NT, du + koff, db + koff, idesc, af);
+                  } else {           // chain k -> columns 32 k
+                    tc_mma_f16(d0 + k * NT, da + koff, db + koff, idesc, accf);
+                  }
+                }
+              }
+              tc_commit(&cons[ci]);               // frees this k-block's W and X slots once the MMAs have read them
+              if (kb == sg.kb1 - 1) {
+                tc_commit(&acc_full[a]);
+                if (s == ns - 1) trace_stamp(p, l, phase_of_g(g), 5);
+              }
+            }
+            __syncwarp();
+            ci = (ci + 1) & (CONS_R - 1);
+            if (++xs == SX) { xs = 0; xph ^= 1u; }
           }
+          ++sc;
         }
       }
     }
   } else if (warp == 2) {
     // ===================== activation producer =====================
-    if (lane == 0) {
-      pdl_wait();
-      uint32_t xi = 0;
-      for (int l = p.l0; l < p.l1; ++l) {
-        for (int g = 0; g < 4; ++g) {
-          const int ns = sched->nseg[g][cta];
-          if (ns == 0) continue;
-          grid_wait(p.sync, (uint32_t)phase_epoch(l - p.l0, g) * (uint32_t)p.G, 10 + g);
-          fence_proxy_async_all();
-          const CUtensorMap* map = (g == G_QKV || g == G_GU) ? &map_x : (g == G_O ? &map_att : &map_mid);
-          for (int s = 0; s < ns; ++s) {
-            const Seg sg = sched->seg[g][cta][s];
-            for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-              const uint32_t slot = xi % SX;
-              mbar_wait(&x_empty[slot], ((xi / SX) & 1u) ^ 1u, 7);
-              mbar_expect_tx(&x_full[slot], X_SLOT);
-              tma_load_2d(xring + slot * X_SLOT, map, &x_full[slot], kb * BK, 0, HINT_EVICT_LAST);
-              ++xi;
+    pdl_wait();
+    uint32_t xi = 0, slot = 0;
+    for (int l = p.l0; l < p.l1; ++l) {
+      for (int g = 0; g < 4; ++g) {
+        const int ns = sched->nseg[g];
+        if (ns == 0) continue;
+        if (lane == 0) grid_wait(p.sync, (uint32_t)phase_epoch(l - p.l0, g) * (uint32_t)p.G, 10 + g);
+        __syncwarp();
+        fence_proxy_async_all();
+        if (lane == 0) trace_stamp(p, l, phase_of_g(g), 6);
+        const CUtensorMap* map = (g == G_QKV || g == G_GU) ? &map_x : (g == G_O ? &map_att : &map_mid);
+        for (int s = 0; s < ns; ++s) {
+          const Seg sg = sched->seg[g][s];
+          for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+            if (xi >= SX) {
+              const uint32_t old = xi - SX;
+              mbar_wait(&cons[old & (CONS_R - 1)], (old / CONS_R) & 1u, 7);
             }
+            __syncwarp();
+            if (elect_one()) {
+              if (p.dbg & 1) {
+                mbar_arrive(&x_full[slot]);       // diagnostic: no activation traffic
+              } else {
+                mbar_expect_tx(&x_full[slot], X_SLOT);
+                tma_load_2d(xring + slot * X_SLOT, map, &x_full[slot], kb * BK, 0, HINT_EVICT_LAST);
+              }
+            }
+            __syncwarp();
+            ++xi;
+            if (++slot == SX) slot = 0;
           }
         }
       }
@@ -497,17 +588,33 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     for (int l = p.l0; l < p.l1; ++l) {
       const LayerDev L = p.lay[l];
       for (int ph = 0; ph < 5; ++ph) {
+        if (ph == 0 || ph == 3) {
+          // RMSNorm weights of this CTA's k-blocks -> shared memory (constants: fetched while the grid barrier is pending)
+          const int g = ph == 0 ? G_QKV : G_GU;
+          const T* lnw = reinterpret_cast<const T*>(g == G_QKV ? L.ln1 : L.ln2);
+          const int ns = sched->nseg[g];
+          const int len0 = ns > 0 ? sched->seg[g][0].kb1 - sched->seg[g][0].kb0 : 0;
+          int n_x = 0;
+          for (int s = 0; s < ns; ++s) n_x += sched->seg[g][s].kb1 - sched->seg[g][s].kb0;
+          n_x = n_x > LNW_KB ? LNW_KB : n_x;
+          for (int idx = wtid; idx < n_x * 8; idx += WORKERS) {
+            const int i = idx >> 3, c = idx & 7;
+            const int kb = i < len0 ? sched->seg[g][0].kb0 + i : sched->seg[g][1].kb0 + (i - len0);
+            *reinterpret_cast<uint4*>(s_lnw + (size_t)idx * 16) = *reinterpret_cast<const uint4*>(lnw + kb * BK + c * 8);
+          }
+        }
         // wait for the previous phase of the whole grid
         if (wtid == 0) grid_wait(p.sync, epoch * (uint32_t)p.G, 20 + ph);
         worker_bar();
+        if (wtid == 0) trace_stamp(p, l, ph, 0);
         if (ph == 1) {
           attention_items<T>(p, L, cta, ww, lane, xring, att_bar, s_red, att_seq);
         } else {
           const int g = ph == 0 ? G_QKV : ph - 1;
           const bool norm = (g == G_QKV || g == G_GU), gu = (g == G_GU);
-          const int ns = sched->nseg[g][cta];
+          const int ns = sched->nseg[g];
           int n_x = 0;
-          for (int s = 0; s < ns; ++s) n_x += sched->seg[g][cta][s].kb1 - sched->seg[g][cta][s].kb0;
+          for (int s = 0; s < ns; ++s) n_x += sched->seg[g][s].kb1 - sched->seg[g][s].kb0;
           if (norm && ns > 0) {
             // ---- RMSNorm statistics: rstd[j] = rsqrt(mean(x_j^2) + eps), fp32 (modeling_llama_imgemb.py:85-93) ----
             if (g == G_QKV && l == p.l0) {
@@ -521,28 +628,43 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 ss = warp_sum(ss);
                 if (lane == 0) s_rstd[j] = 1.0f / sqrtf(ss / (float)H + p.eps);
               }
-            } else if (wtid < B) {
-              float tot = 0.f;
-              const int nt = H / TILE_N;
-              for (int t = 0; t < nt; ++t) tot += __ldcg(p.ssq + t * 32 + wtid);
-              s_rstd[wtid] = 1.0f / sqrtf(tot / (float)H + p.eps);
+            } else {
+              // fixed-order sum of the per-tile partials the o_proj / down_proj epilogues left in L2
+              const int j = wtid & 31, part = wtid >> 5, nt = H / TILE_N;
+              float v = 0.f;
+#pragma unroll 4
+              for (int t = part; t < nt; t += 8) v += __ldcg(p.ssq + t * 32 + j);
+              s_ssq[part * 32 + j] = v;
+              worker_bar();
+              if (wtid < B) {
+                float tot = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tot += s_ssq[q * 32 + wtid];
+                s_rstd[wtid] = 1.0f / sqrtf(tot / (float)H + p.eps);
+              }
             }
             worker_bar();
             // ---- normalise the token tiles in place: xn = T(w * T(x * rstd)) ----
             const T* lnw = reinterpret_cast<const T*>(g == G_QKV ? L.ln1 : L.ln2);
-            const int r = wtid >> 3, pc = wtid & 7, c = pc ^ (r & 7);
-            const float rs = r < B ? s_rstd[r] : 0.f;
+            // Each warp owns every 8th tile and transforms it alone (wait / 8 rounds of 32 chunks / fence / arrive), so the
+            // eight latency chains run in parallel instead of all 256 threads serialising on every tile.
+            int it = 0;
             for (int s = 0; s < ns; ++s) {
-              const Seg sg = sched->seg[g][cta][s];
-              for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-                const uint32_t slot = xi % SX;
-                mbar_wait(&x_full[slot], (xi / SX) & 1u, 30);
+              const Seg sg = sched->seg[g][s];
+              for (int kb = sg.kb0; kb < sg.kb1; ++kb, ++it) {
+                const uint32_t slot = xi % SX, par = (xi / SX) & 1u;
                 ++xi;
-                if (r < B) {
+                if ((it & (WORK_WARPS - 1)) != ww) continue;
+                mbar_wait_warp(&x_full[slot], par, 30, lane);
+                const int pc = lane & 7;
+#pragma unroll 2
+                for (int r = lane >> 3; r < B; r += 4) {
+                  const int c = pc ^ (r & 7);
+                  const float rs = s_rstd[r];
                   uint4* cp = reinterpret_cast<uint4*>(xring + slot * X_SLOT + r * 128 + pc * 16);
                   uint4 raw = *cp;
                   const Vec8<T> xv = *reinterpret_cast<const Vec8<T>*>(&raw);
-                  const Vec8<T> wv = ld16(lnw + kb * BK + c * 8);
+                  const Vec8<T> wv = it < LNW_KB ? *reinterpret_cast<const Vec8<T>*>(s_lnw + (size_t)(it * 8 + c) * 16) : ld16(lnw + kb * BK + c * 8);
                   Vec8<T> o;
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
@@ -552,31 +674,50 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                   *cp = *reinterpret_cast<const uint4*>(&o);
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(&xn_full[slot]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xn_full[slot]);
               }
             }
           } else {
             xi += (uint32_t)n_x;
           }
+          if (wtid == 0) trace_stamp(p, l, ph, 1);
           // ---- epilogues of this CTA's segments ----
           for (int s = 0; s < ns; ++s) {
-            const Seg sg = sched->seg[g][cta][s];
+            const Seg sg = sched->seg[g][s];
             const uint32_t a = sc % NACC;
-            mbar_wait(&acc_full[a], (sc / NACC) & 1u, 31);
+            if (wtid == 0) mbar_wait(&acc_full[a], (sc / NACC) & 1u, 31);
+            worker_bar();
+            if (wtid == 0 && s == 0) trace_stamp(p, l, ph, 2);
             ++sc;
             tc_fence_after();
             const uint32_t taddr = tmem_base + a * ACC_COLS + col0 + ((uint32_t)(quad * 32) << 16);
-            uint32_t r0[16], r1[16];
-            tc_ld16(taddr, r0);
-            if (gu) tc_ld16(taddr + NT, r1);
-            tc_wait_ld();
+            float acc[16], accu[16];
+            {
+              uint32_t r0[16], r1[16];
+              tc_ld16(taddr, r0);
+              tc_ld16(taddr + NT, r1);
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+              tc_ld16(taddr + 2 * NT, r0);
+              tc_ld16(taddr + 3 * NT, r1);
+              tc_wait_ld();
+              if (gu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) accu[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { acc[j] = (acc[j] + __uint_as_float(r0[j])) + __uint_as_float(r1[j]); accu[j] = 0.f; }
+              }
+            }
             tc_fence_before();
             mbar_arrive(&acc_empty[a]);
-            float acc[16], accu[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { acc[j] = __uint_as_float(r0[j]); accu[j] = gu ? __uint_as_float(r1[j]) : 0.f; }
+            // Stream-K fix-up with a FIXED finaliser: the CTA that holds the head of the tile's k range (split 0; it is that
+            // CTA's last segment, so it finishes when the phase ends) sums the other contributors' fp32 partials from L2 onto
+            // its own accumulator, in split order (deterministic).  Contributors only publish and move on.
             bool finalise = true;
-            if (sg.nsplits > 1) {
+            if (sg.nsplits > 1 && sg.split != 0) {
               float* part = p.ws + ((int64_t)sg.tile * MAX_SPLIT + sg.split) * PART_STRIDE;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -587,30 +728,33 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
               }
               __threadfence();
               worker_bar();
+              if (wtid == 0) atomicAdd(tile_ctr + sg.tile, 1u);
+              finalise = false;
+            } else if (sg.nsplits > 1) {
               if (wtid == 0) {
-                const uint32_t prev = atomicAdd(tile_ctr + sg.tile, 1u);
-                const uint32_t last = (prev == (uint32_t)sg.nsplits - 1) ? 1u : 0u;
-                if (last) tile_ctr[sg.tile] = 0;          // re-arm for the next phase that uses this tile index
-                *s_flag = last;
+                grid_wait(tile_ctr + sg.tile, (uint32_t)sg.nsplits - 1, 50);
+                tile_ctr[sg.tile] = 0;                    // re-arm for the next phase that uses this tile index
               }
               worker_bar();
-              finalise = *s_flag != 0;
-              if (finalise) {
-                __threadfence();
+              __threadfence();
+              const float* ps0 = p.ws + (int64_t)sg.tile * MAX_SPLIT * PART_STRIDE + n_local;
+#pragma unroll 1
+              for (int sp = 1; sp < sg.nsplits; sp += 2) {       // two contributors (32 / 64 loads) in flight per round
+                const bool two = sp + 1 < sg.nsplits;
+                const float* pa = ps0 + (int64_t)sp * PART_STRIDE;
+                const float* pb = pa + PART_STRIDE;
+                float v0[16], v1[16], u0[16], u1[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { acc[j] = 0.f; accu[j] = 0.f; }
-                for (int sp = 0; sp < sg.nsplits; ++sp) {       // fixed split order: deterministic
-                  const float* ps = p.ws + ((int64_t)sg.tile * MAX_SPLIT + sp) * PART_STRIDE;
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    if (col0 + j < B) {
-                      acc[j] += __ldcg(ps + (col0 + j) * TILE_N + n_local);
-                      if (gu) accu[j] += __ldcg(ps + (NT + col0 + j) * TILE_N + n_local);
-                    }
-                  }
+                for (int j = 0; j < 16; ++j) {
+                  const bool ok = col0 + j < B;
+                  v0[j] = ok ? __ldcg(pa + (col0 + j) * TILE_N) : 0.f;
+                  v1[j] = (ok && two) ? __ldcg(pb + (col0 + j) * TILE_N) : 0.f;
+                  u0[j] = (ok && gu) ? __ldcg(pa + (NT + col0 + j) * TILE_N) : 0.f;
+                  u1[j] = (ok && gu && two) ? __ldcg(pb + (NT + col0 + j) * TILE_N) : 0.f;
                 }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { acc[j] = (acc[j] + v0[j]) + v1[j]; accu[j] = (accu[j] + u0[j]) + u1[j]; }
               }
-              worker_bar();                               // s_flag may be rewritten by the next segment
             }
             if (finalise) {
               const int n = sg.tile * TILE_N + n_local;
@@ -661,6 +805,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
         // arrive at the grid barrier that closes this phase
         worker_bar();
+        if (wtid == 0) trace_stamp(p, l, ph, 3);
         if (wtid == 0) {
           __threadfence();
           atomicAdd(p.sync, 1u);
@@ -742,10 +887,15 @@ bool build_phase(Sched* sc, int g, int tiles, int kb, int G, int G_all) {
 
 }  // namespace
 
+static unsigned long long* g_mega_trace = nullptr;
+// development aid (tools/trace_mega.py): device buffer of [ctas][layers][5][8] u64 globaltimer stamps, nullptr = off
+extern "C" int rd_mega_set_trace(void* buf) { g_mega_trace = (unsigned long long*)buf; return RD_OK; }
+extern "C" int rd_mega_ctas(rd_mega* m);
+
 struct rd_mega {
   MegaCreate c;
   int G = 0, n_qkv = 0;
-  CUtensorMap* wmaps = nullptr;
+  WeightMaps* wmaps_host = nullptr;
   LayerDev* lay = nullptr;
   Sched* sched = nullptr;
   float *ws = nullptr, *ssq = nullptr;
@@ -760,6 +910,7 @@ const char* rd_mega_unsupported_reason(const MegaCreate* c) {
   if (c->lora_r > 16) return "lora_r > 16";
   if (c->cmax > ATT_MAX_CTX + 1) return "max_ctx > 1024";
   if (c->H / 128 > 480) return "hidden size too large";
+  if (c->layers > MAX_LAYERS) return "too many layers for the tensor-map parameter block";
   return nullptr;
 }
 
@@ -786,17 +937,21 @@ int rd_mega_create(const MegaCreate* c, const MegaLayerDesc* layers, rd_mega** o
   for (int g = 0; g < 4; ++g) {
     max_tiles = tiles[g] > max_tiles ? tiles[g] : max_tiles;
     const long long U = (long long)tiles[g] * kbs[g];
-    int Gp = (int)(U / 8 > 0 ? U / 8 : 1);          // at least ~8 k-blocks per active CTA
-    Gp = Gp > m->G ? m->G : Gp;
-    while (Gp > 1 && !build_phase(sc, g, tiles[g], kbs[g], Gp, m->G)) --Gp;
-    if (Gp == 1 && !build_phase(sc, g, tiles[g], kbs[g], 1, m->G)) {
+    int Gp0 = (int)(U / 8 > 0 ? U / 8 : 1);         // at least ~8 k-blocks per active CTA
+    Gp0 = Gp0 > m->G ? m->G : Gp0;
+    bool ok = false;
+    for (int Gp = Gp0; Gp <= m->G && !ok; ++Gp) ok = build_phase(sc, g, tiles[g], kbs[g], Gp, m->G);
+    for (int Gp = Gp0 - 1; Gp >= 1 && !ok; --Gp) ok = build_phase(sc, g, tiles[g], kbs[g], Gp, m->G);
+    if (!ok) {
       delete m;
       rd_set_error("rd_mega_create: cannot schedule GEMM phase %d (%d tiles x %d k-blocks)", g, tiles[g], kbs[g]);
       return RD_ERR_UNSUPPORTED;
     }
   }
   // tensor maps of the weights
-  std::vector<CUtensorMap> hm((size_t)c->layers * 4);
+  m->wmaps_host = new WeightMaps();
+  memset(m->wmaps_host, 0, sizeof(WeightMaps));
+  CUtensorMap* hm = m->wmaps_host->m;
   std::vector<LayerDev> hl(c->layers);
   for (int l = 0; l < c->layers; ++l) {
     const MegaLayerDesc& d = layers[l];
@@ -804,13 +959,11 @@ int rd_mega_create(const MegaCreate* c, const MegaLayerDesc* layers, rd_mega** o
     if (r == RD_OK) r = make_map(&hm[l * 4 + G_O], d.o, H, H, H, TILE_N, c->dtype);
     if (r == RD_OK) r = make_map(&hm[l * 4 + G_GU], d.gate_up, H, 2 * I, H, TILE_N, c->dtype);
     if (r == RD_OK) r = make_map(&hm[l * 4 + G_DN], d.down, I, H, I, TILE_N, c->dtype);
-    if (r != RD_OK) { delete m; return r; }
+    if (r != RD_OK) { rd_mega_destroy(m); return r; }
     hl[l].ln1 = d.ln1; hl[l].ln2 = d.ln2; hl[l].lora_b = d.lora_b; hl[l].kc = d.kc; hl[l].vc = d.vc;
   }
   auto fail = [&](cudaError_t e) { rd_set_error("rd_mega_create: CUDA error %s", cudaGetErrorString(e)); rd_mega_destroy(m); return RD_ERR_CUDA; };
   cudaError_t e;
-  if ((e = cudaMalloc((void**)&m->wmaps, hm.size() * sizeof(CUtensorMap))) != cudaSuccess) return fail(e);
-  if ((e = cudaMemcpy(m->wmaps, hm.data(), hm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void**)&m->lay, hl.size() * sizeof(LayerDev))) != cudaSuccess) return fail(e);
   if ((e = cudaMemcpy(m->lay, hl.data(), hl.size() * sizeof(LayerDev), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc((void**)&m->sched, sizeof(Sched))) != cudaSuccess) return fail(e);
@@ -826,10 +979,13 @@ int rd_mega_create(const MegaCreate* c, const MegaLayerDesc* layers, rd_mega** o
   return RD_OK;
 }
 
+extern "C" int rd_mega_ctas(rd_mega* m) { return m ? m->G : 0; }
+
 void rd_mega_destroy(rd_mega* m) {
   if (!m) return;
-  void* ptrs[] = {m->wmaps, m->lay, m->sched, m->ws, m->ssq, m->sync};
+  void* ptrs[] = {m->lay, m->sched, m->ws, m->ssq, m->sync};
   for (void* p : ptrs) if (p) cudaFree(p);
+  delete m->wmaps_host;
   delete m;
 }
 
@@ -846,13 +1002,19 @@ static int launch_mega(rd_mega* m, const MegaStep* s, cudaStream_t st) {
   RD_CHECK(make_map(&map_att, s->att, c.H, s->B, c.H, NT, c.dtype));
   RD_CHECK(make_map(&map_mid, s->mid, c.I, s->B, c.I, NT, c.dtype));
   MegaParams p{};
-  p.wmaps = m->wmaps; p.lay = m->lay; p.sched = m->sched;
+  p.lay = m->lay; p.sched = m->sched;
   p.x = s->x; p.qkv = s->qkv; p.att = s->att; p.mid = s->mid;
   p.ws = m->ws; p.ssq = m->ssq; p.sync = m->sync;
   p.keymask = s->keymask; p.ctx_len = s->ctx_len; p.pos = s->pos; p.cos_t = s->cos; p.sin_t = s->sin;
   p.B = s->B; p.H = c.H; p.I = c.I; p.nh = c.nh; p.n_qkv = m->n_qkv; p.ldq = m->n_qkv; p.cmax = c.cmax; p.lora_r = c.lora_r;
   p.l0 = s->layer_begin; p.l1 = s->layer_end; p.G = m->G;
   p.lora_scale = c.lora_scale; p.eps = c.eps;
+  p.trace = g_mega_trace;
+  p.sw = SW;
+  p.cb = 1;
+  if (const char* e = getenv("RD_MEGA_CB")) { const int v = atoi(e); if (v >= 1 && v <= 2) p.cb = v; }
+  if (const char* e = getenv("RD_MEGA_DBG")) p.dbg = atoi(e);
+  if (const char* e = getenv("RD_MEGA_SW")) { const int v = atoi(e); if (v >= 2 && v <= SW) p.sw = v; }
   // warps per (sequence, head): as many as keeps every item in one round
   const int items = s->B * c.nh;
   int P = 8;
@@ -864,7 +1026,7 @@ static int launch_mega(rd_mega* m, const MegaStep* s, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = rd_pdl_enabled() ? 1 : 0;
-  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T>, map_x, map_att, map_mid, p));
+  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T>, map_x, map_att, map_mid, *m->wmaps_host, p));
   return RD_OK;
 }
 

@@ -123,7 +123,7 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
 extern "C" int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* p) {
   RD_REQUIRE(h && p, "rd_llm_set_weight: null argument");
   RD_REQUIRE(((uintptr_t)p & 15) == 0, "rd_llm_set_weight: pointer for slot %d must be 16-byte aligned", slot);
-  if (h->mega) { rd_mega_destroy(h->mega); h->mega = nullptr; }      // its tensor maps point at the old weights
+  if (h->mega && slot >= 10) { rd_mega_destroy(h->mega); h->mega = nullptr; }      // its tensor maps point at the old layer weights
   if (slot < 10) {
     switch (slot) {
       case RD_W_EMBED: h->embed = p; break;

@@ -22,7 +22,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a protocol bug must surface as a launch failure with a message, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+__device__ __forceinline__ uint32_t mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done, spins = 0;
   long long t0 = 0;
@@ -32,7 +32,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (!done && (++spins & 0x3FFu) == 0) {
+    ++spins;
+    if (!done && (spins & 0x3FFu) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 6000000000ll) {      // ~3 s
@@ -41,6 +42,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
       }
     }
   } while (!done);
+  return spins;       // number of try_wait probes (1 = the phase had already completed)
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t hint) {
   asm volatile(
@@ -90,6 +92,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // UMMA instruction descriptor, kind::f16: D=f32, A/B = fmt (0 f16, 1 bf16), both K-major.
 __host__ __device__ constexpr uint32_t make_idesc(int fmt, int umma_m, int umma_n) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+
+// one lane of a fully converged warp (elect.sync): keeps the surrounding loop warp-uniform for the compiler
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
