@@ -259,7 +259,7 @@ def run_own_arm(args):
     out = None
     if rank == 0:
         hbm_peak, peak_src = peaks()
-        roof, prof, per_op = dominant_kernel_roofline(llm, B, hbm_peak, peak_src)
+        roof, prof, mega = dominant_kernel_roofline(llm, B, hbm_peak, peak_src)
         dec_ms = sum(s["decode_ms"] for s in stats) / len(stats) / (NEW - 1)
         c_mid = T_PROMPT + NEW // 2
         step_bytes = W_DEC_BYTES + B * KV_BYTES_PER_TOKEN * (c_mid + 1)
@@ -282,7 +282,7 @@ def run_own_arm(args):
                             "tokens_per_s": B / (dec_ms * 1e-3)},
             "phases_ms": {k: sum(s[k] for s in stats) / len(stats) for k in ("vision_ms", "prefill_ms", "decode_ms")},
             "kernel_classes_ms_per_decode_step": {k: v["ms"] / PROFILE_STEPS for k, v in prof.items()},
-            "per_op_path": per_op,
+            "persistent_kernel": mega,
         }
     if world > 1:
         dist.barrier()
@@ -299,30 +299,31 @@ def run_own_arm(args):
 
 
 def dominant_kernel_roofline(llm, B, hbm_peak, peak_src):
-    """Dominant kernel = decode_mega_kernel: ONE launch runs the 32 decoder layers of a decode step.  Algorithmic bytes
-    per launch = layer weights + B x (KV read of c cached tokens + KV write); duration = CUDA events around
-    each eager launch (the engine records them on the launching stream).  Also times the one-kernel-per-op path."""
+    """Dominant kernel of the default (one kernel per op) decode path = the fused gate|up projection GEMM: algorithmic
+    bytes per launch = its weights; duration = CUDA events around each eager launch (the engine records them
+    on the launching stream).  Also times the experimental persistent all-layers kernel (rd_llm_set_mega(1)) the same way:
+    ONE launch runs the 32 decoder layers, bytes = layer weights + B x (KV read of c cached tokens + KV write)."""
     prof = llm.profile_decode_steps(B, T_PROMPT, steps=PROFILE_STEPS)
-    n = max(1, prof["mega"]["launches"])
-    mega_ms = prof["mega"]["ms"] / n
+    gu_ms = prof["gate_up"]["ms"] / max(1, prof["gate_up"]["launches"])
+    gu_gbs = GATE_UP_BYTES / (gu_ms * 1e-3) / 1e9 if gu_ms > 0 else 0.0
+    kern = "linear_tc_kernel<NT=32,SWIGLU>" if B > 4 else "linear_tc_kernel<NT=16,SWIGLU>"
+    roof = {"kernel": f"{kern} (gate|up projection of one decoder layer, decode, B={B})", "bound": "hbm",
+            "achieved": gu_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gu_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": GATE_UP_BYTES, "ms_per_launch": gu_ms,
+            "how": f"CUDA events around each eager launch, {PROFILE_STEPS} decode steps x 32 layers, after the timed region"}
+    llm.set_mega(True)
+    try:
+        pm = llm.profile_decode_steps(B, T_PROMPT, steps=PROFILE_STEPS)
+    finally:
+        llm.set_mega(False)
+    mega_ms = pm["mega"]["ms"] / max(1, pm["mega"]["launches"])
     c_mean = T_PROMPT + 1 + (PROFILE_STEPS - 1) / 2.0          # cached tokens seen by the profiled steps
     mega_bytes = LAYER_W_BYTES + B * KV_BYTES_PER_TOKEN * (c_mean + 1)
-    gbs = mega_bytes / (mega_ms * 1e-3) / 1e9 if mega_ms > 0 else 0.0
-    roof = {"kernel": f"decode_mega_kernel (all 32 decoder layers of one decode step, B={B}, ctx~{int(c_mean)})", "bound": "hbm",
-            "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": int(mega_bytes), "ms_per_launch": mega_ms,
-            "how": f"CUDA events around each eager launch, {PROFILE_STEPS} decode steps, after the timed region"}
-    llm.set_mega(False)
-    try:
-        pp = llm.profile_decode_steps(B, T_PROMPT, steps=PROFILE_STEPS)
-    finally:
-        llm.set_mega(True)
-    gu_ms = pp["gate_up"]["ms"] / max(1, pp["gate_up"]["launches"])
-    per_op = {"note": "same steps with one kernel per op (rd_llm_set_mega(0)); eager launches, events around each",
-              "gate_up_gbs": GATE_UP_BYTES / (gu_ms * 1e-3) / 1e9 if gu_ms > 0 else None,
-              "gate_up_frac": GATE_UP_BYTES / (gu_ms * 1e-3) / 1e9 / hbm_peak if gu_ms > 0 else None,
-              "kernel_classes_ms_per_decode_step": {k: v["ms"] / PROFILE_STEPS for k, v in pp.items()}}
-    return roof, prof, per_op
+    mega = {"note": "experimental persistent kernel (rd_llm_set_mega(1), off by default): all 32 decoder layers of a step in one launch",
+            "ms_per_launch": mega_ms, "algorithmic_bytes_per_launch": int(mega_bytes),
+            "achieved_gbs": mega_bytes / (mega_ms * 1e-3) / 1e9 if mega_ms > 0 else None,
+            "frac_of_hbm_peak": mega_bytes / (mega_ms * 1e-3) / 1e9 / hbm_peak if mega_ms > 0 else None}
+    return roof, prof, mega
 
 
 def bench_b1(pipe, llm, dev, new_tokens, hbm_peak):
@@ -341,11 +342,11 @@ def bench_b1(pipe, llm, dev, new_tokens, hbm_peak):
     ms = e0.elapsed_time(e1)
     dec_ms = pipe.last_stats["decode_ms"] / (new_tokens - 1)
     step_bytes = W_DEC_BYTES + KV_BYTES_PER_TOKEN * (T_PROMPT + new_tokens // 2 + 1)
-    roof, _, per_op = dominant_kernel_roofline(llm, 1, hbm_peak, "")
+    roof, _, mega = dominant_kernel_roofline(llm, 1, hbm_peak, "")
     return {"reports_per_s": 1e3 / ms, "ms_per_report": ms, "decode_ms_per_token": dec_ms,
             "decode_step_gbs": step_bytes / (dec_ms * 1e-3) / 1e9, "decode_step_frac_of_hbm_peak": step_bytes / (dec_ms * 1e-3) / 1e9 / hbm_peak,
-            "mega_kernel_gbs": roof["achieved"], "mega_kernel_frac": roof["frac"],
-            "gemv_gate_up_gbs": per_op["gate_up_gbs"], "gemv_gate_up_frac": per_op["gate_up_frac"]}
+            "gate_up_gbs": roof["achieved"], "gate_up_frac": roof["frac"],
+            "persistent_kernel_ms": mega["ms_per_launch"], "persistent_kernel_frac": mega["frac_of_hbm_peak"]}
 
 
 def main():

@@ -167,7 +167,7 @@ int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* ptr_dev);
 int rd_llm_set_algo(rd_llm* h, int algo);
 /* Single-token decode steps with B <= 32 run ALL decoder layers in one persistent kernel (one CTA per SM, weights of
  * every phase streamed through one TMA ring, stream-K work split, grid barriers between phases; csrc/decode_mega.cu).
- * on = 1 (default) / 0 = one kernel per op.  Same rounding contract either way (LlamaDecoderLayer.forward,
+ * on = 1 / 0 (default) = one kernel per op.  Same rounding contract either way (LlamaDecoderLayer.forward,
  * modeling_llama_imgemb.py:266-318).  Call outside stream capture.                                              */
 int rd_llm_set_mega(rd_llm* h, int on);
 /* Decode step: bytes of W_qkv / W_o / W_gate|up that the (latency-bound, HBM-idle) norm and attention kernels pull into

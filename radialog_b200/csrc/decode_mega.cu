@@ -101,7 +101,7 @@ __device__ __forceinline__ void trace_stamp(const MegaParams& p, int l, int ph, 
   if (p.trace != nullptr) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.trace[(((size_t)blockIdx.x * (p.l1 - p.l0) + (l - p.l0)) * 5 + ph) * 8 + ev] = t;
+    p.trace[(((size_t)blockIdx.x * (p.l1 - p.l0) + (l - p.l0)) * 5 + ph) * 16 + ev] = t;
   }
 }
 __device__ __forceinline__ int phase_of_g(int g) { return g == 0 ? 0 : g + 1; }
@@ -175,7 +175,9 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
   const float sqrt_d = 11.313708498984761f;
   const int nitems = p.B * nh;
 
+  long long tA = 0, tB = 0, tC = 0, tD = 0, tE = 0;
   for (int item = team * p.G + cta; item < nitems; item += teams * p.G) {
+    const long long c_start = clock64();
     const int b = item / nh, h = item % nh;
     const T* kbase = kc + ((int64_t)b * nh + h) * cmax * HD;
     const T* vbase = vc + ((int64_t)b * nh + h) * cmax * HD;
@@ -193,101 +195,132 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
       if (2 * n_my > 0) issue(0);
       if (2 * n_my > 1) issue(1);
     }
-    // ---- RoPE of q (every warp of the team), of k and the LoRA'd v (team leader), KV append ----------------------
+    // ---- RoPE of q, of k, the LoRA'd v, KV append -------------------------------------------------------------------
+    // The two half-warps split the work: lanes 0-15 produce q (LoRA + RoPE), lanes 16-31 produce k (RoPE) and v (LoRA);
+    // every lane owns dims [D, D+8), its RoPE partner dims live in lane ^ 8.  All loads of a lane are independent of
+    // each other (one L2 round trip), results are exchanged with shuffles.
     const T* row = reinterpret_cast<const T*>(p.qkv) + (int64_t)b * p.ldq;
-    const int D = l16 * 8, Dp = D ^ 64;
+    const int D = l16 * 8;
     const bool lo_half = D < 64;
     const int ppos = p.pos[b];
-    float tq[16], tv[16];
+    const Vec8<T> cv = ld16(cos_t + (int64_t)ppos * HD + D), sv = ld16(sin_t + (int64_t)ppos * HD + D);
+    const Vec8<T> A = ldcg16(row + (g2 ? H : 0) + h * HD + D);                    // q (lanes 0-15) or k (lanes 16-31)
+    const Vec8<T> Bv = ldcg16(row + 2 * H + h * HD + D);                           // v
+    float xl[8];                                                                     // LoRA'd q (lanes 0-15) / v (lanes 16-31)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { tq[i] = 0.f; tv[i] = 0.f; }
-    if (lora_r == 8) {                           // the adapter rank of the reference (finetune.py:167): 128-bit rows
-      const Vec8<T> a = ldcg16(row + 3 * H), bb = ldcg16(row + 3 * H + 8);
+    for (int e = 0; e < 8; ++e) xl[e] = Tr<T>::f(g2 ? Bv.v[e] : A.v[e]);
+    if (lora_r > 0) {
+      const T* tsrc = row + 3 * H + (g2 ? lora_r : 0);
+      const T* brows = lora_b + ((int64_t)(g2 ? H : 0) + h * HD + D) * lora_r;
+      float t[16];
+      if (lora_r == 8) {                         // the adapter rank of the reference (finetune.py:167): 128-bit rows
+        const Vec8<T> tt = ldcg16(tsrc);
+        Vec8<T> br[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { tq[i] = Tr<T>::f(a.v[i]); tv[i] = Tr<T>::f(bb.v[i]); }
-    } else if (lora_r > 0) {
+        for (int e = 0; e < 8; ++e) br[e] = ld16(brows + e * 8);
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < lora_r) { tq[i] = Tr<T>::f(ldcg_t(row + 3 * H + i)); tv[i] = Tr<T>::f(ldcg_t(row + 3 * H + lora_r + i)); }
-    }
-    auto lora = [&](float y, int n_row, const float* t) {
-      const T* brow = lora_b + (int64_t)n_row * lora_r;
-      float sdot = 0.f;
-      if (lora_r == 8) {
-        const Vec8<T> bv = ld16(brow);
+        for (int i = 0; i < 8; ++i) t[i] = Tr<T>::f(tt.v[i]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sdot = fmaf(Tr<T>::f(bv.v[i]), t[i], sdot);
+        for (int e = 0; e < 8; ++e) {
+          float sdot = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sdot = fmaf(Tr<T>::f(br[e].v[i]), t[i], sdot);
+          xl[e] = Tr<T>::rr(xl[e] + Tr<T>::rr(p.lora_scale * Tr<T>::rr(sdot)));
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < lora_r) sdot = fmaf(Tr<T>::f(brow[i]), t[i], sdot);
-      }
-      return Tr<T>::rr(y + Tr<T>::rr(p.lora_scale * Tr<T>::rr(sdot)));
-    };
-    const Vec8<T> cv = ld16(cos_t + (int64_t)ppos * HD + D), sv = ld16(sin_t + (int64_t)ppos * HD + D);
-    float q[8], kn[8], vn[8];
-    {
-      const Vec8<T> own = ldcg16(row + h * HD + D), oth = ldcg16(row + h * HD + Dp);
+        for (int i = 0; i < 16; ++i) t[i] = i < lora_r ? Tr<T>::f(ldcg_t(tsrc + i)) : 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float a = Tr<T>::f(own.v[e]), o = Tr<T>::f(oth.v[e]);
-        if (lora_r > 0) { a = lora(a, h * HD + D + e, tq); o = lora(o, h * HD + Dp + e, tq); }
-        const float c = Tr<T>::f(cv.v[e]), s = Tr<T>::f(sv.v[e]);
-        q[e] = Tr<T>::rr(Tr<T>::rr(a * c) + Tr<T>::rr((lo_half ? -o : o) * s));
+        for (int e = 0; e < 8; ++e) {
+          float sdot = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < lora_r) sdot = fmaf(Tr<T>::f(brows[e * lora_r + i]), t[i], sdot);
+          xl[e] = Tr<T>::rr(xl[e] + Tr<T>::rr(p.lora_scale * Tr<T>::rr(sdot)));
+        }
       }
     }
-    if (pw == 0) {
-      const Vec8<T> own = ldcg16(row + H + h * HD + D), oth = ldcg16(row + H + h * HD + Dp);
-      const Vec8<T> vv = ldcg16(row + 2 * H + h * HD + D);
-      Vec8<T> ko, vo;
+    float q[8], kn[8], vn[8];
+    {
+      float rot[8];                              // RoPE: q (lanes 0-15) from the LoRA'd values, k (lanes 16-31) from the raw ones
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float a = Tr<T>::f(own.v[e]), o = Tr<T>::f(oth.v[e]);
-        const float c = Tr<T>::f(cv.v[e]), s = Tr<T>::f(sv.v[e]);
-        kn[e] = Tr<T>::rr(Tr<T>::rr(a * c) + Tr<T>::rr((lo_half ? -o : o) * s));
-        float v = Tr<T>::f(vv.v[e]);
-        if (lora_r > 0) v = lora(v, H + h * HD + D + e, tv);
-        vn[e] = v;
-        ko.v[e] = Tr<T>::r(kn[e]); vo.v[e] = Tr<T>::r(v);
+        const float own = g2 ? Tr<T>::f(A.v[e]) : xl[e];
+        const float oth = __shfl_xor_sync(0xffffffffu, own, 8);
+        const float c = Tr<T>::f(cv.v[e]), sn = Tr<T>::f(sv.v[e]);
+        rot[e] = Tr<T>::rr(Tr<T>::rr(own * c) + Tr<T>::rr((lo_half ? -oth : oth) * sn));
       }
-      if (g2 == 0) {
+      if (pw == 0 && g2 == 1) {                  // append the new token's k (post-RoPE) and v to the cache
+        Vec8<T> ko, vo;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ko.v[e] = Tr<T>::r(rot[e]); vo.v[e] = Tr<T>::r(xl[e]); }
         const int64_t slot_off = (((int64_t)b * nh + h) * cmax + ctx) * HD + D;
         *reinterpret_cast<uint4*>(reinterpret_cast<T*>(L.kc) + slot_off) = *reinterpret_cast<const uint4*>(&ko);
         *reinterpret_cast<uint4*>(reinterpret_cast<T*>(L.vc) + slot_off) = *reinterpret_cast<const uint4*>(&vo);
       }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        q[e] = __shfl_sync(0xffffffffu, rot[e], l16);
+        kn[e] = __shfl_sync(0xffffffffu, rot[e], 16 + l16);
+        vn[e] = __shfl_sync(0xffffffffu, xl[e], 16 + l16);
+      }
     }
     const uint8_t* km = p.keymask + (int64_t)b * cmax;
-    auto score_of = [&](float dot, int j) {      // modeling_llama_imgemb.py:216-230 (decode: padding mask only)
+    auto score_of = [&](float dot, unsigned keep) {      // modeling_llama_imgemb.py:216-230 (decode: padding mask only)
       float s = Tr<T>::rr(dot);
       s = Tr<T>::rr(s / sqrt_d);
-      s = Tr<T>::rr(s + (km[j] ? 0.f : lowest));
+      s = Tr<T>::rr(s + (keep ? 0.f : lowest));
       return fmaxf(s, lowest);
     };
+    // padding-mask bytes: lane l16 holds the byte of key l16 of the current chunk, fetched one chunk ahead (a per-key
+    // global load inside the key loop costs an L2 round trip per key: L1 is invalidated by every gpu-scope fence)
+    auto km_load = [&](int s) -> unsigned {
+      const int j = (pw + s * P) * ATT_CH + l16;
+      return (s < n_my && j < ctx) ? (unsigned)km[j] : 0u;
+    };
+    const unsigned km_new = km[ctx];
+    unsigned km_cur = km_load(0);
+    const long long c_pro = clock64();
     // ---- scores of this warp's K chunks ------------------------------------------------------------------------------
     float lmax = -INFINITY;
     for (int s = 0; s < n_my; ++s) {
+      const unsigned km_next = km_load(s + 1);
       const uint32_t qi = seq + (uint32_t)s;
       mbar_wait_warp(bar + (qi & 1u), (qi >> 1) & 1u, 40, lane);
       const T* buf = reinterpret_cast<const T*>(cbuf + (qi & 1u) * (ATT_CH * HD * 2));
       const int c = pw + s * P;
       int keys = ctx - c * ATT_CH;
       keys = keys > ATT_CH ? ATT_CH : keys;
-#pragma unroll 2
-      for (int jl = g2; jl < ATT_CH; jl += 2) {  // uniform trip count: the half-warp shuffles stay converged
+      // the 8 key pairs of the chunk are independent: all dot products first, then the shuffle trees interleaved, then the
+      // rounding chain of the scores - one dependent chain per key pair would run at instruction latency
+      float dd[ATT_CH / 2];
+#pragma unroll
+      for (int i = 0; i < ATT_CH / 2; ++i) {
+        const int jl = g2 + 2 * i;
         float d = 0.f;
         if (jl < keys) {
           const Vec8<T> kk = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + D);
 #pragma unroll
           for (int e = 0; e < 8; ++e) d = fmaf(q[e], Tr<T>::f(kk.v[e]), d);
         }
+        dd[i] = d;
+      }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
+      for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < ATT_CH / 2; ++i) dd[i] += __shfl_xor_sync(hmask, dd[i], o);
+      }
+#pragma unroll
+      for (int i = 0; i < ATT_CH / 2; ++i) {
+        const int jl = g2 + 2 * i;
+        const unsigned keep = __shfl_sync(hmask, km_cur, (lane & 16) + jl);
         if (jl < keys) {
-          const float svv = score_of(d, c * ATT_CH + jl);
+          const float svv = score_of(dd[i], keep);
           if (l16 == 0) sc[c * ATT_CH + jl] = Tr<T>::r(svv);
           lmax = fmaxf(lmax, svv);
         }
       }
+      km_cur = km_next;
       __syncwarp();
       if (lane == 0 && s + 2 < 2 * n_my) issue(s + 2);
     }
@@ -297,10 +330,11 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
       for (int e = 0; e < 8; ++e) d = fmaf(q[e], kn[e], d);
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
-      const float svv = score_of(d, ctx);
+      const float svv = score_of(d, km_new);
       if (lane == 0) sc[ctx] = Tr<T>::r(svv);
       lmax = fmaxf(lmax, svv);
     }
+    const long long c_sc = clock64();
     lmax = warp_max(lmax);
     float mx = lmax;
     if (P > 1) {
@@ -322,6 +356,7 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
       sum = 0.f;
       for (int i = 0; i < P; ++i) sum += s_red[(team * P + i) * 2 + 1];
     }
+    const long long c_sm = clock64();
     // ---- P.V over this warp's V chunks -------------------------------------------------------------------------------
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int s = n_my; s < 2 * n_my; ++s) {
@@ -331,11 +366,20 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
       const int c = pw + (s - n_my) * P;
       int keys = ctx - c * ATT_CH;
       keys = keys > ATT_CH ? ATT_CH : keys;
-      for (int jl = g2; jl < keys; jl += 2) {
-        const Vec8<T> vv = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + D);
-        const float pj = Tr<T>::rr(expf(Tr<T>::f(sc[c * ATT_CH + jl]) - mx) / sum);      // softmax(fp32).to(dtype)
+      float pj[ATT_CH / 2];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, Tr<T>::f(vv.v[e]), acc[e]);
+      for (int i = 0; i < ATT_CH / 2; ++i) {       // softmax(fp32).to(dtype), independent per key
+        const int jl = g2 + 2 * i;
+        pj[i] = jl < keys ? Tr<T>::rr(expf(Tr<T>::f(sc[c * ATT_CH + jl]) - mx) / sum) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < ATT_CH / 2; ++i) {
+        const int jl = g2 + 2 * i;
+        if (jl < keys) {
+          const Vec8<T> vv = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + D);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj[i], Tr<T>::f(vv.v[e]), acc[e]);
+        }
       }
       __syncwarp();
       if (lane == 0 && s + 2 < 2 * n_my) issue(s + 2);
@@ -345,6 +389,7 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vn[e], acc[e]);
     }
+    const long long c_pv = clock64();
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] += __shfl_down_sync(0xffffffffu, acc[e], 16);
     if (P > 1) {
@@ -370,6 +415,13 @@ __device__ __forceinline__ void attention_items(const MegaParams& p, const Layer
     seq += (uint32_t)(2 * n_my);
     if (P > 1) team_bar(team, P * 32);           // partial accumulators / scores are free for the next item
     else __syncwarp();
+    const long long c_end = clock64();
+    tA += c_pro - c_start; tB += c_sc - c_pro; tC += c_sm - c_sc; tD += c_pv - c_sm; tE += c_end - c_pv;
+  }
+  if (p.trace != nullptr && lane == 0) {
+    unsigned long long* o = p.trace + (size_t)p.G * (p.l1 - p.l0) * 80 + 320 + (size_t)p.G * 12 + ((size_t)cta * WORK_WARPS + ww) * 8;
+    o[0] += (unsigned long long)tA; o[1] += (unsigned long long)tB; o[2] += (unsigned long long)tC; o[3] += (unsigned long long)tD;
+    o[4] += (unsigned long long)tE;
   }
 }
 
@@ -433,6 +485,9 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   // (measured ~2000 cycles per k-block against a budget of 700).
   if (warp == 0) {
     // ===================== weight producer: never waits on anything but a free ring slot =====================
+    // (Tried and dropped: a second cursor running up to 48 tiles ahead with cp.async.bulk.prefetch.tensor into L2 while the
+    // ring is full.  It did not shorten the streams and lengthened every phase tail - the extra traffic competes with the
+    // latency-critical partial-sum / barrier round trips - so the ring is the only prefetch.)
     uint32_t slot = 0, ki = 0, filled = 0;
     bool first = true;
     for (int l = p.l0; l < p.l1; ++l) {
@@ -603,6 +658,24 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             *reinterpret_cast<uint4*>(s_lnw + (size_t)idx * 16) = *reinterpret_cast<const uint4*>(lnw + kb * BK + c * 8);
           }
         }
+        if (ph == 1) {
+          // cached K/V rows of this warp's (sequence, head) items -> L2 while the QKV phase drains: the rows were written by
+          // earlier steps, and with them L2-resident the chunk copies of the attention sweep are L2 hits, not HBM round trips
+          const int P = p.att_P, team = ww / P, teams = WORK_WARPS / P;
+          if (ww % P == 0) {
+            const int ctx = p.ctx_len[0];
+            const int per = (ctx + 31) / 32, r0 = lane * per;
+            int nr = ctx - r0;
+            nr = nr > per ? per : nr;
+            for (int item = team * p.G + cta; item < B * p.nh; item += teams * p.G) {
+              if (nr > 0) {
+                const size_t off = ((size_t)item * p.cmax + r0) * 128 * sizeof(T);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(L.kc) + off), "r"(nr * 256) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(L.vc) + off), "r"(nr * 256) : "memory");
+              }
+            }
+          }
+        }
         // wait for the previous phase of the whole grid
         if (wtid == 0) grid_wait(p.sync, epoch * (uint32_t)p.G, 20 + ph);
         worker_bar();
@@ -657,8 +730,10 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 if ((it & (WORK_WARPS - 1)) != ww) continue;
                 mbar_wait_warp(&x_full[slot], par, 30, lane);
                 const int pc = lane & 7;
-#pragma unroll 2
-                for (int r = lane >> 3; r < B; r += 4) {
+#pragma unroll
+                for (int i = 0; i < NT / 4; ++i) {
+                  const int r = (lane >> 3) + 4 * i;
+                  if (r >= B) break;
                   const int c = pc ^ (r & 7);
                   const float rs = s_rstd[r];
                   uint4* cp = reinterpret_cast<uint4*>(xring + slot * X_SLOT + r * 128 + pc * 16);
@@ -713,6 +788,13 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[a]);
+            // residual operands of the tile this CTA will finish: requested before the fix-up waits, consumed after them
+            float res[16];
+            if ((g == G_O || g == G_DN) && sg.split == 0) {
+              const int n = sg.tile * TILE_N + n_local;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) res[j] = (col0 + j < B && n < H) ? Tr<T>::f(ldcg_t(xg + (int64_t)(col0 + j) * H + n)) : 0.f;
+            }
             // Stream-K fix-up with a FIXED finaliser: the CTA that holds the head of the tile's k range (split 0; it is that
             // CTA's last segment, so it finishes when the phase ends) sums the other contributors' fp32 partials from L2 onto
             // its own accumulator, in split order (deterministic).  Contributors only publish and move on.
@@ -736,26 +818,43 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 tile_ctr[sg.tile] = 0;                    // re-arm for the next phase that uses this tile index
               }
               worker_bar();
+              if (wtid == 0 && s == ns - 1) trace_stamp(p, l, ph, 8);
               __threadfence();
               const float* ps0 = p.ws + (int64_t)sg.tile * MAX_SPLIT * PART_STRIDE + n_local;
+              if (gu) {
 #pragma unroll 1
-              for (int sp = 1; sp < sg.nsplits; sp += 2) {       // two contributors (32 / 64 loads) in flight per round
-                const bool two = sp + 1 < sg.nsplits;
-                const float* pa = ps0 + (int64_t)sp * PART_STRIDE;
-                const float* pb = pa + PART_STRIDE;
-                float v0[16], v1[16], u0[16], u1[16];
+                for (int sp = 1; sp < sg.nsplits; sp += 2) {     // two contributors (64 loads) in flight per round
+                  const bool two = sp + 1 < sg.nsplits;
+                  const float* pa = ps0 + (int64_t)sp * PART_STRIDE;
+                  const float* pb = pa + PART_STRIDE;
+                  float v0[16], v1[16], u0[16], u1[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const bool ok = col0 + j < B;
-                  v0[j] = ok ? __ldcg(pa + (col0 + j) * TILE_N) : 0.f;
-                  v1[j] = (ok && two) ? __ldcg(pb + (col0 + j) * TILE_N) : 0.f;
-                  u0[j] = (ok && gu) ? __ldcg(pa + (NT + col0 + j) * TILE_N) : 0.f;
-                  u1[j] = (ok && gu && two) ? __ldcg(pb + (NT + col0 + j) * TILE_N) : 0.f;
+                  for (int j = 0; j < 16; ++j) {
+                    const bool ok = col0 + j < B;
+                    v0[j] = ok ? __ldcg(pa + (col0 + j) * TILE_N) : 0.f;
+                    v1[j] = (ok && two) ? __ldcg(pb + (col0 + j) * TILE_N) : 0.f;
+                    u0[j] = ok ? __ldcg(pa + (NT + col0 + j) * TILE_N) : 0.f;
+                    u1[j] = (ok && two) ? __ldcg(pb + (NT + col0 + j) * TILE_N) : 0.f;
+                  }
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { acc[j] = (acc[j] + v0[j]) + v1[j]; accu[j] = (accu[j] + u0[j]) + u1[j]; }
                 }
+              } else {
+#pragma unroll 1
+                for (int sp = 1; sp < sg.nsplits; sp += 4) {     // four contributors (64 loads) in flight per round
+                  float v[4][16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { acc[j] = (acc[j] + v0[j]) + v1[j]; accu[j] = (accu[j] + u0[j]) + u1[j]; }
+                  for (int q = 0; q < 4; ++q) {
+                    const float* pq = ps0 + (int64_t)(sp + q) * PART_STRIDE;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[q][j] = (sp + q < sg.nsplits && col0 + j < B) ? __ldcg(pq + (col0 + j) * TILE_N) : 0.f;
+                  }
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) acc[j] = (((acc[j] + v[0][j]) + v[1][j]) + v[2][j]) + v[3][j];
+                }
               }
             }
+            if (wtid == 0 && s == ns - 1) trace_stamp(p, l, ph, 9);
             if (finalise) {
               const int n = sg.tile * TILE_N + n_local;
               if (g == G_QKV) {
@@ -778,9 +877,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 }
               } else {
                 // o_proj / down_proj: residual add in the storage dtype + sum of squares of the new residual stream
-                float res[16], yy[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) res[j] = (col0 + j < B && n < H) ? Tr<T>::f(ldcg_t(xg + (int64_t)(col0 + j) * H + n)) : 0.f;
+                float yy[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   yy[j] = 0.f;
@@ -809,6 +906,7 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (wtid == 0) {
           __threadfence();
           atomicAdd(p.sync, 1u);
+          trace_stamp(p, l, ph, 10);
         }
         ++epoch;
       }

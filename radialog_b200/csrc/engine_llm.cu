@@ -29,8 +29,10 @@ struct rd_llm {
   const float* img_b = nullptr;
   int algo = 0;
   int esz = 2;
-  // persistent decode-layer kernel (decode_mega.cu): 1 = use it whenever the shape allows (B <= 32), 0 = per-op kernels
-  int mega_mode = 1;
+  // persistent decode-layer kernel (decode_mega.cu): 1 = use it whenever the shape allows (B <= 32), 0 = per-op kernels.
+  // Off by default: at Vicuna-7B size its 5 grid barriers per layer (phase tails of 6-8 us) still cost more than the
+  // per-op path's launch boundaries (measured 4.4 ms vs 3.5 ms per B=32 step); see DESIGN.md section 4.
+  int mega_mode = 0;
   rd_mega* mega = nullptr;
   // L2 weight prefetch from the norm / attention kernels: mechanism kept, OFF by default (A/B runs on B200 showed no
   // gain at B=32 beyond run-to-run noise and a loss at B=1, where the norm kernel is a single CTA)

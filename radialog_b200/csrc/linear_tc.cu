@@ -119,6 +119,15 @@ __device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot)
   }
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one lane of a fully converged warp (elect.sync).  The producer and MMA warps run their loops warp-uniformly and elect a
+// lane only for the asynchronous instruction: with a lane-0-only loop ptxas wraps every UTMALDG / UTCHMMA operand in an
+// ELECT / R2UR.BROADCAST / BRA waterfall and the serial instruction stream (~0.7 us per k-block, measured with per-role
+// clock64 accounting in the persistent decode kernel) - not HBM - paces a small-N tile.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major operand, 128-byte swizzle, rows of 128 B,
 // 8-row groups 1024 B apart.  [0,14) addr>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4,
@@ -292,58 +301,73 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   EpiCtx<T> cx;                                   // epilogue operands hoisted into registers (epilogue warps only)
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      auto stage_ptr = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
-      auto load_w = [&](int s, int kb) {
-        uint8_t* sp = stage_ptr(s);
-        tma_load_2d(sp, &map_w, &full_bar[s], kb * BLOCK_K, n0, p.hint_w);
-        if (SWIGLU) tma_load_2d(sp + Cfg::A_BYTES, &map_w, &full_bar[s], kb * BLOCK_K, p.N + n0, p.hint_w);
-      };
-      auto load_x = [&](int s, int kb) {
-        tma_load_2d(stage_ptr(s) + Cfg::ACCS * Cfg::A_BYTES, &map_x, &full_bar[s], kb * BLOCK_K, m0, p.hint_x);
-      };
-      const int pre = nkb < STAGES ? nkb : STAGES;
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    auto stage_ptr = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+    auto load_w = [&](int s, int kb) {
+      uint8_t* sp = stage_ptr(s);
+      tma_load_2d(sp, &map_w, &full_bar[s], kb * BLOCK_K, n0, p.hint_w);
+      if (SWIGLU) tma_load_2d(sp + Cfg::A_BYTES, &map_w, &full_bar[s], kb * BLOCK_K, p.N + n0, p.hint_w);
+    };
+    auto load_x = [&](int s, int kb) {
+      tma_load_2d(stage_ptr(s) + Cfg::ACCS * Cfg::A_BYTES, &map_x, &full_bar[s], kb * BLOCK_K, m0, p.hint_x);
+    };
+    const int pre = nkb < STAGES ? nkb : STAGES;
+    if (elect_one()) {
       for (int i = 0; i < pre; ++i) {            // weights first: independent of the previous kernel
         mbar_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
         load_w(i, kb_begin + i);
       }
-      pdl_wait();                                // activations were written by the previous kernel
+    }
+    __syncwarp();
+    pdl_wait();                                  // activations were written by the previous kernel
+    if (elect_one()) {
       trace_stamp(p.trace, 2);
       for (int i = 0; i < pre; ++i) load_x(i, kb_begin + i);
-      for (int i = pre; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u, 1);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = pre; i < nkb; ++i) {
+      mbar_wait(&empty_bar[s], ph, 1);
+      __syncwarp();
+      if (elect_one()) {
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         load_w(s, kb_begin + i);
         load_x(s, kb_begin + i);
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(Tr<T>::umma_fmt, BLOCK_N, NT);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph, 2);
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    constexpr uint32_t idesc = make_idesc(Tr<T>::umma_fmt, BLOCK_N, NT);
+    const uint64_t d0 = make_smem_desc(smem_u32(smem));
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&full_bar[s], ph, 2);
+      tc_fence_after();
+      const uint64_t da = d0 + (uint64_t)((uint32_t)s * (Cfg::STAGE_BYTES >> 4));
+      const uint64_t du = da + (uint64_t)(Cfg::A_BYTES >> 4);
+      const uint64_t db = da + (uint64_t)((Cfg::ACCS * Cfg::A_BYTES) >> 4);
+      __syncwarp();
+      if (elect_one()) {
         if (i == 0) trace_stamp(p.trace, 3);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + Cfg::ACCS * Cfg::A_BYTES;
-        const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(b_addr);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
           const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
           const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);     // advance inside the 128-byte swizzle row
           tc_mma_f16(tmem_base, da + koff, db + koff, idesc, acc);
-          if (SWIGLU) tc_mma_f16(tmem_base + NT, make_smem_desc(a_addr + Cfg::A_BYTES) + koff, db + koff, idesc, acc);
+          if (SWIGLU) tc_mma_f16(tmem_base + NT, du + koff, db + koff, idesc, acc);
         }
         tc_commit(&empty_bar[s]);                 // frees the smem stage once these MMAs have read it
+        if (i == nkb - 1) {
+          tc_commit(tmem_full_bar);               // accumulators complete
+          trace_stamp(p.trace, 4);
+        }
       }
-      tc_commit(tmem_full_bar);                   // accumulators complete
-      trace_stamp(p.trace, 4);
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================

@@ -111,7 +111,7 @@ class LlamaForCausalLM:
         self._cached_ids: Optional[torch.Tensor] = None     # host copy of the ids whose KV are in the cache
         self._img_w_packed = None
         self.algo = _lib.ALGO_AUTO
-        self.mega = True
+        self.mega = False     # persistent all-layers decode kernel (experimental)
         self.use_cuda_graph = True
         self.last_stats: Dict[str, float] = {}
 

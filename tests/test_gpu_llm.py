@@ -221,7 +221,7 @@ def test_persistent_decode_kernel_matches_per_op_kernels(cuda_dev, dtype_name, B
         model.set_mega(mega)
         outs[mega] = model.generate(prompts.to(cuda_dev), img_embeds=img.to(cuda_dev), max_new_tokens=n_new, suppress_eos=True,
                                     return_dict_in_generate=True, output_scores=True)
-    model.set_mega(True)
+    model.set_mega(False)
     a, b = outs[False], outs[True]
     scale = a.scores[1].float().abs().max().item()
     # step 0 comes from the prefill (identical code either way); step 1 is the first decode step

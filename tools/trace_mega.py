@@ -28,13 +28,14 @@ sd = synth.make_llama_weights(cfg, seed=0, dtype=dtype, device="cuda:0")
 llm = LlamaForCausalLM.from_state_dict(cfg, sd, torch_dtype=dtype, device=dev)
 del sd
 llm.use_cuda_graph = False
+llm.set_mega(True)
 prompts = synth.make_prompts(B, seed=4321).to(dev)
 img = torch.randn(B, 32, 768, device=dev) * 0.5
 llm.reserve(B, 64 + extra + 8)
 llm.generate(prompts, img_embeds=img, max_new_tokens=extra, suppress_eos=True)
 torch.cuda.synchronize()
 G, L = 148, cfg.num_hidden_layers
-trace = torch.zeros(G * L * 5 * 8 + 320 + G * 12, dtype=torch.int64, device=dev)
+trace = torch.zeros(G * L * 5 * 16 + 320 + G * 12 + G * 64, dtype=torch.int64, device=dev)
 st = _lib.current_stream()
 _lib.check(lib.rd_llm_decode_step(llm._h, st), "decode_step")
 torch.cuda.synchronize()
@@ -45,8 +46,8 @@ _lib.check(lib.rd_llm_decode_step(llm._h, st), "decode_step")
 e1.record()
 torch.cuda.synchronize()
 lib.rd_mega_set_trace(None)
-t = trace[:G * L * 5 * 8].view(G, L, 5, 8).cpu().double()
-kbt = trace[G * L * 5 * 8:].cpu().double()
+t = trace[:G * L * 5 * 16].view(G, L, 5, 16).cpu().double()
+kbt = trace[G * L * 5 * 16:].cpu().double()
 print(f"B={B} ctx~{64 + extra}: traced decode step {e0.elapsed_time(e1) * 1e3:.0f} us (all kernels of the step)")
 names = ["qkv", "attn", "o", "gate_up", "down"]
 
@@ -83,6 +84,16 @@ for ph in range(5):
             d["acc_ready"] = (ev[work, 2] - prev_last).mean().item()
             d["epi"] = (ev[work, 3] - ev[work, 2]).mean().item()
             d["w_first_issue"] = (ev[work, 7] - prev_last).mean().item()
+            fin = ev[:, 8] > 0
+            if fin.any():
+                slow = ev[fin, 3].argmax()
+                e = ev[fin][slow]
+                # the finalising CTA that arrives last: last MMA commit -> accumulator seen -> contributors seen -> partials summed -> arrive issued
+                d["L:mma"] = e[5].item() - prev_last
+                d["L:ctr"] = e[8].item() - prev_last
+                d["L:sum"] = e[9].item() - prev_last
+                d["L:pre_arrive"] = e[3].item() - prev_last
+                d["L:arrived"] = e[10].item() - prev_last
         rows.append(d)
     keys = rows[0].keys()
     avg = {k: sum(r[k] for r in rows) / len(rows) / 1e3 for k in keys}
@@ -107,9 +118,16 @@ nk = max(1.0, m[5].item())
 print("MMA thread, mean over CTAs (cycles per k-block): wait W %.0f  wait X %.0f  fence+MMA issue %.0f  commit %.0f | acc_empty wait total %.0f  k-blocks %.0f  thread total %.0f cycles"
       % (m[0] / nk, m[1] / nk, m[2] / nk, m[3] / nk, m[4], nk, m[6]))
 
-spw = (trace[G * L * 5 * 8 + 320:G * L * 5 * 8 + 320 + G * 8].view(G, 8)[:, 7].cpu() >> 32).double().mean().item()
-spx = (trace[G * L * 5 * 8 + 320:G * L * 5 * 8 + 320 + G * 8].view(G, 8)[:, 7].cpu() & 0xFFFFFFFF).double().mean().item()
+spw = (trace[G * L * 5 * 16 + 320:G * L * 5 * 16 + 320 + G * 8].view(G, 8)[:, 7].cpu() >> 32).double().mean().item()
+spx = (trace[G * L * 5 * 16 + 320:G * L * 5 * 16 + 320 + G * 8].view(G, 8)[:, 7].cpu() & 0xFFFFFFFF).double().mean().item()
 print("MMA thread try_wait probes per k-block: W %.2f  X %.2f" % (spw / nk, spx / nk))
 wp = kbt[320 + G * 8:320 + G * 12].view(G, 4).mean(0)
 print("W producer: tiles %.0f, cycles waiting for a free slot per tile %.0f (probes %.2f), thread total %.0f cycles" %
       (wp[3], wp[0] / max(1, wp[3]), wp[2] / max(1, wp[3]), wp[1]))
+
+att = kbt[320 + G * 12:320 + G * 12 + G * 64].view(G * 8, 8)
+busy = att[att[:, 0] > 0]
+if busy.numel():
+    mm = busy.mean(0) / L / 1.965e3
+    print("attention per warp with work, us per layer: prologue(RoPE/LoRA/append) %.1f  scores %.1f  max+sum %.1f  P.V %.1f  combine/write %.1f   (%d of %d warps busy)"
+          % (mm[0], mm[1], mm[2], mm[3], mm[4], busy.shape[0], G * 8))
