@@ -485,43 +485,48 @@ decode_mega_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   // (measured ~2000 cycles per k-block against a budget of 700).
   if (warp == 0) {
     // ===================== weight producer: never waits on anything but a free ring slot =====================
-    // (Tried and dropped: a second cursor running up to 48 tiles ahead with cp.async.bulk.prefetch.tensor into L2 while the
-    // ring is full.  It did not shorten the streams and lengthened every phase tail - the extra traffic competes with the
-    // latency-critical partial-sum / barrier round trips - so the ring is the only prefetch.)
+    // (Tried and dropped, both measured with tools/trace_mega.py: a second cursor pulling tiles beyond the ring into L2 with
+    // cp.async.bulk.prefetch.tensor - either continuously or only while the ring is stalled in a phase boundary.  Neither
+    // shortened the streams and both lengthened every phase (extra traffic competing with the latency-critical fix-up /
+    // barrier round trips), so the ring is the only prefetch.)
     uint32_t slot = 0, ki = 0, filled = 0;
-    bool first = true;
     for (int l = p.l0; l < p.l1; ++l) {
       for (int g = 0; g < 4; ++g) {
         const CUtensorMap* map = &wmaps.m[l * 4 + g];
         const int ns = sched->nseg[g];
-        first = true;
+        const int reps = g == G_GU ? 2 : 1;
+        bool first = true;
         for (int s = 0; s < ns; ++s) {
           const Seg sg = sched->seg[g][s];
           const int row = sg.tile * TILE_N;
           for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-            const int reps = g == G_GU ? 2 : 1;
+            // the one (gate|up: two) slots of this k-block; their previous tiles must have been read by their MMAs
+            uint32_t sl[2] = {0, 0};
             for (int r = 0; r < reps; ++r) {
-              if (filled >= SW) {                 // the slot's previous tile must have been read by its MMAs
+              sl[r] = slot;
+              if (filled >= SW) {
                 const uint32_t old = s_wkb[slot];
                 mbar_wait(&cons[old & (CONS_R - 1)], (old / CONS_R) & 1u, 1);
               } else {
                 ++filled;
               }
-              __syncwarp();
-              if (elect_one()) {
-                s_wkb[slot] = ki;
-                if (first) trace_stamp(p, l, phase_of_g(g), 7);
-                if (p.dbg & 2) {
-                  mbar_arrive(&w_full[slot]);     // diagnostic: no weight traffic
-                } else {
-                  mbar_expect_tx(&w_full[slot], W_SLOT);
-                  tma_load_2d(wring + slot * W_SLOT, map, &w_full[slot], kb * BK, r == 0 ? row : p.I + row, HINT_EVICT_FIRST);
-                }
-              }
-              __syncwarp();
-              first = false;
               if (++slot == SW) slot = 0;
             }
+            __syncwarp();
+            if (elect_one()) {
+              if (first) trace_stamp(p, l, phase_of_g(g), 7);
+              for (int r = 0; r < reps; ++r) {
+                s_wkb[sl[r]] = ki;
+                if (p.dbg & 2) {
+                  mbar_arrive(&w_full[sl[r]]);      // diagnostic: no weight traffic
+                } else {
+                  mbar_expect_tx(&w_full[sl[r]], W_SLOT);
+                  tma_load_2d(wring + sl[r] * W_SLOT, map, &w_full[sl[r]], kb * BK, r == 0 ? row : p.I + row, HINT_EVICT_FIRST);
+                }
+              }
+            }
+            __syncwarp();
+            first = false;
             ++ki;
           }
         }
