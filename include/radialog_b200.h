@@ -170,6 +170,12 @@ int rd_llm_set_algo(rd_llm* h, int algo);
  * on = 1 / 0 (default) = one kernel per op.  Same rounding contract either way (LlamaDecoderLayer.forward,
  * modeling_llama_imgemb.py:266-318).  Call outside stream capture.                                              */
 int rd_llm_set_mega(rd_llm* h, int on);
+/* The GEMMs of single-token decode steps with B <= 32 as stream-K kernels (one CTA per SM, equal contiguous runs of
+ * (weight tile, k-block) units, fp32 fix-up through L2 in fixed split order) with the RMSNorm of
+ * LlamaDecoderLayer.forward (modeling_llama_imgemb.py:287,305) applied to the token tiles in shared memory instead of by
+ * a separate kernel (csrc/linear_sk.cu).  on = 1 / 0 (default) = tile x split-K kernels + norm kernels.  Same rounding
+ * contract either way.  Call outside stream capture.                                                              */
+int rd_llm_set_streamk(rd_llm* h, int on);
 /* Decode step: bytes of W_qkv / W_o / W_gate|up that the (latency-bound, HBM-idle) norm and attention kernels pull into
  * the 126 MB L2 with cp.async.bulk.prefetch ahead of the GEMM that streams them; 0,0,0 turns it off. */
 int rd_llm_set_l2_prefetch(rd_llm* h, long long qkv_bytes, long long o_bytes, long long gate_up_bytes);

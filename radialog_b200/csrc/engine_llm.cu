@@ -6,6 +6,7 @@
 #include <vector>
 #include "common.cuh"
 #include "decode_mega.h"
+#include "linear_sk.h"
 
 extern "C" int rd_attention_decode(const void*, int64_t, const int32_t*, const void*, const void*, void*, void*, const uint8_t*,
                                    const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
@@ -34,6 +35,12 @@ struct rd_llm {
   // per-op path's launch boundaries (measured 4.4 ms vs 3.5 ms per B=32 step); see DESIGN.md section 4.
   int mega_mode = 0;
   rd_mega* mega = nullptr;
+  // stream-K decode GEMMs with the RMSNorm fused on their input (linear_sk.cu) for single-token steps with B <= 32.
+  // Off by default: measured slower than the tile x split-K kernels (B=32: qkv 37 vs 29 us, gate|up 56 vs 43 us per launch) -
+  // the fix-up through L2 costs more than the cluster/DSMEM reduction, and <= 113 KB of smem per CTA is too little in flight.
+  int sk_mode = 0;
+  rd_sk* sk = nullptr;
+  float* ssq = nullptr;          // [H/128][32] sum-of-squares partials of the residual stream
   // L2 weight prefetch from the norm / attention kernels: mechanism kept, OFF by default (A/B runs on B200 showed no
   // gain at B=32 beyond run-to-run noise and a loss at B=1, where the norm kernel is a single CTA)
   bool l2_prefetch = false;
@@ -119,6 +126,8 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   rd_mega_destroy(h->mega);
+  rd_sk_destroy(h->sk);
+  if (h->ssq) cudaFree(h->ssq);
   delete h;
 }
 
@@ -243,6 +252,70 @@ static int run_layers_mega(rd_llm* h, int B, const int32_t* pos, cudaStream_t st
   return rd_mega_launch(h->mega, &s, st);
 }
 
+// ---- stream-K decode path -------------------------------------------------------------------------------------------------
+static bool sk_wanted(const rd_llm* h, int B) {
+  const rd_llm_config& c = h->c;
+  return h->sk_mode && h->algo == 0 && B <= 32 && c.hidden % 128 == 0 && c.inter % 64 == 0;
+}
+
+// plans + buffers of the stream-K GEMMs (allocates: called from prefill / extend, never inside a stream capture)
+static int sk_ensure(rd_llm* h) {
+  const rd_llm_config& c = h->c;
+  const int H = c.hidden, I = c.inter, R2 = c.lora_r ? 2 * c.lora_r : 0;
+  if (!h->sk) RD_CHECK(rd_sk_create(&h->sk));
+  if (!h->ssq) {
+    RD_CHECK_CUDA(cudaMalloc((void**)&h->ssq, (size_t)(H / 128) * 32 * 4));
+    RD_CHECK_CUDA(cudaMemset(h->ssq, 0, (size_t)(H / 128) * 32 * 4));
+  }
+  RD_CHECK(rd_sk_plan(h->sk, 3 * H + R2, H, RD_SK_PLAIN));
+  RD_CHECK(rd_sk_plan(h->sk, H, H, RD_SK_RES1));
+  RD_CHECK(rd_sk_plan(h->sk, I, H, RD_SK_SWIGLU));
+  RD_CHECK(rd_sk_plan(h->sk, H, I, RD_SK_RES1));
+  RD_CHECK(rd_sk_plan(h->sk, c.vocab, H, RD_SK_PLAIN));
+  return RD_OK;
+}
+
+static int run_layers_sk(rd_llm* h, int B, const int32_t* pos, cudaStream_t st) {
+  const rd_llm_config& c = h->c;
+  const int H = c.hidden, I = c.inter, nh = c.heads, hd = H / nh, dt = c.dtype;
+  const int R2 = c.lora_r ? 2 * c.lora_r : 0;
+  const int64_t ldq = 3 * H + R2;
+  const bool fuse_qkv = rd_sk_max_segments(h->sk, 3 * H + R2, H, RD_SK_PLAIN) <= 2;
+  const bool fuse_gu = rd_sk_max_segments(h->sk, I, H, RD_SK_SWIGLU) <= 2;
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerW& w = h->L[l];
+    char* kc = h->kc + (int64_t)l * h->kv_layer_bytes;
+    char* vc = h->vc + (int64_t)l * h->kv_layer_bytes;
+    SkNorm n1{h->ssq, H / 128, w.ln1, c.rms_eps}, n2{h->ssq, H / 128, w.ln2, c.rms_eps};
+    if (l == 0 || !fuse_qkv) {     // the first layer's input comes from the embedding kernel: no partials yet
+      { ProfScope ps(h, st, C_RMSNORM);
+        RD_CHECK(rd_rmsnorm(h->x, w.ln1, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
+      ProfScope ps(h, st, C_QKV);
+      RD_CHECK(rd_sk_linear(h->sk, h->xn, H, w.qkv, H, h->qkv, ldq, B, 3 * H + R2, H, RD_SK_PLAIN, nullptr, 0, nullptr, nullptr, dt, st));
+    } else {
+      ProfScope ps(h, st, C_QKV);
+      RD_CHECK(rd_sk_linear(h->sk, h->x, H, w.qkv, H, h->qkv, ldq, B, 3 * H + R2, H, RD_SK_PLAIN, nullptr, 0, &n1, nullptr, dt, st));
+    }
+    { ProfScope ps(h, st, C_ATTN);
+      RD_CHECK(rd_attention_decode(h->qkv, ldq, pos, h->cos, h->sin, kc, vc, h->keymask, h->ctx_len, h->att, B, nh, hd, c.max_ctx,
+                                   h->ctx_host, c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st)); }
+    { ProfScope ps(h, st, C_O);
+      RD_CHECK(rd_sk_linear(h->sk, h->att, H, w.o, H, h->x, H, B, H, H, RD_SK_RES1, h->x, H, nullptr, h->ssq, dt, st)); }
+    if (fuse_gu) {
+      ProfScope ps(h, st, C_GATEUP);
+      RD_CHECK(rd_sk_linear(h->sk, h->x, H, w.gate_up, H, h->mid, I, B, I, H, RD_SK_SWIGLU, nullptr, 0, &n2, nullptr, dt, st));
+    } else {
+      { ProfScope ps(h, st, C_RMSNORM);
+        RD_CHECK(rd_rmsnorm(h->x, w.ln2, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
+      ProfScope ps(h, st, C_GATEUP);
+      RD_CHECK(rd_sk_linear(h->sk, h->xn, H, w.gate_up, H, h->mid, I, B, I, H, RD_SK_SWIGLU, nullptr, 0, nullptr, nullptr, dt, st));
+    }
+    { ProfScope ps(h, st, C_DOWN);
+      RD_CHECK(rd_sk_linear(h->sk, h->mid, I, w.down, I, h->x, H, B, H, I, RD_SK_RES1, h->x, H, nullptr, h->ssq, dt, st)); }
+  }
+  return RD_OK;
+}
+
 // layers over M = B*q_len tokens whose embeddings are in h->x; positions in `pos`
 static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStream_t st) {
   const rd_llm_config& c = h->c;
@@ -333,6 +406,7 @@ static int extend_impl(rd_llm* h, const int64_t* ids, const void* img_embeds, in
   { ProfScope ps(h, st, C_EMBED);
     RD_CHECK(rd_embed_splice(ids, h->embed, img_rows, h->x, B, T, H, c.vocab, dt, st)); }
   if (mega_wanted(h, B)) RD_CHECK(mega_ensure(h));
+  if (sk_wanted(h, B)) RD_CHECK(sk_ensure(h));
   RD_CHECK(run_layers(h, B, T, h->pos, st));
   RD_CHECK(head_and_select(h, B, T, all_logits, st));
   h->ctx_host += T;
@@ -391,6 +465,7 @@ extern "C" int rd_llm_decode_step(rd_llm* h, void* stream) {
   { ProfScope ps(h, st, C_EMBED);
     RD_CHECK(rd_embed_splice(h->cur_tok, h->embed, nullptr, h->x, h->B, 1, c.hidden, c.vocab, c.dtype, st)); }
   if (mega_wanted(h, h->B) && h->mega != nullptr) RD_CHECK(run_layers_mega(h, h->B, h->pos_cur, st));
+  else if (sk_wanted(h, h->B) && h->sk != nullptr) RD_CHECK(run_layers_sk(h, h->B, h->pos_cur, st));
   else RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
   RD_CHECK(head_and_select(h, h->B, 1, nullptr, st));
   h->ctx_host += 1;
@@ -404,6 +479,15 @@ extern "C" int rd_llm_set_mega(rd_llm* h, int on) {
   RD_REQUIRE(h, "rd_llm_set_mega: null handle");
   h->mega_mode = on ? 1 : 0;
   if (h->mega_mode && h->mega == nullptr && h->B > 0 && mega_wanted(h, h->B) && check_weights(h) == RD_OK) return mega_ensure(h);
+  return RD_OK;
+}
+
+// 1: the GEMMs of single-token steps with B <= 32 run as stream-K kernels with the RMSNorm fused on their input
+// (linear_sk.cu); 0 (default): tile x split-K kernels of linear_tc.cu + separate norm kernels.  Call it outside stream capture.
+extern "C" int rd_llm_set_streamk(rd_llm* h, int on) {
+  RD_REQUIRE(h, "rd_llm_set_streamk: null handle");
+  h->sk_mode = on ? 1 : 0;
+  if (h->sk_mode && h->B > 0 && sk_wanted(h, h->B) && check_weights(h) == RD_OK) return sk_ensure(h);
   return RD_OK;
 }
 
