@@ -239,6 +239,20 @@ int rd_vision_forward(rd_vision* h, const float* images_dev, int B, float* q_out
                       void* stream);
 int64_t rd_vision_launch_count(rd_vision* h);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Image preprocessing on the device
+ * ---------------------------------------------------------------------------------------------------------- */
+/* Bit-exact replacement of the reference's per-image CPU pipeline: remap_to_uint8 (demo.py:173-203) -> PIL "L" image
+ * (demo.py:218) -> Resize(resize) -> CenterCrop(crop) -> ToTensor -> ExpandChannels
+ * (model/lavis/data/ReportDataset.py:80-106, create_chest_xray_transform_for_inference(512, 448)).
+ * img_dev: [H,W] row-major grey image on the device, dtype 0 = uint8, 1 = uint16, 2 = float32; remap = 0 skips
+ * remap_to_uint8 (uint8 input only: an already remapped PIL image).  out_dev: float32 [3, crop, crop].          */
+typedef struct rd_preproc rd_preproc;
+int rd_preproc_create(int max_h, int max_w, int resize, int crop, rd_preproc** out);
+void rd_preproc_destroy(rd_preproc* p);
+int rd_preproc_run(rd_preproc* p, const void* img_dev, int dtype, int H, int W, int remap, float* out_dev, void* stream);
+int64_t rd_preproc_launch_count(rd_preproc* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,10 @@ SIGNATURES = {
     "rd_vision_set_weight": (_i, [_p, C.c_char_p, _p]),
     "rd_vision_forward": (_i, [_p, _p, _i, _p, _p, _p]),
     "rd_vision_launch_count": (_i64, [_p]),
+    "rd_preproc_create": (_i, [_i, _i, _i, _i, C.POINTER(_p)]),
+    "rd_preproc_destroy": (None, [_p]),
+    "rd_preproc_run": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "rd_preproc_launch_count": (_i64, [_p]),
 }
 
 _lib = None
