@@ -176,6 +176,10 @@ int rd_llm_set_mega(rd_llm* h, int on);
  * a separate kernel (csrc/linear_sk.cu).  on = 1 / 0 (default) = tile x split-K kernels + norm kernels.  Same rounding
  * contract either way.  Call outside stream capture.                                                              */
 int rd_llm_set_streamk(rd_llm* h, int on);
+/* Single-token steps with B <= 32: LlamaRMSNorm (modeling_llama_imgemb.py:85-93) applied to the token tiles inside the
+ * QKV / gate|up GEMMs (row statistics from sum-of-squares partials written by the o_proj / down_proj epilogues) instead of
+ * by separate kernels.  on = 1 / 0 (default).  Bit-identical results (tests/test_gpu_llm.py).                    */
+int rd_llm_set_fused_norm(rd_llm* h, int on);
 /* Decode step: bytes of W_qkv / W_o / W_gate|up that the (latency-bound, HBM-idle) norm and attention kernels pull into
  * the 126 MB L2 with cp.async.bulk.prefetch ahead of the GEMM that streams them; 0,0,0 turns it off. */
 int rd_llm_set_l2_prefetch(rd_llm* h, long long qkv_bytes, long long o_bytes, long long gate_up_bytes);

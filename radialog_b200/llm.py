@@ -112,6 +112,7 @@ class LlamaForCausalLM:
         self._img_w_packed = None
         self.algo = _lib.ALGO_AUTO
         self.mega = False     # persistent all-layers decode kernel (experimental)
+        self.fused_norm = False   # RMSNorm inside the decode GEMMs (experimental)
         self.streamk = False  # stream-K decode GEMMs with fused RMSNorm (experimental)
         self.use_cuda_graph = True
         self.last_stats: Dict[str, float] = {}
@@ -295,6 +296,7 @@ class LlamaForCausalLM:
         _lib.check(self._lib.rd_llm_set_algo(h, self.algo), "set_algo")
         _lib.check(self._lib.rd_llm_set_mega(h, 1 if self.mega else 0), "set_mega")
         _lib.check(self._lib.rd_llm_set_streamk(h, 1 if self.streamk else 0), "set_streamk")
+        _lib.check(self._lib.rd_llm_set_fused_norm(h, 1 if self.fused_norm else 0), "set_fused_norm")
 
     def _bind_img_proj(self):
         lin = self.model.img_proj_layer
@@ -312,6 +314,13 @@ class LlamaForCausalLM:
         self._graphs = {}
         if self._h is not None:
             _lib.check(self._lib.rd_llm_set_algo(self._h, algo), "set_algo")
+
+    def set_fused_norm(self, on: bool):
+        """RMSNorm inside the QKV / gate|up GEMMs of single-token steps, or (default) as separate kernels."""
+        self.fused_norm = bool(on)
+        self._graphs = {}
+        if self._h is not None:
+            _lib.check(self._lib.rd_llm_set_fused_norm(self._h, 1 if on else 0), "set_fused_norm")
 
     def set_streamk(self, on: bool):
         """Decode GEMMs as stream-K kernels with fused RMSNorm, or (default) tile x split-K kernels + norm kernels."""

@@ -19,7 +19,10 @@ cfg = synth.LlamaCfg()
 sd = synth.make_llama_weights(cfg, seed=0, dtype=dtype, device="cuda:0")
 llm = LlamaForCausalLM.from_state_dict(cfg, sd, torch_dtype=dtype, device=dev)
 del sd
-for sk in (True, False):
-    llm.set_streamk(sk)
+modes = [("fused_norm", lambda: (llm.set_streamk(False), llm.set_fused_norm(True))),
+         ("separate_norm", lambda: (llm.set_streamk(False), llm.set_fused_norm(False))),
+         ("streamk", lambda: llm.set_streamk(True))]
+for sk, fn in modes:
+    fn()
     prof = llm.profile_decode_steps(B, 64, steps=8)
-    print(f"B={B} streamk={int(sk)}: " + "  ".join(f"{k} {v['ms'] / max(1, v['launches']) * 1e3:.1f}us x{v['launches'] // 8}" for k, v in prof.items() if v["launches"]))
+    print(f"B={B} {sk}: " + "  ".join(f"{k} {v['ms'] / max(1, v['launches']) * 1e3:.1f}us x{v['launches'] // 8}" for k, v in prof.items() if v["launches"]))
