@@ -379,11 +379,141 @@ attention_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ kc, T* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Prefill / extend attention (q_len > 1) with the K and V rows of one (sequence, head) staged ONCE in shared memory:
+// one CTA per (head, sequence), every warp takes query rows warp, warp + 8, ...  The kernel above re-reads up to c keys
+// and values from L2 for every query row (64x redundant at T = 64: 306 us per layer at B = 32); here they are read once.
+// Same rounding points (modeling_llama_imgemb.py:216-234): scores T(q.k) -> T(/sqrt(d)) -> T(+ mask) -> max(finfo.min),
+// fp32 softmax rounded to the storage dtype before P.V; rows with no visible key are evaluated over every key.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATP_THREADS = 256, ATP_WARPS = ATP_THREADS / 32;
+
+template <class T>
+__global__ void __launch_bounds__(ATP_THREADS, 2)
+attention_prefill_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __restrict__ kc, const T* __restrict__ vc,
+                         const uint8_t* __restrict__ keymask, const int32_t* __restrict__ ctx_len_p, T* __restrict__ out,
+                         int q_len, int nh, int cmax) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int HD = 128;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g2 = lane >> 4, l16 = lane & 15;
+  const int ctx = ctx_len_p[0];
+  const int c_tot = ctx + q_len;
+  T* ks = reinterpret_cast<T*>(smem_att);                               // [c_tot][128]
+  T* vs = ks + (size_t)cmax * HD;                                       // [c_tot][128]
+  float* sc = reinterpret_cast<float*>(vs + (size_t)cmax * HD) + (size_t)warp * cmax;    // [warps][cmax]
+  __shared__ int s_first;
+  const uint8_t* km = keymask + (int64_t)b * cmax;
+  const T* kbase = kc + ((int64_t)b * nh + h) * cmax * HD;
+  const T* vbase = vc + ((int64_t)b * nh + h) * cmax * HD;
+  if (tid == 0) s_first = 0x7fffffff;
+  __syncthreads();
+  for (int idx = tid; idx < c_tot * 16; idx += ATP_THREADS) {           // 16-byte chunks, coalesced
+    reinterpret_cast<uint4*>(ks)[idx] = *reinterpret_cast<const uint4*>(kbase + (size_t)idx * 8);
+    reinterpret_cast<uint4*>(vs)[idx] = *reinterpret_cast<const uint4*>(vbase + (size_t)idx * 8);
+  }
+  int first = 0x7fffffff;                                               // first key that is not padding
+  for (int j = tid; j < c_tot; j += ATP_THREADS)
+    if (km[j]) { first = j; break; }
+  if (first != 0x7fffffff) atomicMin(&s_first, first);
+  __syncthreads();
+  first = s_first;
+  const float lowest = Tr<T>::lowest();
+  const float sqrt_d = 11.313708498984761f;  // math.sqrt(128)
+  const unsigned hmask = 0xFFFFu << (lane & 16);
+
+  for (int i = warp; i < q_len; i += ATP_WARPS) {
+    const int jcausal = ctx + i;
+    const bool any = first <= jcausal;
+    const int jend = any ? (jcausal + 1) : c_tot;
+    const int64_t m = (int64_t)b * q_len + i;
+    float q[8];
+    {
+      const Vec8<T> qv = ld16(qkv + m * ldq + h * HD + l16 * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q[e] = Tr<T>::f(qv.v[e]);
+    }
+    // ---- scores: one key per half-warp and iteration, four keys in flight per half-warp ----
+    float mx = -INFINITY;
+    for (int jb = 0; jb < jend; jb += 8) {
+      float d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = jb + 2 * u + g2;
+        d[u] = 0.f;
+        if (j < jend) {
+          const Vec8<T> kk = *reinterpret_cast<const Vec8<T>*>(ks + (size_t)j * HD + l16 * 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[u] = fmaf(q[e], Tr<T>::f(kk.v[e]), d[u]);
+        }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] += __shfl_xor_sync(hmask, d[u], o);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = jb + 2 * u + g2;
+        if (j < jend) {
+          float s = Tr<T>::rr(d[u]);                             // matmul output in the storage dtype
+          s = Tr<T>::rr(s / sqrt_d);                             // / math.sqrt(head_dim)
+          float madd = km[j] ? 0.f : lowest;                     // _expand_mask
+          if (j > jcausal) madd = Tr<T>::rr(madd + lowest);      // + _make_causal_mask (may be -inf)
+          s = Tr<T>::rr(s + madd);
+          s = fmaxf(s, lowest);                                  // torch.max(attn_weights, finfo.min)
+          if (l16 == 0) sc[j] = s;
+          mx = fmaxf(mx, s);
+        }
+      }
+    }
+    mx = warp_max(mx);
+    __syncwarp();
+    float sum = 0.f;
+    for (int j = lane; j < jend; j += 32) { const float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    __syncwarp();
+    for (int j = lane; j < jend; j += 32) sc[j] = Tr<T>::rr(sc[j] / sum);   // softmax(fp32).to(dtype)
+    __syncwarp();
+    // ---- P.V ----
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = g2; j < jend; j += 2) {
+      const Vec8<T> vv = *reinterpret_cast<const Vec8<T>*>(vs + (size_t)j * HD + l16 * 8);
+      const float pj = sc[j];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, Tr<T>::f(vv.v[e]), acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += __shfl_down_sync(0xffffffffu, acc[e], 16);
+    if (lane < 16) {
+      Vec8<T> o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o.v[e] = Tr<T>::r(acc[e]);
+      *reinterpret_cast<uint4*>(out + m * (int64_t)(nh * HD) + h * HD + l16 * 8) = *reinterpret_cast<const uint4*>(&o);
+    }
+    __syncwarp();
+  }
+}
+
 extern "C" int rd_attention(const void* qkv, int64_t ldq, const void* kc, const void* vc, const uint8_t* keymask,
                             const int32_t* ctx_len, void* out, int B, int q_len, int nh, int hd, int cmax, int dtype,
                             void* stream) {
   RD_REQUIRE(hd == 128, "rd_attention: head_dim must be 128 (Vicuna-7B); got %d", hd);
   RD_REQUIRE(B > 0 && q_len > 0 && cmax > 0 && cmax * 4 <= 160 * 1024, "rd_attention: bad shape");
+  // several query rows per (sequence, head) and a cache that fits shared memory: K / V staged once per CTA
+  const size_t atp_smem = (size_t)cmax * 128 * 2 * 2 + (size_t)ATP_WARPS * cmax * 4;
+  if (q_len >= 4 && atp_smem <= 200 * 1024) {
+    RD_DISPATCH_DTYPE(dtype, T, {
+      static bool attr_set2 = false;
+      if (!attr_set2) { RD_CHECK_CUDA(cudaFuncSetAttribute(attention_prefill_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set2 = true; }
+      RD_CHECK_CUDA(rd_launch(attention_prefill_kernel<T>, dim3(nh, B), dim3(ATP_THREADS), atp_smem, (cudaStream_t)stream, rd_pdl_enabled(),
+                              (const T*)qkv, ldq, (const T*)kc, (const T*)vc, keymask, ctx_len, (T*)out, q_len, nh, cmax));
+      return RD_OK;
+    });
+  }
   RD_DISPATCH_DTYPE(dtype, T, {
     static bool attr_set = false;
     if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
