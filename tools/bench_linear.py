@@ -26,9 +26,11 @@ def main():
     ap.add_argument("--ms", default="1,4,8,32")
     ap.add_argument("--splits", default="0")
     ap.add_argument("--dtype", default="float16")
+    ap.add_argument("--splitk-mode", type=int, default=0, help="0 cluster/DSMEM reduction, 1 global workspace")
     args = ap.parse_args()
     lib = _lib.load()
     lib.rd_set_pdl(args.pdl)
+    lib.rd_linear_splitk_mode(args.splitk_mode)
     dev = torch.device("cuda:0")
     dtype = getattr(torch, args.dtype)
     peak = 6551.7
