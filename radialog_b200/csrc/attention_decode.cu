@@ -180,16 +180,31 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
       if (s < n_kv) {                              // ---- scores of this K chunk ----
         int keys = ctx - s * CH;
         keys = keys > CH ? CH : keys;
-        for (int jl = g; jl < CH; jl += GROUPS) {  // uniform trip count: the half-warp shuffles stay converged
+        // the CH / GROUPS keys of a 16-lane group are independent: all dot products first, then the shuffle trees
+        // interleaved (one dependent chain per key would run at instruction latency); uniform trip count keeps the
+        // half-warp shuffles converged
+        constexpr int KPG = CH / GROUPS;
+        float dd[KPG];
+#pragma unroll
+        for (int u = 0; u < KPG; ++u) {
+          const int jl = g + u * GROUPS;
           float d = 0.f;
           if (jl < keys) {
             const Vec8<T> kk = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + l16 * 8);
 #pragma unroll
             for (int e = 0; e < 8; ++e) d = fmaf(q[e], Tr<T>::f(kk.v[e]), d);
           }
+          dd[u] = d;
+        }
 #pragma unroll
-          for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
-          if (l16 == 0 && jl < keys) sc[s * CH + jl] = score_of(d, s * CH + jl);
+        for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < KPG; ++u) dd[u] += __shfl_xor_sync(hmask, dd[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < KPG; ++u) {
+          const int jl = g + u * GROUPS;
+          if (l16 == 0 && jl < keys) sc[s * CH + jl] = score_of(dd[u], s * CH + jl);
         }
       }
     } else {
@@ -226,11 +241,15 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
       }
       int keys = ctx - c * CH;
       keys = keys > CH ? CH : keys;
-      for (int jl = g; jl < keys; jl += GROUPS) {  // ---- P.V of this V chunk ----
-        const Vec8<T> vv = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + l16 * 8);
-        const float pj = sc[c * CH + jl];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, Tr<T>::f(vv.v[e]), acc[e]);
+      for (int u = 0; u < CH / GROUPS; ++u) {      // ---- P.V of this V chunk ----
+        const int jl = g + u * GROUPS;
+        if (jl < keys) {
+          const Vec8<T> vv = *reinterpret_cast<const Vec8<T>*>(buf + jl * HD + l16 * 8);
+          const float pj = sc[c * CH + jl];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, Tr<T>::f(vv.v[e]), acc[e]);
+        }
       }
     }
     __syncthreads();                               // everyone is done with this ring slot

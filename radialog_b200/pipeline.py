@@ -10,6 +10,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 
 
@@ -85,6 +87,47 @@ def gather_sequences(local: torch.Tensor, counts: List[int], dst: int = 0) -> Op
     if rank != dst:
         return None
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+
+
+def write_embedding_pickle(path: str, embeddings: Dict[str, "torch.Tensor"]) -> None:
+    """The reference's on-disk hand-off of Q-Former outputs (pretraining/train.py:139-149, read back by
+    modeling_llama_imgemb.py:454-462): a pickled ``{dicom_id: np.float32[32, 768]}`` dict."""
+    import pickle
+
+    import numpy as np
+    out = {}
+    for k, v in embeddings.items():
+        a = v.detach().float().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, dtype=np.float32)
+        if a.ndim != 2:
+            raise ValueError(f"embedding of {k!r} must be [num_query_tokens, hidden], found {a.shape}")
+        out[str(k)] = np.ascontiguousarray(a, dtype=np.float32)
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "wb") as f:
+        pickle.dump(out, f)
+
+
+@torch.no_grad()
+def precompute_embeddings(vision, batches, path: Optional[str] = None) -> Dict[str, "torch.Tensor"]:
+    """Bulk precompute of the Q-Former outputs - the evaluate branch of pretraining/train.py:134-173: ``batches`` yields
+    ``(images [B,3,448,448], dicom ids)``; returns ``{dicom: float32 [32,768] (cpu)}`` and, with ``path``, writes the pickle
+    in the reference format (e.g. ``pretraining/embs/<run>_embeddings_test.pkl``)."""
+    embs: Dict[str, torch.Tensor] = {}
+    for images, ids in batches:
+        q_out, _ = vision.forward_image(images)
+        q_cpu = q_out.float().cpu()
+        for j, d in enumerate(ids):
+            embs[str(d)] = q_cpu[j].clone()
+    if path is not None:
+        write_embedding_pickle(path, embs)
+    return embs
+
+
+def save_chat_image(q_out_row: "torch.Tensor", path: str = "current_chat_img.pt") -> None:
+    """demo.py:269-273: the conversational path parks the image's ``[32, 768]`` Q-Former output in ``current_chat_img.pt`` (CWD),
+    which ``generate(use_img=True)`` reads back (modeling_llama_imgemb.py:576)."""
+    if q_out_row.dim() != 2:
+        raise ValueError(f"expected [num_query_tokens, hidden], found {tuple(q_out_row.shape)}")
+    torch.save(q_out_row.detach().float().cpu(), path)
 
 
 class ReportPipeline:

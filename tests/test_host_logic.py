@@ -122,3 +122,41 @@ def test_data_parallel_world2_gloo(tmp_path):
     img = torch.randn(5, 32, cfg.qformer_hidden, generator=torch.Generator().manual_seed(9))
     want = O.LlamaOracle(cfg, sd, torch.float32).generate(prompts, img, 3, suppress_eos=True)
     assert torch.equal(got, want)
+
+
+def test_embedding_pickle_and_chat_image_formats(tmp_path, monkeypatch):
+    """The reference's on-disk hand-offs (pretraining/train.py:139-149, demo.py:269-273) written by the pipeline helpers are
+    what modeling_llama_imgemb.py:454-462,576 reads: {dicom: np.float32[32,768]} pickles relative to the CWD, a [32,768] .pt."""
+    import pickle
+
+    import numpy as np
+    import torch
+    from radialog_b200 import pipeline
+    from radialog_b200.llm import EMB_PKL_TEST, CHAT_IMG_FILE
+
+    monkeypatch.chdir(tmp_path)
+    embs = {"d1": torch.randn(32, 768, dtype=torch.float64), "d2": np.random.rand(32, 768)}
+    pipeline.write_embedding_pickle(EMB_PKL_TEST, embs)
+    with open(EMB_PKL_TEST, "rb") as f:
+        back = pickle.load(f)
+    assert sorted(back) == ["d1", "d2"]
+    assert all(isinstance(v, np.ndarray) and v.dtype == np.float32 and v.shape == (32, 768) for v in back.values())
+    assert np.allclose(back["d1"], embs["d1"].numpy().astype(np.float32))
+    import pytest
+    with pytest.raises(ValueError):
+        pipeline.write_embedding_pickle(EMB_PKL_TEST, {"bad": torch.zeros(768)})
+    pipeline.save_chat_image(torch.randn(32, 768, dtype=torch.float16))
+    t = torch.load(CHAT_IMG_FILE)
+    assert t.shape == (32, 768) and t.dtype == torch.float32
+
+    class FakeVision:
+        def forward_image(self, images):
+            b = images.shape[0]
+            return images.reshape(b, -1)[:, :32 * 8].reshape(b, 32, 8), None
+
+    batches = [(torch.arange(2 * 3 * 16 * 16, dtype=torch.float32).reshape(2, 3, 16, 16), ["a", "b"]),
+               (torch.ones(1, 3, 16, 16), ["c"])]
+    out = pipeline.precompute_embeddings(FakeVision(), batches, path=str(tmp_path / "x" / "emb.pkl"))
+    assert sorted(out) == ["a", "b", "c"] and out["b"].shape == (32, 8)
+    with open(tmp_path / "x" / "emb.pkl", "rb") as f:
+        assert sorted(pickle.load(f)) == ["a", "b", "c"]
