@@ -267,6 +267,8 @@ def run_own_arm(args):
         step_bytes = W_DEC_BYTES + B * KV_BYTES_PER_TOKEN * (c_mid + 1)
         step_gbs = step_bytes / (dec_ms * 1e-3) / 1e9
         value = B * world * args.steps / (ms * 1e-3)
+        # the dominant kernel's share of a decode step (32 launches per step), to set beside the ncu launch list's share
+        roof["share_of_decode_step"] = roof["ms_per_launch"] * lcfg.num_hidden_layers / dec_ms
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
