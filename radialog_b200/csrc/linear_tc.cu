@@ -25,6 +25,8 @@ bool rd_pdl_enabled();
 unsigned long long* rd_linear_trace_buffer();
 static int g_force_generic_epilogue = 0;   // test hook
 extern "C" int rd_linear_force_generic_epilogue(int on) { g_force_generic_epilogue = on; return RD_OK; }
+static int g_wide_epi = 1;        // test hook: 0 = direct (per-thread strided) epilogue also for wide token tiles
+extern "C" int rd_linear_wide_epilogue(int on) { g_wide_epi = on; return RD_OK; }
 static int g_splitk_mode = 0;     // 0: cluster/DSMEM reduction when possible, 1: always the global workspace
 extern "C" int rd_linear_splitk_mode(int mode) { g_splitk_mode = mode; return RD_OK; }
 
@@ -257,6 +259,7 @@ struct TcParams {
   int norm_tiles;
   float norm_eps;
   float* ssq_out;              // EPI_RES1 (N % 128 == 0): sum_n out[m,n]^2 of this 128-row tile -> ssq_out[tile][m]
+  int wide_epi;                // NT >= 64: transposed epilogue through shared memory (coalesced residual loads / stores)
   EpiParams epi;
 };
 
@@ -491,7 +494,81 @@ _Pragma("unroll")
     mbar_wait(tmem_full_bar, 0, 3);
     tc_fence_after();
     if (threadIdx.x == 64) trace_stamp(p.trace, 5);
-    if (p.splits == 1) {
+    if (NT >= 64 && p.wide_epi) {
+      // ---- wide token tiles (prefill, convolutions): transposed epilogue.  A thread owns one weight row n, so the direct
+      // ---- epilogue issues one 2-byte residual load and one 2-byte store per (token, thread) at a stride of ldo - with 256
+      // ---- tokens per tile that, not the MMAs, set the pace (prefill o_proj tile: 17 us of MMA, ~90 us of epilogue).
+      // ---- Phase A parks the fp32 values [token][n] in the (now idle) pipeline smem, phase B walks it token-major: each
+      // ---- thread finishes 4 consecutive n of a token with one 8-byte residual load and one 8-byte store (a warp covers the
+      // ---- tile's 128 columns of a token row: 256 contiguous bytes).  Same arithmetic and rounding points as the direct path.
+      float* stg = reinterpret_cast<float*>(smem);
+      const int mode = p.epi_mode;
+      for (int c = 0; c < m_valid; c += 16) {
+        uint32_t r[16], ru[16];
+        tc_ld16(taddr + c, r);
+        if (SWIGLU) tc_ld16(taddr + NT + c, ru);
+        tc_wait_ld();
+_Pragma("unroll")
+        for (int j = 0; j < 16; ++j) {
+          if (c + j < m_valid) {
+            float v = __uint_as_float(r[j]);
+            if (SWIGLU) {
+              const float g = Tr<T>::rr(v), u = Tr<T>::rr(__uint_as_float(ru[j]));
+              v = Tr<T>::rr(Tr<T>::rr(silu_f(g)) * u);                    // T(T(silu(T(g))) * T(u))
+            } else if (mode == EPI_AFFINE) {
+              v += cx.bias_n;
+            }
+            stg[(c + j) * BLOCK_N + n_local] = v;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;
+      const int n4 = (e & 31) * 4, nn = n0 + n4;
+      if (nn < p.N) {
+        const bool has_res = (mode == EPI_RES1) || (mode == EPI_AFFINE && p.epi.residual != nullptr && p.epi.res_mode == 2);
+        const T* resb = reinterpret_cast<const T*>(p.epi.residual) + nn;
+        T* outb = out + nn;
+        const int act = p.epi.act;
+        constexpr int UNR = 4;
+        for (int mb = e >> 5; mb < m_valid; mb += 4 * UNR) {
+          float4 v[UNR];
+          uint2 rv[UNR];
+_Pragma("unroll")
+          for (int u = 0; u < UNR; ++u) {
+            const int m = mb + 4 * u;
+            if (m < m_valid) {
+              v[u] = *reinterpret_cast<const float4*>(stg + m * BLOCK_N + n4);
+              if (has_res) rv[u] = *reinterpret_cast<const uint2*>(resb + (int64_t)(m0 + m) * p.epi.ld_res);
+            }
+          }
+_Pragma("unroll")
+          for (int u = 0; u < UNR; ++u) {
+            const int m = mb + 4 * u;
+            if (m < m_valid) {
+              const float a[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+              const T* rt = reinterpret_cast<const T*>(&rv[u]);
+              T y[4];
+_Pragma("unroll")
+              for (int q = 0; q < 4; ++q) {
+                if (mode == EPI_RES1) {
+                  y[q] = Tr<T>::r(Tr<T>::f(rt[q]) + Tr<T>::rr(a[q]));       // fp16 residual add after rounding Wx
+                } else if (mode == EPI_AFFINE) {
+                  float w = a[q];
+                  if (has_res) w += Tr<T>::f(rt[q]);
+                  if (act == RD_ACT_RELU) w = fmaxf(w, 0.0f);
+                  else if (act == RD_ACT_GELU) w = gelu_erf(w);
+                  y[q] = Tr<T>::r(w);
+                } else {
+                  y[q] = Tr<T>::r(a[q]);
+                }
+              }
+              *reinterpret_cast<uint2*>(outb + (int64_t)(m0 + m) * p.ldo) = *reinterpret_cast<const uint2*>(y);
+            }
+          }
+        }
+      }
+    } else if (p.splits == 1) {
       EPI_DISPATCH(p.epi_mode,
         for (int c = 0; c < m_valid; c += 16) {
           uint32_t r[16], ru[16];
@@ -777,6 +854,12 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
   const bool use_cluster = splits > 1 && splits <= 8 && g_splitk_mode == 0 &&
                            Cfg::ACCS * NT * BLOCK_N * 4 <= Cfg::STAGES * Cfg::STAGE_BYTES;
   p.cluster = use_cluster ? 1 : 0;
+  {
+    const bool res_ok = epi.residual == nullptr || (epi.ld_res % 4 == 0 && ((uintptr_t)epi.residual & 7) == 0);
+    p.wide_epi = (NT >= 64 && splits == 1 && g_wide_epi && (p.epi_mode == EPI_PLAIN || p.epi_mode == EPI_RES1 || p.epi_mode == EPI_AFFINE) &&
+                  N % 4 == 0 && ldo % 4 == 0 && ((uintptr_t)out & 7) == 0 && res_ok &&
+                  (int64_t)NT * BLOCK_N * 4 <= (int64_t)Cfg::STAGES * Cfg::STAGE_BYTES) ? 1 : 0;
+  }
   if (g_fuse != nullptr) {
     const TcFuse& f = *g_fuse;
     RD_REQUIRE(NT <= 32 && m_tiles == 1, "rd_linear_tc_fused: needs M <= 32");
