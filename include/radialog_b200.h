@@ -81,7 +81,7 @@ int rd_linear_force_splits(int splits);
  * the global fp32 workspace.  Both reduce in fixed split order (deterministic). */
 int rd_linear_splitk_mode(int mode);
 /* Launch every kernel with the programmatic-dependent-launch attribute (prologue of kernel N+1 — barrier init, TMEM
- * allocation, the first weight tiles — overlaps the tail of kernel N).  Off by default. */
+ * allocation, the first weight tiles — overlaps the tail of kernel N).  On by default; 0 switches it off. */
 int rd_set_pdl(int on);
 
 /* LlamaRMSNorm.forward (modeling_llama_imgemb.py:85-93): fp32 mean of squares, x*rsqrt in fp32, round, then

@@ -172,7 +172,8 @@ simt_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ w, int64
 // ------------------------------------------------------------------------------------------------
 // dispatcher
 // ------------------------------------------------------------------------------------------------
-static bool g_pdl = false;
+// programmatic dependent launch between the kernels of a step: on by default (3.77 vs 4.02 ms per B=32 decode step)
+static bool g_pdl = true;
 extern "C" int rd_set_pdl(int on) { g_pdl = on != 0; return RD_OK; }
 bool rd_pdl_enabled() { return g_pdl; }
 
