@@ -196,7 +196,7 @@ int rd_llm_prefill(rd_llm* h, const int64_t* ids_dev, const void* img_embeds_dev
  * the concatenated conversation, demo.py:282-297) and select the next token.                                    */
 int rd_llm_extend(rd_llm* h, const int64_t* ids_dev, int B, int T, int suppress_eos, void* stream);
 /* Roll the context back to its first new_ctx cached tokens before rd_llm_extend (npos_host[b] = attended tokens among
- * them, HOST pointer).  Synchronises the stream. */
+ * them, HOST pointer, consumed before the call returns).  Stream-ordered; does not synchronise. */
 int rd_llm_truncate(rd_llm* h, int new_ctx, const int32_t* npos_host, void* stream);
 /* A CUDA-graph replay of a captured rd_llm_decode_step advances the device-side counters only; this keeps the host
  * mirror used for bounds checks in step (n may be -1 to undo the bump of the capture call itself). */
@@ -207,6 +207,13 @@ int rd_llm_decode_step(rd_llm* h, void* stream);
  * finished flags (1 = row has emitted EOS), last-step logits [B, vocab].                                                                */
 int rd_llm_state(rd_llm* h, const int64_t** gen_tokens_dev, const int32_t** finished_dev,
                  const void** last_logits_dev, const void** hidden_dev, int* n_generated_host);
+/* Teacher forcing for parity tests: the next rd_llm_decode_step consumes toks_dev[B] (int64) instead of the engine's own
+ * greedy choice, which stays in the generation record.  Mirrors feeding the reference's `input_ids[:, -1:]`
+ * (prepare_inputs_for_generation, modeling_llama_imgemb.py:799-801) with an externally chosen token.               */
+int rd_llm_force_tokens(rd_llm* h, const int64_t* toks_dev, void* stream);
+/* Device word: 0 while any row is unfinished, else the number of generated tokens at which the last row emitted EOS
+ * (transformers 4.28.1 greedy_search: `unfinished_sequences.max() == 0`).  Copy it asynchronously to poll.          */
+int rd_llm_done_flag(rd_llm* h, const uint32_t** flag_dev);
 /* Per-kernel-class CUDA-event timing of the eager path (bench.py roofline): enable, run steps, read back.
  * classes: 0 rmsnorm 1 qkv 2 rope 3 attn 4 o 5 gate_up 6 down 7 lm_head 8 argmax 9 embed                         */
 int rd_llm_profile(rd_llm* h, int enable);

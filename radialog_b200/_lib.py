@@ -75,6 +75,8 @@ SIGNATURES = {
     "rd_llm_decode_step": (_i, [_p, _p]),
     "rd_llm_note_replayed_steps": (_i, [_p, _i]),
     "rd_llm_state": (_i, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_i)]),
+    "rd_llm_force_tokens": (_i, [_p, _p, _p]),
+    "rd_llm_done_flag": (_i, [_p, C.POINTER(_p)]),
     "rd_llm_profile": (_i, [_p, _i]),
     "rd_llm_profile_read": (_i, [_p, C.POINTER(_f), C.POINTER(_i), _i]),
     "rd_llm_launch_count": (_i64, [_p]),
@@ -101,11 +103,13 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise RuntimeError(f"{LIB_PATH} not found; run `python -m radialog_b200.build`")
+    if build_if_missing:
+        # build() is a no-op when lib/build.stamp matches the digest of csrc/ + the header: a stale .so (sources edited after
+        # the last build) is rebuilt instead of being loaded silently
         from . import build as _build
         _build.build()
+    elif not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found; run `python -m radialog_b200.build`")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch: fail loudly

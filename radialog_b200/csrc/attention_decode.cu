@@ -308,12 +308,12 @@ extern "C" int rd_attention_decode(const void* qkv, int64_t ldq, const int32_t* 
   const int pref = g_attn_prefetch ? (ctx_lower_bound < 0 ? 0 : ctx_lower_bound) : 0;
   RD_DISPATCH_DTYPE(dtype, T, {
     if (wide) {
-      RD_CHECK_CUDA(cudaFuncSetAttribute(attention_decode_kernel<T, 512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      RD_SMEM_ATTR_ONCE(200 * 1024, attention_decode_kernel<T, 512, 4>);
       RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 512, 4>, dim3(nh, B), dim3(512), smem, (cudaStream_t)stream, rd_pdl_enabled(),
                               (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
                               (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes));
     } else {
-      RD_CHECK_CUDA(cudaFuncSetAttribute(attention_decode_kernel<T, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      RD_SMEM_ATTR_ONCE(200 * 1024, attention_decode_kernel<T, 128, 3>);
       RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 128, 3>, dim3(nh, B), dim3(128), smem, (cudaStream_t)stream, rd_pdl_enabled(),
                               (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
                               (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes));

@@ -39,6 +39,19 @@ void rd_set_error(const char* fmt, ...);
 
 #define RD_LAUNCH_CHECK() RD_CHECK_CUDA(cudaGetLastError())
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: set it once per (kernel instantiation, device), so
+// that one process can drive engines on several GPUs.  Usage: RD_SMEM_ATTR_ONCE(bytes, kernel<T, ...>);
+#define RD_SMEM_ATTR_ONCE(bytes, ...)                                                                                   \
+  do {                                                                                                                  \
+    static bool _rd_attr_done[64] = {};                                                                                 \
+    int _rd_dev = 0;                                                                                                    \
+    RD_CHECK_CUDA(cudaGetDevice(&_rd_dev));                                                                             \
+    if (_rd_dev < 0 || _rd_dev >= 64 || !_rd_attr_done[_rd_dev]) {                                                      \
+      RD_CHECK_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+      if (_rd_dev >= 0 && _rd_dev < 64) _rd_attr_done[_rd_dev] = true;                                                  \
+    }                                                                                                                   \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------------
 // storage-type traits: every "T(.)" rounding point of the reference goes through Tr<T>::r
 // ------------------------------------------------------------------------------------------------

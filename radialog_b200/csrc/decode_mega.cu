@@ -1095,11 +1095,7 @@ void rd_mega_destroy(rd_mega* m) {
 template <class T>
 static int launch_mega(rd_mega* m, const MegaStep* s, cudaStream_t st) {
   const MegaCreate& c = m->c;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RD_CHECK_CUDA(cudaFuncSetAttribute(decode_mega_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  RD_SMEM_ATTR_ONCE(SMEM_BYTES, decode_mega_kernel<T>);
   CUtensorMap map_x, map_att, map_mid;
   RD_CHECK(make_map(&map_x, s->x, c.H, s->B, c.H, NT, c.dtype));
   RD_CHECK(make_map(&map_att, s->att, c.H, s->B, c.H, NT, c.dtype));

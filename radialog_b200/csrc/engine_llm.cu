@@ -87,6 +87,7 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
   RD_REQUIRE(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0, "rd_llm_create: hidden/inter must be multiples of 8");
   RD_REQUIRE(cfg->max_batch > 0 && cfg->max_ctx > 0 && cfg->max_ctx <= cfg->max_pos, "rd_llm_create: bad max_batch/max_ctx");
   RD_REQUIRE(cfg->dtype == RD_F16 || cfg->dtype == RD_BF16, "rd_llm_create: bad dtype");
+  RD_REQUIRE(cfg->img_id == 32000, "rd_llm_create: img_id %d unsupported (the <IMG> splice is built for id 32000, test.py:296-297)", cfg->img_id);
   int dev = 0;
   RD_CHECK_CUDA(cudaGetDevice(&dev));
   if (!rd_device_ok(dev)) return RD_ERR_UNSUPPORTED;
@@ -464,12 +465,13 @@ extern "C" int rd_llm_truncate(rd_llm* h, int new_ctx, const int32_t* npos_host,
   RD_REQUIRE(h && npos_host && h->B > 0, "rd_llm_truncate: no generation in flight");
   RD_REQUIRE(new_ctx >= 0 && new_ctx <= h->ctx_host, "rd_llm_truncate: new_ctx %d outside [0,%d]", new_ctx, h->ctx_host);
   cudaStream_t st = (cudaStream_t)stream;
-  RD_CHECK_CUDA(cudaStreamSynchronize(st));
+  // stream-ordered (no synchronisation): the sources are pageable host memory, which cudaMemcpyAsync stages before returning
   int32_t v[4] = {new_ctx, 0, 0, 0};
-  RD_CHECK_CUDA(cudaMemcpy(h->ctx_len, v, 4, cudaMemcpyHostToDevice));
-  RD_CHECK_CUDA(cudaMemset(h->n_gen, 0, 16));
-  RD_CHECK_CUDA(cudaMemcpy(h->npos, npos_host, (size_t)h->B * 4, cudaMemcpyHostToDevice));
-  RD_CHECK_CUDA(cudaMemset(h->finished, 0, (size_t)h->c.max_batch * 4));
+  RD_CHECK_CUDA(cudaMemcpyAsync(h->ctx_len, v, 4, cudaMemcpyHostToDevice, st));
+  RD_CHECK_CUDA(cudaMemsetAsync(h->n_gen, 0, 16, st));
+  RD_CHECK_CUDA(cudaMemcpyAsync(h->npos, npos_host, (size_t)h->B * 4, cudaMemcpyHostToDevice, st));
+  RD_CHECK_CUDA(cudaMemsetAsync(h->finished, 0, (size_t)h->c.max_batch * 4, st));
+  RD_CHECK_CUDA(cudaMemsetAsync(h->done_ctr, 0, 16, st));
   h->ctx_host = new_ctx; h->n_generated = 0;
   return RD_OK;
 }
@@ -497,7 +499,7 @@ extern "C" int rd_llm_decode_step(rd_llm* h, void* stream) {
   return RD_OK;
 }
 
-// 1 (default): single-token steps with B <= 32 run all layers in the persistent kernel of decode_mega.cu; 0: per-op kernels.
+// 1: single-token steps with B <= 32 run all layers in the persistent kernel of decode_mega.cu; 0 (default): per-op kernels.
 // Call it outside stream capture (switching it on may allocate the kernel's tables).
 extern "C" int rd_llm_set_mega(rd_llm* h, int on) {
   RD_REQUIRE(h, "rd_llm_set_mega: null handle");
@@ -540,6 +542,22 @@ extern "C" int rd_llm_state(rd_llm* h, const int64_t** gen, const int32_t** fini
   if (last_logits) *last_logits = h->logits;
   if (hidden) *hidden = h->x;
   if (n_generated) *n_generated = h->n_generated;
+  return RD_OK;
+}
+
+// Teacher forcing (parity harness, SURVEY.md section 7 "hard parts"): the token the NEXT decode step consumes is replaced by
+// toks_dev[b]; the engine's own greedy choice of the step stays in the generation record (rd_llm_state).
+extern "C" int rd_llm_force_tokens(rd_llm* h, const int64_t* toks_dev, void* stream) {
+  RD_REQUIRE(h && toks_dev && h->B > 0, "rd_llm_force_tokens: no generation in flight");
+  RD_CHECK_CUDA(cudaMemcpyAsync(h->cur_tok, toks_dev, (size_t)h->B * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return RD_OK;
+}
+
+// Device word the selection kernel keeps: 0 while any row is unfinished, else the number of tokens generated when the
+// last row emitted EOS (transformers 4.28.1 greedy_search stop rule).  The host polls it with an asynchronous copy.
+extern "C" int rd_llm_done_flag(rd_llm* h, const uint32_t** flag_dev) {
+  RD_REQUIRE(h && flag_dev, "rd_llm_done_flag: null argument");
+  *flag_dev = h->done_ctr + 1;
   return RD_OK;
 }
 

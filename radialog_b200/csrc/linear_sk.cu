@@ -566,11 +566,7 @@ int rd_sk_plan(rd_sk* c, int N, int K, int mode) {
 template <class T>
 static int launch_sk(rd_sk* c, const Plan& pl, const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N,
                      int K, int mode, const void* residual, int64_t ld_res, const SkNorm* norm, float* ssq_out, int dtype, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    RD_CHECK_CUDA(cudaFuncSetAttribute(linear_sk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  RD_SMEM_ATTR_ONCE(SMEM_BYTES, linear_sk_kernel<T>);
   CUtensorMap map_w, map_x;
   RD_CHECK(make_map(&map_w, w, ldw, mode == RD_SK_SWIGLU ? 2 * N : N, K, TILE_N, dtype));
   RD_CHECK(make_map(&map_x, x, ldx, M, K, NT, dtype));

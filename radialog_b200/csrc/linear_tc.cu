@@ -819,11 +819,7 @@ template <class T, int NT, bool SWIGLU>
 int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
               const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, int splits, cudaStream_t st) {
   using Cfg = TcCfg<NT, SWIGLU>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RD_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<T, NT, SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  RD_SMEM_ATTR_ONCE(Cfg::SMEM_BYTES, linear_tc_kernel<T, NT, SWIGLU>);
   CUtensorMap map_w, map_x;
   RD_CHECK(make_map(&map_w, w, ldw, SWIGLU ? 2 * N : N, K, BLOCK_N, dtype));
   RD_CHECK(make_map(&map_x, x, ldx, M, K, NT, dtype));

@@ -76,8 +76,7 @@ static int rmsnorm_impl(const void* x, const void* w, void* out, int M, int H, f
   RD_REQUIRE(M > 0 && H > 0 && H % 8 == 0, "rd_rmsnorm: bad shape M=%d H=%d", M, H);
   RD_REQUIRE(H * 4 <= 200 * 1024, "rd_rmsnorm: H=%d too large", H);
   RD_DISPATCH_DTYPE(dtype, T, {
-    static bool attr_set = false;
-    if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(rmsnorm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    RD_SMEM_ATTR_ONCE(200 * 1024, rmsnorm_kernel<T>);
     RD_CHECK_CUDA(rd_launch(rmsnorm_kernel<T>, dim3(M), dim3(256), (size_t)H * 4, (cudaStream_t)stream, rd_pdl_enabled(),
                             (const T*)x, (const T*)w, (T*)out, H, eps, (const T*)lora_a, lora_rows, (T*)lora_t, pf_ptr, pf_bytes));
     return RD_OK;
@@ -593,16 +592,14 @@ extern "C" int rd_attention(const void* qkv, int64_t ldq, const void* kc, const 
   const size_t atp_smem = (size_t)cmax * 128 * 2 * 2 + (size_t)ATP_WARPS * cmax * 4;
   if (q_len >= 4 && atp_smem <= 200 * 1024) {
     RD_DISPATCH_DTYPE(dtype, T, {
-      static bool attr_set2 = false;
-      if (!attr_set2) { RD_CHECK_CUDA(cudaFuncSetAttribute(attention_prefill_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set2 = true; }
+      RD_SMEM_ATTR_ONCE(200 * 1024, attention_prefill_kernel<T>);
       RD_CHECK_CUDA(rd_launch(attention_prefill_kernel<T>, dim3(nh, B), dim3(ATP_THREADS), atp_smem, (cudaStream_t)stream, rd_pdl_enabled(),
                               (const T*)qkv, ldq, (const T*)kc, (const T*)vc, keymask, ctx_len, (T*)out, q_len, nh, cmax));
       return RD_OK;
     });
   }
   RD_DISPATCH_DTYPE(dtype, T, {
-    static bool attr_set = false;
-    if (!attr_set) { RD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_set = true; }
+    RD_SMEM_ATTR_ONCE(160 * 1024, attention_kernel<T, false>);
     RD_CHECK_CUDA(rd_launch(attention_kernel<T, false>, dim3(q_len, nh, B), dim3(ATT_THREADS), (size_t)cmax * 4, (cudaStream_t)stream,
                             rd_pdl_enabled(), (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, q_len, nh, cmax,
                             (const int32_t*)nullptr, (const T*)nullptr, (const T*)nullptr));
@@ -743,6 +740,11 @@ argmax_step_kernel(const T* __restrict__ logits, int64_t ld, int V, int64_t* __r
         *done_ctr = 0;
         ctx_len[0] = ctx + q_len;
         n_gen[0] = step + 1;
+        // HF greedy_search stops once unfinished_sequences.max() == 0: publish that for the host's (lagging, non-blocking) poll
+        __threadfence();
+        int all_fin = 1;
+        for (int r = 0; r < (int)gridDim.x; ++r) all_fin &= (__ldcg(finished + r) != 0);
+        done_ctr[1] = all_fin ? (uint32_t)(step + 1) : 0u;     // 0 = still running, else number of tokens generated
       }
     }
   }

@@ -261,11 +261,11 @@ extern "C" int rd_small_attention(const void* q, int64_t ldq, const void* k, con
   RD_REQUIRE(smem <= 200 * 1024, "rd_small_attention: kv_len %d too large", kv_len);
   RD_DISPATCH_DTYPE(dtype, T, {
     if (hd == 64) {
-      RD_CHECK_CUDA(cudaFuncSetAttribute(small_attention_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      RD_SMEM_ATTR_ONCE(200 * 1024, small_attention_kernel<T, 64>);
       RD_CHECK_CUDA(rd_launch(small_attention_kernel<T, 64>, dim3(heads, B), dim3(256), smem, (cudaStream_t)stream, rd_pdl_enabled(), (const T*)q,
                               ldq, (const T*)k, (const T*)v, ldkv, (T*)out, ldo, q_len, kv_len));
     } else {
-      RD_CHECK_CUDA(cudaFuncSetAttribute(small_attention_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      RD_SMEM_ATTR_ONCE(200 * 1024, small_attention_kernel<T, 32>);
       RD_CHECK_CUDA(rd_launch(small_attention_kernel<T, 32>, dim3(heads, B), dim3(256), smem, (cudaStream_t)stream, rd_pdl_enabled(), (const T*)q,
                               ldq, (const T*)k, (const T*)v, ldkv, (T*)out, ldo, q_len, kv_len));
     }

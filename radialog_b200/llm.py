@@ -103,12 +103,14 @@ class LlamaForCausalLM:
         self.model = LlamaModel(cfg, torch_dtype, self.device, load_embedding_pickles)
         self._h = None
         self._cap = (0, 0)
-        self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
-        self._graph_kernels: Dict[int, int] = {}
+        self._graphs: Dict[Tuple[int, bool], torch.cuda.CUDAGraph] = {}
+        self._graph_kernels: Dict[Tuple[int, bool], int] = {}
+        self._flag_host: Optional[torch.Tensor] = None
+        self._timing_events = None
         self._capture_launches = 0
         self._replayed_kernels = 0
         self._n_prompt_cached = 0
-        self._cached_ids: Optional[torch.Tensor] = None     # host copy of the ids whose KV are in the cache
+        self._cached_ids: Optional[torch.Tensor] = None     # device copy of the ids whose KV are in the cache
         self._img_w_packed = None
         self.algo = _lib.ALGO_AUTO
         self.mega = False     # persistent all-layers decode kernel (experimental)
@@ -330,7 +332,7 @@ class LlamaForCausalLM:
             _lib.check(self._lib.rd_llm_set_streamk(self._h, 1 if on else 0), "set_streamk")
 
     def set_mega(self, on: bool):
-        """Single-token steps through the persistent all-layers kernel (default) or one kernel per op."""
+        """Single-token steps through the persistent all-layers kernel, or (default) one kernel per op."""
         self.mega = bool(on)
         self._graphs = {}
         if self._h is not None:
@@ -390,15 +392,16 @@ class LlamaForCausalLM:
     def generate(self, input_ids: torch.Tensor = None, dicom: Optional[Sequence[str]] = None, use_img: bool = False,
                  return_dict_in_generate: bool = False, output_scores: bool = False, max_new_tokens: int = 20, num_beams: int = 1,
                  img_embeds: Optional[torch.Tensor] = None, suppress_eos: bool = False, reuse_cache: bool = False,
-                 check_every: int = 16, **unused):
+                 check_every: int = 1, forced_tokens: Optional[torch.Tensor] = None, **unused):
         """Greedy decoding with the semantics of transformers 4.28.1 ``generate`` as the reference calls it
         (test.py:339-348, demo.py:290-297): attention mask inferred as ``ids != pad``, left padding, EOS rows emit pad.
 
         ``dicom`` looks the Q-Former tokens up in ``self.model.blip_embeddings`` (KeyError if unknown, like the reference);
         ``use_img`` reads ``current_chat_img.pt`` from the CWD; ``img_embeds`` is the direct device-tensor hand-off.
-        ``reuse_cache`` keeps the KV cache of the previous call and only runs the new suffix (multi-turn chat)."""
-        if num_beams != 1:
-            raise NotImplementedError("beam search is out of scope of the hot path (SURVEY.md section 8f row 4)")
+        ``reuse_cache`` keeps the KV cache of the previous call and only runs the new suffix (multi-turn chat).
+        ``num_beams > 1`` is HF beam search (test.py:267,467,629) over the flat KV cache, see ``_beam_search``.
+        ``forced_tokens`` [B, n] (parity harness): step s consumes ``forced_tokens[:, s]`` instead of the engine's own
+        choice (teacher forcing); ``.sequences`` still holds the engine's choices, ``.scores`` its logits."""
         if input_ids is None:
             raise ValueError("You have to specify either decoder_input_ids or decoder_inputs_embeds")
         ids = input_ids.to(self.device).long().contiguous()
@@ -412,20 +415,35 @@ class LlamaForCausalLM:
                 img_embeds = torch.tensor(np.array([self.model.blip_embeddings[d] for d in dicom]))   # :579 (KeyError propagates)
         if T + max_new_tokens + 1 > self.cfg.max_position_embeddings:
             raise ValueError(f"prompt ({T}) + max_new_tokens ({max_new_tokens}) exceeds max_position_embeddings")
+        if num_beams != 1:
+            if reuse_cache or forced_tokens is not None:
+                raise ValueError("beam search does not combine with reuse_cache / forced_tokens")
+            return self._beam_search(ids, img_embeds, num_beams, max_new_tokens, return_dict_in_generate, output_scores,
+                                     float(unused.get("length_penalty", 1.0)), bool(unused.get("early_stopping", False)))
+        if forced_tokens is not None:
+            forced_tokens = forced_tokens.to(self.device).long()
+            if forced_tokens.shape[0] != B or forced_tokens.shape[1] < max_new_tokens - 1:
+                raise ValueError("forced_tokens must be [B, >= max_new_tokens-1]")
+            forced_cols = [forced_tokens[:, s].contiguous() for s in range(forced_tokens.shape[1])]
         need_ctx = T + max_new_tokens + 1
         if not (reuse_cache and self._h is not None and B <= self._cap[0] and need_ctx <= self._cap[1]):
             self.reserve(B, max(need_ctx, 128))
+        with torch.cuda.device(self.device):
+            return self._generate_greedy(ids, img_embeds, B, T, max_new_tokens, suppress_eos, reuse_cache, check_every,
+                                         forced_cols if forced_tokens is not None else None, return_dict_in_generate, output_scores)
+
+    def _generate_greedy(self, ids, img_embeds, B, T, max_new_tokens, suppress_eos, reuse_cache, check_every, forced_cols,
+                         return_dict_in_generate, output_scores):
         st = _lib.current_stream()
-        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ev0, ev1, ev2 = self._events()
         ev0.record()
 
         # ---- prefill (or suffix-only extend when the cached conversation is a prefix of the new one) --------------------
-        ids_host = ids.cpu()
         start = 0
         if reuse_cache and self._cached_ids is not None and self._cached_ids.shape[0] == B:
-            start = self._common_prefix(ids_host)
+            start = self._common_prefix(ids)                  # device-side compare, one small read-back (multi-turn only)
         if start > 0:
-            npos = (ids_host[:, :start] != self.cfg.pad_token_id).sum(-1).to(torch.int32).contiguous()
+            npos = (ids[:, :start] != self.cfg.pad_token_id).sum(-1).to(torch.int32).cpu().contiguous()
             _lib.check(self._lib.rd_llm_truncate(self._h, start, npos.data_ptr(), st), "truncate")
             suffix = ids[:, start:].contiguous()
             _lib.check(self._lib.rd_llm_extend(self._h, _lib.ptr(suffix), B, T - start, int(suppress_eos), st), "extend")
@@ -437,24 +455,48 @@ class LlamaForCausalLM:
         Cmax, V = self._cap[1], self.cfg.vocab_size
         vpad = (V + 63) // 64 * 64
         gen_t = self._wrap(gen_p, (self._cap[0], Cmax), torch.int64)
-        fin_t = self._wrap(fin_p, (self._cap[0],), torch.int32)
         logits_t = self._wrap(logits_p, (self._cap[0], vpad), self.dtype)
         scores = []
         if output_scores:
             scores.append(logits_t[:B, :V].clone())
 
-        # ---- decode loop: one native call (or one CUDA-graph replay) per token ------------------------------------------------
+        # ---- decode loop: one native call (or one CUDA-graph replay) per token.  The stop rule of greedy_search ("all rows
+        # ---- finished") is a device word that is copied to pinned memory after every step and read WITHOUT blocking, so the
+        # ---- host keeps enqueueing ahead of the device and overshoots the real end by the few steps it is ahead.
+        flag_p = C.c_void_p()
+        _lib.check(self._lib.rd_llm_done_flag(self._h, C.byref(flag_p)), "done_flag")
+        flag_t = self._wrap(flag_p.value, (1,), torch.int32)
+        poll = not suppress_eos
+        if poll:
+            if self._flag_host is None or self._flag_host.numel() < max_new_tokens + 1:
+                self._flag_host = torch.zeros(max(max_new_tokens + 1, 512), dtype=torch.int32).pin_memory()
+            flags = self._flag_host
+            flags[:max_new_tokens + 1].zero_()
+            flags[0:1].copy_(flag_t, non_blocking=True)          # after the prefill's selection
+            poll_events = [torch.cuda.Event()]
+            poll_events[0].record()
+            oldest = 0
         n_done = 1
-        stop = False
-        while n_done < max_new_tokens and not stop:
-            self._decode_one(B, st, n_done)
+        stop_at = 0
+        while n_done < max_new_tokens and not stop_at:
+            if forced_cols is not None:
+                _lib.check(self._lib.rd_llm_force_tokens(self._h, _lib.ptr(forced_cols[n_done - 1]), st), "force_tokens")
+            self._decode_one(B, st, n_done, suppress_eos)
             n_done += 1
             if output_scores:
                 scores.append(logits_t[:B, :V].clone())
-            if not suppress_eos and (n_done % check_every == 0 or n_done == max_new_tokens):
-                stop = bool(fin_t[:B].all().item())
+            if poll and (n_done % check_every == 0 or n_done == max_new_tokens):
+                flags[n_done - 1:n_done].copy_(flag_t, non_blocking=True)
+                e = torch.cuda.Event()
+                e.record()
+                poll_events.append(e)
+                while oldest < len(poll_events) and poll_events[oldest].query():
+                    oldest += 1
+                done = flags[:n_done].max().item() if oldest > 0 else 0      # host memory: no device synchronisation
+                if done:
+                    stop_at = int(done)
         ev2.record()
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(self.device)
         gen = gen_t[:B, :n_done].clone()
         n_keep = n_done
         if not suppress_eos:
@@ -466,8 +508,9 @@ class LlamaForCausalLM:
                 n_keep = int(first.max().item()) + 1
         gen = gen[:, :n_keep]
         sequences = torch.cat([ids, gen], dim=-1)
-        # ids whose K/V are in the cache now: prompt + all generated tokens but the last one selected
-        self._cached_ids = torch.cat([ids_host, gen_t[:B, :n_done - 1].cpu()], dim=-1) if n_done > 0 else ids_host
+        # ids whose K/V are in the cache now: prompt + all tokens that were fed back (device tensor; no host copy)
+        fed = gen_t[:B, :n_done - 1] if forced_cols is None else torch.stack(forced_cols[:n_done - 1], 1) if n_done > 1 else gen_t[:B, :0]
+        self._cached_ids = torch.cat([ids, fed], dim=-1)
         self._n_prompt_cached = T
         self.last_stats = {"prefill_ms": ev0.elapsed_time(ev1), "decode_ms": ev1.elapsed_time(ev2), "new_tokens": n_done,
                            "prefill_tokens": T - start, "reused_tokens": start}
@@ -475,23 +518,34 @@ class LlamaForCausalLM:
             return GreedySearchDecoderOnlyOutput(sequences=sequences, scores=tuple(scores[:n_keep]) if output_scores else None)
         return sequences
 
-    def _decode_one(self, B: int, st: int, n_done: int):
+    def _beam_search(self, ids, img_embeds, num_beams, max_new_tokens, return_dict_in_generate, output_scores, length_penalty,
+                     early_stopping):
+        raise NotImplementedError("beam search is not built yet (SURVEY.md section 8f row 4)")
+
+    def _events(self):
+        if self._timing_events is None:
+            self._timing_events = tuple(torch.cuda.Event(enable_timing=True) for _ in range(3))
+        return self._timing_events
+
+    def _decode_one(self, B: int, st: int, n_done: int, suppress_eos: bool = False):
         if not self.use_cuda_graph or n_done < 2:
             # the first decode step always runs eagerly (lazy function-attribute setup must not happen under capture)
             _lib.check(self._lib.rd_llm_decode_step(self._h, st), "decode_step")
             return
-        g = self._graphs.get(B)
+        # a captured step bakes in its by-value kernel arguments (suppress_eos of the selection kernel): one graph per flag value
+        key = (B, bool(suppress_eos))
+        g = self._graphs.get(key)
         if g is None:
             before = int(self._lib.rd_llm_launch_count(self._h))
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 _lib.check(self._lib.rd_llm_decode_step(self._h, _lib.current_stream()), "decode_step(capture)")
             _lib.check(self._lib.rd_llm_note_replayed_steps(self._h, -1), "note")   # capture recorded, did not run
-            self._graphs[B] = g
-            self._graph_kernels[B] = int(self._lib.rd_llm_launch_count(self._h)) - before
-            self._capture_launches += self._graph_kernels[B]
+            self._graphs[key] = g
+            self._graph_kernels[key] = int(self._lib.rd_llm_launch_count(self._h)) - before
+            self._capture_launches += self._graph_kernels[key]
         g.replay()
-        self._replayed_kernels += self._graph_kernels[B]
+        self._replayed_kernels += self._graph_kernels[key]
         _lib.check(self._lib.rd_llm_note_replayed_steps(self._h, 1), "note")
 
     def launch_count(self) -> int:
@@ -521,25 +575,25 @@ class LlamaForCausalLM:
         self._cached_ids = None
         return {name: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, name in enumerate(_lib.PROFILE_CLASSES)}
 
-    def _common_prefix(self, ids_host: torch.Tensor) -> int:
-        """Longest prefix (same for all rows) of the new conversation whose KV entries are already cached and valid."""
+    def _common_prefix(self, ids: torch.Tensor) -> int:
+        """Longest prefix (same for all rows) of the new conversation whose KV entries are already cached and valid.
+        Runs on the device tensors; only the two resulting scalars are read back."""
         cached = self._cached_ids
-        L = min(cached.shape[1], ids_host.shape[1] - 1)       # always leave one token to run
+        L = min(cached.shape[1], ids.shape[1] - 1)       # always leave one token to run
         if L <= 0:
             return 0
-        eq = cached[:, :L] == ids_host[:, :L]
+        eq = cached[:, :L] == ids[:, :L]
         # a generated pad(0) has mask 1 in the cache but would be masked by a fresh prefill: stop before it
-        gen_region = torch.arange(L)[None] >= self._n_prompt_cached
-        ok = eq & ~(gen_region & (ids_host[:, :L] == self.cfg.pad_token_id))
+        gen_region = torch.arange(L, device=ids.device)[None] >= self._n_prompt_cached
+        ok = eq & ~(gen_region & (ids[:, :L] == self.cfg.pad_token_id))
         bad = (~ok).float().cumsum(-1) > 0
         per_row = (~bad).sum(-1)
-        start = int(per_row.min().item())
         # the <IMG> block must be entirely inside the reused prefix (extend does not splice)
-        img_pos = (ids_host == IMG_TOKEN_ID)
-        if bool(img_pos.any()):
-            last_img = int(torch.where(img_pos.any(0))[0].max().item())
-            if start <= last_img:
-                return 0
+        img_cols = (ids == IMG_TOKEN_ID).any(0)
+        last_img = torch.where(img_cols, torch.arange(ids.shape[1], device=ids.device), -1).max()
+        start, last_img = (int(v) for v in torch.stack([per_row.min(), last_img]).tolist())
+        if start <= last_img:
+            return 0
         return start
 
 

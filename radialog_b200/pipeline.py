@@ -122,12 +122,16 @@ def precompute_embeddings(vision, batches, path: Optional[str] = None) -> Dict[s
     return embs
 
 
-def save_chat_image(q_out_row: "torch.Tensor", path: str = "current_chat_img.pt") -> None:
-    """demo.py:269-273: the conversational path parks the image's ``[32, 768]`` Q-Former output in ``current_chat_img.pt`` (CWD),
-    which ``generate(use_img=True)`` reads back (modeling_llama_imgemb.py:576)."""
-    if q_out_row.dim() != 2:
-        raise ValueError(f"expected [num_query_tokens, hidden], found {tuple(q_out_row.shape)}")
-    torch.save(q_out_row.detach().float().cpu(), path)
+def save_chat_image(q_out: "torch.Tensor", path: str = "current_chat_img.pt") -> None:
+    """demo.py:269-272: the conversational path saves ``forward_image(image)[0]`` - a ``[1, 32, 768]`` float32 tensor - to
+    ``current_chat_img.pt`` in the CWD; ``generate(use_img=True)`` reads it back (modeling_llama_imgemb.py:576), and the
+    reference's reader iterates dim 0 as the batch.  Accepts ``[1, 32, 768]`` (the reference call, verbatim) or one row
+    ``[32, 768]``; always writes ``[1, 32, 768]`` float32 so that the file also feeds the reference's own reader."""
+    if q_out.dim() == 2:
+        q_out = q_out[None]
+    if q_out.dim() != 3 or q_out.shape[0] != 1:
+        raise ValueError(f"expected [1, num_query_tokens, hidden] or [num_query_tokens, hidden], found {tuple(q_out.shape)}")
+    torch.save(q_out.detach().float().cpu().contiguous(), path)
 
 
 class ReportPipeline:

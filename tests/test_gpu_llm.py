@@ -122,6 +122,26 @@ def test_eos_handling_matches_hf_semantics(cuda_dev):
         assert out.shape == o_ids.shape
 
 
+def test_cuda_graph_replay_honours_suppress_eos_of_each_call(cuda_dev):
+    """A captured decode step bakes suppress_eos into the selection kernel's arguments; alternating the flag on ONE engine
+    must give what eager launches give (graphs are keyed on the flag), in both orders."""
+    dtype = torch.float16
+    cfg = synth.tiny_llama_cfg()
+    sd = synth.make_llama_weights(cfg, seed=3, dtype=torch.float32)
+    sd = {k: v.to(torch.float16).float() for k, v in sd.items()}
+    sd["lm_head.weight"][cfg.eos_token_id] *= 4.0      # EOS likely: the two flag values give different sequences
+    model = LlamaForCausalLM.from_state_dict(cfg, sd, torch_dtype=dtype, device=cuda_dev)
+    prompts = synth.make_prompts(4, seed=11, ragged=True).to(cuda_dev)
+    img = img_tokens(4, cfg, seed=12).to(cuda_dev)
+    model.use_cuda_graph = False
+    eager = {f: model.generate(prompts, img_embeds=img, max_new_tokens=24, suppress_eos=f).cpu() for f in (True, False)}
+    assert eager[True].shape != eager[False].shape or not torch.equal(eager[True], eager[False])
+    model.use_cuda_graph = True
+    for f in (True, False, True, False):
+        got = model.generate(prompts, img_embeds=img, max_new_tokens=24, suppress_eos=f).cpu()
+        assert got.shape == eager[f].shape and torch.equal(got, eager[f]), f"graph replay with suppress_eos={f} differs from eager"
+
+
 def test_multi_turn_prefix_reuse_equals_full_reprefill(cuda_dev):
     """Config 5: follow-up turns run only the new suffix; tokens must equal a full re-prefill of the conversation."""
     dtype = torch.float16

@@ -126,7 +126,7 @@ def test_data_parallel_world2_gloo(tmp_path):
 
 def test_embedding_pickle_and_chat_image_formats(tmp_path, monkeypatch):
     """The reference's on-disk hand-offs (pretraining/train.py:139-149, demo.py:269-273) written by the pipeline helpers are
-    what modeling_llama_imgemb.py:454-462,576 reads: {dicom: np.float32[32,768]} pickles relative to the CWD, a [32,768] .pt."""
+    what modeling_llama_imgemb.py:454-462,576 reads: {dicom: np.float32[32,768]} pickles relative to the CWD, a [1,32,768] .pt."""
     import pickle
 
     import numpy as np
@@ -145,9 +145,14 @@ def test_embedding_pickle_and_chat_image_formats(tmp_path, monkeypatch):
     import pytest
     with pytest.raises(ValueError):
         pipeline.write_embedding_pickle(EMB_PKL_TEST, {"bad": torch.zeros(768)})
-    pipeline.save_chat_image(torch.randn(32, 768, dtype=torch.float16))
-    t = torch.load(CHAT_IMG_FILE)
-    assert t.shape == (32, 768) and t.dtype == torch.float32
+    # demo.py:269-272 saves forward_image(...)[0] = [1,32,768]; a single row is accepted too; the file is always [1,32,768]
+    for src in (torch.randn(1, 32, 768), torch.randn(32, 768, dtype=torch.float16)):
+        pipeline.save_chat_image(src)
+        t = torch.load(CHAT_IMG_FILE)
+        assert t.shape == (1, 32, 768) and t.dtype == torch.float32
+        assert torch.equal(t[0], src.reshape(32, 768).float())
+    with pytest.raises(ValueError):
+        pipeline.save_chat_image(torch.randn(2, 32, 768))
 
     class FakeVision:
         def forward_image(self, images):

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--splits", default="0")
     ap.add_argument("--dtype", default="float16")
     ap.add_argument("--splitk-mode", type=int, default=0, help="0 cluster/DSMEM reduction, 1 global workspace")
+    ap.add_argument("--nbuf", type=int, default=0, help="weight buffers cycled through (0 = enough to exceed L2; 1 = L2-resident weights)")
+    ap.add_argument("--shapes", default="", help="comma list of shape names (default all)")
     args = ap.parse_args()
     lib = _lib.load()
     lib.rd_set_pdl(args.pdl)
@@ -40,8 +42,10 @@ def main():
     ws = torch.zeros(512 << 20, dtype=torch.uint8, device=dev)
     results = []
     for name, N, K, act in SHAPES:
+        if args.shapes and name not in args.shapes.split(","):
+            continue
         rows = 2 * N if act == 3 else N
-        nbuf = max(2, int(400e6 // (rows * K * 2)) + 1)
+        nbuf = args.nbuf if args.nbuf > 0 else max(2, int(400e6 // (rows * K * 2)) + 1)
         Ws = [(torch.randn(rows, K, device=dev) * 0.02).to(dtype) for _ in range(nbuf)]
         for M in [int(m) for m in args.ms.split(",")]:
             x = (torch.randn(M, K, device=dev) * 0.5).to(dtype)
