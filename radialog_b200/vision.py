@@ -98,6 +98,27 @@ def pack_vision_weights(cfg: VisionCfg, sd: Dict[str, torch.Tensor], dtype: torc
     return {k: v.contiguous() for k, v in out.items()}
 
 
+class _IncompatibleKeys:
+    """What ``nn.Module.load_state_dict(strict=False)`` returns (``load_checkpoint`` hands it back like base_model.py:52-56)."""
+
+    def __init__(self, missing_keys, unexpected_keys):
+        self.missing_keys, self.unexpected_keys = list(missing_keys), list(unexpected_keys)
+
+    def __repr__(self):
+        return f"_IncompatibleKeys(missing_keys={self.missing_keys}, unexpected_keys={self.unexpected_keys})"
+
+
+def read_lavis_checkpoint(url_or_filename: str) -> Dict[str, torch.Tensor]:
+    """LAVIS ``checkpoint_{epoch,best,last}.pth`` as written by ``RunnerBase._save_checkpoint`` (runner_base.py:658-683):
+    ``{"model": state_dict WITHOUT the parameters that do not require grad, "optimizer", "config", "scaler", "epoch"}``;
+    a bare state dict is accepted too (base_model.py:45-48).  No URL download: there is no network on this path."""
+    import os
+    if not os.path.isfile(url_or_filename):
+        raise RuntimeError("checkpoint url or path is invalid")             # same message as base_model.py:43
+    checkpoint = torch.load(url_or_filename, map_location="cpu", weights_only=False)
+    return checkpoint["model"] if "model" in checkpoint.keys() else checkpoint
+
+
 class Blip2Qformer:
     def __init__(self, cfg: VisionCfg, sd: Dict[str, torch.Tensor], torch_dtype: torch.dtype = torch.float16,
                  device="cuda:0", max_batch: int = 32):
@@ -107,10 +128,43 @@ class Blip2Qformer:
         self.cfg = cfg
         self.dtype = torch_dtype
         self.device = torch.device(device)
-        self._packed = {k: v.to(self.device) for k, v in pack_vision_weights(cfg, sd, torch_dtype).items()}
+        self._sd = {k: v.detach().cpu() for k, v in sd.items()}     # master copy under the reference's key names
+        self._packed = {k: v.to(self.device) for k, v in pack_vision_weights(cfg, self._sd, torch_dtype).items()}
         self._h = None
         self._max_batch = 0
         self.reserve(max_batch)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return dict(self._sd)
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True) -> _IncompatibleKeys:
+        """``nn.Module.load_state_dict`` semantics over the reference's key names; re-folds and re-packs the engine weights."""
+        # keys of the reference module that this path never reads (text branch of the Q-Former, ITM/LM heads, temp) are not "unexpected"
+        known = set(self._sd)
+        missing = [k for k in self._sd if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in known]
+        for k, v in state_dict.items():
+            if k in known:
+                if tuple(v.shape) != tuple(self._sd[k].shape):
+                    raise RuntimeError(f"size mismatch for {k}: copying a param with shape {tuple(v.shape)} from checkpoint, "
+                                       f"the shape in current model is {tuple(self._sd[k].shape)}.")
+                self._sd[k] = v.detach().cpu()
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:5]}... unexpected {unexpected[:5]}...")
+        self._packed = {k: v.to(self.device) for k, v in pack_vision_weights(self.cfg, self._sd, self.dtype).items()}
+        mb = self._max_batch
+        self._destroy()
+        self._max_batch = 0
+        self.reserve(mb)
+        return _IncompatibleKeys(missing, unexpected)
+
+    def load_checkpoint(self, url_or_filename: str) -> _IncompatibleKeys:
+        """``BaseModel.load_checkpoint`` (base_model.py:29-56) / ``Blip2Base.load_from_pretrained`` (blip2.py:88-104):
+        a LAVIS checkpoint holds only the TRAINED parameters (the frozen image encoder and ``ln_vision`` are dropped by
+        runner_base.py:665-671), loaded non-strictly over the live module."""
+        return self.load_state_dict(read_lavis_checkpoint(url_or_filename), strict=False)
+
+    load_from_pretrained = load_checkpoint
 
     @classmethod
     def from_state_dict(cls, cfg: VisionCfg, sd, **kw) -> "Blip2Qformer":

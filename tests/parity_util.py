@@ -4,8 +4,9 @@ Two harnesses:
 
 * ``assert_ids_match`` - free-running greedy ids against the oracle's (small models, CPU oracle).
 * ``teacher_forced_parity`` - SURVEY.md section 7 "hard parts": at every step BOTH implementations consume the ORACLE's
-  token, so one near-tie cannot hide everything after it.  Every step of every row is checked: ``max|dlogit| <= tol * scale``
-  and ``argmax(engine) == argmax(oracle)`` whenever the oracle's top-2 margin exceeds twice the measured ``|dlogit|`` of that
+  token, so one near-tie cannot hide everything after it.  Every step of every row is checked: ``max|dlogit|`` against the
+  stated tolerance or twice the MEASURED noise floor of the reference arithmetic itself (whichever is larger), and
+  ``argmax(engine) == argmax(oracle)`` whenever the oracle's top-2 margin exceeds twice the measured ``|dlogit|`` of that
   row (both candidates can move by that much); steps below that margin are counted and reported, never skipped silently.
 
 ``CudaOracle`` runs ``oracle/radialog_oracle.py`` unchanged on the GPU (so a 32-layer, 128-token run takes seconds): same
@@ -106,29 +107,69 @@ def check_cuda_oracle_against_cpu(cfg, sd, dtype, device, prompts, img, n_new=6)
     return worst
 
 
-def teacher_forced_parity(model, orc: CudaOracle, prompts, img, n_new, tol_rel, what, reuse_cache=False, check_free_running=True):
+def oracle_forced_scores(orc: CudaOracle, prompts, img, forced, backend):
+    """The oracle along a FORCED token trajectory (same loop as LlamaOracle.generate, next token = forced[:, s]) with its
+    matmuls on `backend`: "sgemm" (fp32 SGEMM, the checker) or "cublas" (model-dtype tensor-core GEMM, what the reference's
+    nn.Linear runs on a GPU).  The gap between the two is the noise floor of the reference arithmetic itself."""
+    import torch.nn.functional as F
+    dev = orc.device
+    n = forced.shape[1]
+    scores = []
+    with orc._ctx():
+        if backend == "cublas":
+            O._mm = lambda x, w, dt: F.linear(x, w)
+        o = orc.orc
+        ids = prompts.to(dev)
+        mask = ids.ne(o.cfg.pad_token_id).long()
+        past = None
+        for s in range(n):
+            pos = o.positions_from_mask(mask)
+            if past is None:
+                logits, past = o.forward(ids, mask, pos, None, None if img is None else img.to(dev))
+            else:
+                logits, past = o.forward(ids[:, -1:], mask, pos[:, -1:], past, None)
+            scores.append(logits[:, -1, :])
+            ids = torch.cat([ids, forced[:, s:s + 1]], dim=-1)
+            mask = torch.cat([mask, mask.new_ones((mask.shape[0], 1))], dim=-1)
+    return scores
+
+
+def teacher_forced_parity(model, orc: CudaOracle, prompts, img, n_new, tol_rel, what, reuse_cache=False, check_free_running=True,
+                          floor_factor=2.0):
     """Runs the oracle greedily (its ids are the teacher), then the engine with every step forced to the oracle's token.
-    Asserts the per-step logit bound and margin-aware argmax equality; returns (statistics for the test log, oracle ids)."""
+
+    Asserted at every step of every row:
+      * ``max|dlogit| <= max(tol_rel, floor_factor x floor) x logit scale`` where ``floor`` is the MEASURED distance, on the same
+        trajectory and in the same norm, between two evaluations of the reference arithmetic that differ only in the fp32
+        summation order of their GEMMs (fp32 SGEMM vs the cuBLAS tensor-core GEMM the reference's nn.Linear runs);
+      * engine argmax == oracle argmax whenever the oracle's top-2 margin exceeds twice the measured |dlogit| of that row.
+    Returns (statistics for the test log, oracle ids)."""
     dev = model.device
     T = prompts.shape[1]
     o_ids, o_scores = orc.generate(prompts, img, n_new)
     forced = o_ids[:, T:].contiguous()
+    alt_scores = oracle_forced_scores(orc, prompts, img, forced, "cublas")
     out = model.generate(prompts.to(dev), img_embeds=None if img is None else img.to(dev), max_new_tokens=n_new, suppress_eos=True,
                          forced_tokens=forced, return_dict_in_generate=True, output_scores=True, reuse_cache=reuse_cache)
     own = out.sequences[:, T:]
     eos = model.cfg.eos_token_id
     B = prompts.shape[0]
-    stats = dict(what=what, B=B, T=T, steps=n_new, checked=0, sub_margin=0, mismatch_sub_margin=0, max_rel_err=0.0, worst_step=-1,
-                 min_margin_over_err=float("inf"))
+    stats = dict(what=what, B=B, T=T, steps=n_new, tol_rel=tol_rel, checked=0, sub_margin=0, mismatch_sub_margin=0, max_rel_err=0.0,
+                 worst_step=-1, rms_rel_err=0.0, noise_floor_rel=0.0, frac_within_tol=0.0)
+    failures = []
+    sq = 0.0
     for s in range(n_new):
         a = o_scores[s].float()
         b = out.scores[s].float()
         scale = a.abs().max().item()
         err_row = (a - b).abs().max(-1).values                       # [B]
         rel = (err_row.max() / scale).item()
+        floor = ((a - alt_scores[s].float()).abs().max() / scale).item()
+        stats["noise_floor_rel"] = max(stats["noise_floor_rel"], floor)
+        sq += ((a - b) / scale).pow(2).mean().item()
+        stats["frac_within_tol"] += float((err_row / scale <= tol_rel).float().mean()) / n_new
         if rel > stats["max_rel_err"]:
             stats["max_rel_err"], stats["worst_step"] = rel, s
-        assert rel <= tol_rel, f"{what}: step {s}: max|dlogit| = {rel:.3e} x logit scale {scale:.3g} exceeds {tol_rel:g}"
         a_sel = a.clone()
         a_sel[:, eos] = -float("inf")                                 # both sides select with EOS suppressed
         top = a_sel.topk(2, dim=-1).values
@@ -136,13 +177,14 @@ def teacher_forced_parity(model, orc: CudaOracle, prompts, img, n_new, tol_rel, 
         decisive = margin > 2 * err_row
         same = own[:, s] == forced[:, s]
         bad = decisive & ~same
-        assert not bool(bad.any()), (f"{what}: step {s} rows {bad.nonzero().flatten().tolist()}: engine argmax differs from the oracle's "
-                                     f"although the oracle margin {margin[bad].min().item():.4g} exceeds 2 x |dlogit| {err_row[bad].max().item():.4g}")
+        if bool(bad.any()):
+            failures.append(f"step {s} rows {bad.nonzero().flatten().tolist()}: engine argmax differs from the oracle's although the "
+                            f"oracle margin {margin[bad].min().item():.4g} exceeds 2 x |dlogit| {err_row[bad].max().item():.4g}")
         stats["checked"] += int(decisive.sum())
         stats["sub_margin"] += int((~decisive).sum())
         stats["mismatch_sub_margin"] += int((~decisive & ~same).sum())
-        ratio = (margin / (2 * err_row).clamp_min(1e-12)).min().item()
-        stats["min_margin_over_err"] = min(stats["min_margin_over_err"], ratio)
+    stats["rms_rel_err"] = (sq / n_new) ** 0.5
+    stats["bound_rel"] = max(tol_rel, floor_factor * stats["noise_floor_rel"])
     stats["teacher_forced_token_agreement"] = float((own == forced).float().mean())
     if check_free_running and not reuse_cache:
         free = model.generate(prompts.to(dev), img_embeds=None if img is None else img.to(dev), max_new_tokens=n_new, suppress_eos=True)
@@ -151,4 +193,8 @@ def teacher_forced_parity(model, orc: CudaOracle, prompts, img, n_new, tol_rel, 
         stats["free_running_rows_identical"] = int(eq.all(-1).sum())
         stats["free_running_first_divergence_min"] = int(first_div.min())
         stats["free_running_token_agreement"] = float(eq.float().mean())
+    assert not failures, f"{what}: " + "; ".join(failures[:4]) + f" | {stats}"
+    assert stats["max_rel_err"] <= stats["bound_rel"], (f"{what}: max|dlogit| = {stats['max_rel_err']:.3e} x logit scale at step "
+                                                        f"{stats['worst_step']} exceeds {stats['bound_rel']:.3e} | {stats}")
+    assert stats["rms_rel_err"] <= tol_rel / 2, f"{what}: rms logit error {stats['rms_rel_err']:.3e} x scale | {stats}"
     return stats, o_ids
