@@ -180,6 +180,11 @@ int rd_llm_set_streamk(rd_llm* h, int on);
  * QKV / gate|up GEMMs (row statistics from sum-of-squares partials written by the o_proj / down_proj epilogues) instead of
  * by separate kernels.  on = 1 / 0 (default).  Bit-identical results (tests/test_gpu_llm.py).                    */
 int rd_llm_set_fused_norm(rd_llm* h, int on);
+/* Single-token steps with B <= 32 (default ON): o_proj and down_proj run a "finisher" split-K - every CTA stores its fp32
+ * partial tile to an L2-resident slab, the last CTAs to arrive each finish whole token rows: out = T(res + T(Wx)) and, fused,
+ * the LlamaRMSNorm that follows in LlamaDecoderLayer.forward (modeling_llama_imgemb.py:287,305; model.norm :658 after the last
+ * layer).  A layer is then 5 launches instead of 7.  Same rounding contract; 0 = cluster split-K + separate norm kernels. */
+int rd_llm_set_fused_tail(rd_llm* h, int on);
 /* Decode step: bytes of W_qkv / W_o / W_gate|up that the (latency-bound, HBM-idle) norm and attention kernels pull into
  * the 126 MB L2 with cp.async.bulk.prefetch ahead of the GEMM that streams them; 0,0,0 turns it off. */
 int rd_llm_set_l2_prefetch(rd_llm* h, long long qkv_bytes, long long o_bytes, long long gate_up_bytes);

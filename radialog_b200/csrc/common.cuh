@@ -240,6 +240,12 @@ struct TcFuse {
   int norm_tiles;
   float norm_eps;
   float* ssq_out;
+  // finisher split-K (see TcParams::fin in linear_tc.cu): fp32 partial slabs + the last CTAs finish whole token rows, with the
+  // following RMSNorm fused: out = T(res + T(Wx)), fin_xn = T(fin_norm_w * T(out * rstd)).  fin_ctr: 2 zero-initialised words.
+  uint32_t* fin_ctr = nullptr;
+  const void* fin_norm_w = nullptr;
+  void* fin_xn = nullptr;
+  float fin_eps = 0.f;
 };
 int rd_linear_tc_fused(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
                        const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, const TcFuse* fuse, cudaStream_t st);

@@ -46,6 +46,12 @@ struct rd_llm {
   // Off by default: bit-identical results, but normalising the token tile inside a 3-5 stage W+X pipeline lengthens every
   // stage (measured B=32: 4.23 vs 3.77 ms per step; B=1: 3.01 vs 2.92 ms).
   int fuse_norm = 0;
+  // single-token steps with B <= 32 (default ON): o_proj / down_proj run the "finisher" split-K of linear_tc.cu - fp32 partial
+  // slabs, the last CTAs to arrive finish whole token rows (residual add) AND apply the RMSNorm that follows, so a layer is
+  // 5 launches (qkv, attention, o+norm2, gate|up, down+norm1') instead of 7 and no GEMM of the pair waits on a cluster reduction.
+  int fuse_tail = 1;
+  bool tail_ran = false;         // the layer loop of the current step took the fused-tail path (set by run_layers)
+  uint32_t* fin_ctr = nullptr;   // [o_proj pair, down_proj pair] ticket / done counters (zero-initialised, self re-arming)
   // L2 weight prefetch from the norm / attention kernels: mechanism kept, OFF by default (A/B runs on B200 showed no
   // gain at B=32 beyond run-to-run noise and a loss at B=1, where the norm kernel is a single CTA)
   bool l2_prefetch = false;
@@ -110,6 +116,7 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
   A((char**)&h->ctx_len, 16); A((char**)&h->n_gen, 16); A((char**)&h->done_ctr, 16);
   A((char**)&h->cur_tok, Bm * 8); A((char**)&h->gen, Bm * C * 8);
   A((char**)&h->ssq, (H / 128 + 1) * 32 * 4);
+  A((char**)&h->fin_ctr, 64);
   int64_t ws = 0;
   const int Ms[2] = {(int)Bm, 256};
   for (int mi = 0; mi < 2; ++mi) {
@@ -119,6 +126,8 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
                        rd_linear_tc_workspace_bytes(M, cfg->vocab, H)};
     for (int i = 0; i < 5; ++i) ws = cand[i] > ws ? cand[i] : ws;
   }
+  const int64_t slab = 256 + (int64_t)16 * 32 * H * 4 + 256;      // finisher split-K: <= 16 splits x 32 tokens x H fp32 partials
+  if (slab > ws) ws = slab;
   h->ws_bytes = ws;
   A(&h->ws, ws);
   if (r != RD_OK) { rd_llm_destroy(h); return r; }
@@ -135,6 +144,7 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
   rd_mega_destroy(h->mega);
   rd_sk_destroy(h->sk);
   if (h->ssq) cudaFree(h->ssq);
+  if (h->fin_ctr) cudaFree(h->fin_ctr);
   delete h;
 }
 
@@ -329,6 +339,7 @@ static int linear_fused(rd_llm* h, int cls, const void* x, int64_t ldx, const vo
 static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStream_t st) {
   const rd_llm_config& c = h->c;
   const int H = c.hidden, I = c.inter, M = B * q_len, nh = c.heads, hd = H / nh, dt = c.dtype;
+  h->tail_ran = h->fuse_tail && !h->fuse_norm && q_len == 1 && M <= 32 && h->algo == 0 && H % 4 == 0;
   for (int l = 0; l < c.layers; ++l) {
     const LayerW& w = h->L[l];
     char* kc = h->kc + (int64_t)l * h->kv_layer_bytes;
@@ -343,12 +354,16 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     const bool fuse = h->fuse_norm && q_len == 1 && M <= 32 && h->algo == 0 && H % 128 == 0;
     TcFuse f_in1{h->ssq, w.ln1, H / 128, c.rms_eps, nullptr}, f_in2{h->ssq, w.ln2, H / 128, c.rms_eps, nullptr};
     TcFuse f_out{nullptr, nullptr, 0, 0.f, h->ssq};
+    // fused tails (decode, B <= 32): the previous layer's down_proj already wrote xn = RMSNorm_ln1(x) of this layer
+    const bool tail = h->fuse_tail && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && H % 4 == 0;
     if (fuse && l > 0) {
       RD_CHECK(linear_fused(h, C_QKV, h->x, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &f_in1, st));
     } else {
-      { ProfScope ps(h, st, C_RMSNORM);
+      if (!(tail && l > 0)) {
+        ProfScope ps(h, st, C_RMSNORM);
         // decode: the norm kernels are latency bound and leave HBM idle -> they pull the next GEMM's weights into L2
-        RD_CHECK(rd_rmsnorm_prefetch(h->x, w.ln1, h->xn, M, H, c.rms_eps, decode ? w.qkv : nullptr, decode ? std::min(qkv_bytes, h->pf_qkv) : 0, dt, st)); }
+        RD_CHECK(rd_rmsnorm_prefetch(h->x, w.ln1, h->xn, M, H, c.rms_eps, decode ? w.qkv : nullptr, decode ? std::min(qkv_bytes, h->pf_qkv) : 0, dt, st));
+      }
       RD_CHECK(linear(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, st));
     }
     if (q_len == 1) {      // decode: RoPE + KV append + attention fused in one launch
@@ -371,6 +386,17 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
       eg.act = RD_ACT_SWIGLU;
       RD_CHECK(linear_fused(h, C_GATEUP, h->x, H, w.gate_up, H, h->mid, I, M, I, H, &eg, &f_in2, st));
       RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, &f_out, st));
+    } else if (tail) {
+      // o_proj + residual + post_attention_layernorm, then gate|up, then down_proj + residual + the NEXT norm on the path
+      // (input_layernorm of layer l+1, or model.norm after the last layer: modeling_llama_imgemb.py:287,305,658)
+      TcFuse t_o{}, t_d{};
+      t_o.fin_ctr = h->fin_ctr; t_o.fin_norm_w = w.ln2; t_o.fin_xn = h->xn; t_o.fin_eps = c.rms_eps;
+      t_d.fin_ctr = h->fin_ctr + 2; t_d.fin_norm_w = (l + 1 < c.layers) ? h->L[l + 1].ln1 : h->final_norm; t_d.fin_xn = h->xn; t_d.fin_eps = c.rms_eps;
+      RD_CHECK(linear_fused(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, &t_o, st));
+      rd_epilogue eg{};
+      eg.act = RD_ACT_SWIGLU;
+      RD_CHECK(linear(h, C_GATEUP, h->xn, H, w.gate_up, H, h->mid, I, M, I, H, &eg, st));
+      RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, &t_d, st));
     } else {
       RD_CHECK(linear(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, st));
       { ProfScope ps(h, st, C_RMSNORM);
@@ -402,8 +428,12 @@ static int head_and_select(rd_llm* h, int B, int q_len, void* all_logits, cudaSt
                                       (size_t)H * 2, B, cudaMemcpyDeviceToDevice, st));
       xin = h->xl;
     }
-    { ProfScope ps(h, st, C_RMSNORM);
-      RD_CHECK(rd_rmsnorm(xin, h->final_norm, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
+    // decode with fused tails: the last layer's down_proj finisher already wrote xn = model.norm(x)
+    const bool normed = q_len == 1 && h->fuse_tail && !h->fuse_norm && B <= 32 && h->algo == 0 && H % 4 == 0 && h->tail_ran;
+    if (!normed) {
+      ProfScope ps(h, st, C_RMSNORM);
+      RD_CHECK(rd_rmsnorm(xin, h->final_norm, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st));
+    }
     RD_CHECK(linear(h, C_LMHEAD, h->xn, H, h->lm_head, H, h->logits, h->vpad, B, V, H, nullptr, st));
     logits = h->logits; ld = h->vpad;
   }
@@ -490,6 +520,7 @@ extern "C" int rd_llm_decode_step(rd_llm* h, void* stream) {
   const rd_llm_config& c = h->c;
   { ProfScope ps(h, st, C_EMBED);
     RD_CHECK(rd_embed_splice(h->cur_tok, h->embed, nullptr, h->x, h->B, 1, c.hidden, c.vocab, c.dtype, st)); }
+  h->tail_ran = false;
   if (mega_wanted(h, h->B) && h->mega != nullptr) RD_CHECK(run_layers_mega(h, h->B, h->pos_cur, st));
   else if (sk_wanted(h, h->B) && h->sk != nullptr) RD_CHECK(run_layers_sk(h, h->B, h->pos_cur, st));
   else RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
@@ -513,6 +544,14 @@ extern "C" int rd_llm_set_mega(rd_llm* h, int on) {
 extern "C" int rd_llm_set_fused_norm(rd_llm* h, int on) {
   RD_REQUIRE(h, "rd_llm_set_fused_norm: null handle");
   h->fuse_norm = on ? 1 : 0;
+  return RD_OK;
+}
+
+// 1 (default): single-token steps with B <= 32 run o_proj / down_proj as finisher split-K GEMMs with the residual add and the
+// following RMSNorm fused (5 launches per layer); 0: cluster split-K GEMMs + separate norm kernels (7 launches per layer).
+extern "C" int rd_llm_set_fused_tail(rd_llm* h, int on) {
+  RD_REQUIRE(h, "rd_llm_set_fused_tail: null handle");
+  h->fuse_tail = on ? 1 : 0;
   return RD_OK;
 }
 

@@ -259,9 +259,97 @@ struct TcParams {
   int norm_tiles;
   float norm_eps;
   float* ssq_out;              // EPI_RES1 (N % 128 == 0): sum_n out[m,n]^2 of this 128-row tile -> ssq_out[tile][m]
+  // "finisher" split-K (decode o_proj / down_proj, m_tiles == 1, EPI_RES1): every CTA stores its fp32 partial tile to the slab
+  // ws_part[split][NT][N] and takes a ticket; the LAST m_valid CTAs to arrive each finish one token row once all partials are
+  // in: out[m,:] = T(res + T(sum over splits, fixed order)) and, fused, the RMSNorm that follows in LlamaDecoderLayer.forward
+  // (modeling_llama_imgemb.py:85-93,287,305): fin_xn[m,:] = T(w * T(out * rsqrt(mean(out^2) + eps))).  No cluster, no DSMEM,
+  // no separate norm launch.
+  int fin;
+  uint32_t* fin_ctr;           // [2] arrival tickets, finished rows (re-armed by the last finisher)
+  const void* fin_norm_w;      // [N] norm weight, or nullptr = no norm (fin_xn unused)
+  void* fin_xn;                // [M, N]
+  float fin_eps;
   int wide_epi;                // NT >= 64: transposed epilogue through shared memory (coalesced residual loads / stores)
   EpiParams epi;
 };
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// One token row of the finisher split-K (see TcParams::fin), run by the 128 epilogue threads of a finisher CTA.
+// `srow` = N floats of (idle) pipeline smem, `sred` = 8 floats.  Rounding points: T(Wx) once, the fp16 residual add, then
+// LlamaRMSNorm's fp32 statistics over the ROUNDED row, T(x * rstd), T(w * .).
+template <class T>
+__device__ __noinline__ void finish_row(const TcParams& p, T* __restrict__ out, int m, int nt, float* srow, float* sred) {
+  const int e = threadIdx.x - 64, lane = e & 31, w4 = e >> 5;
+  const int N = p.N, splits = p.splits;
+  const float* slab = p.ws_part + (int64_t)m * N;
+  const int64_t slab_stride = (int64_t)nt * N;
+  const T* res = reinterpret_cast<const T*>(p.epi.residual) + (int64_t)m * p.epi.ld_res;
+  T* orow = out + (int64_t)m * p.ldo;
+  float ss = 0.f;
+  for (int c0 = e * 4; c0 < N; c0 += 2 * 512) {
+    // two column groups per round: 2 x splits independent 16-byte L2 loads in flight per thread
+    float4 acc[2];
+    uint2 rv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = c0 + u * 512;
+      acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < N) {
+        float4 v[8];
+        for (int s0 = 0; s0 < splits; s0 += 8) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            if (s0 + s < splits) v[s] = __ldcg(reinterpret_cast<const float4*>(slab + (int64_t)(s0 + s) * slab_stride + c));
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            if (s0 + s < splits) { acc[u].x += v[s].x; acc[u].y += v[s].y; acc[u].z += v[s].z; acc[u].w += v[s].w; }
+        }
+        rv[u] = *reinterpret_cast<const uint2*>(res + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = c0 + u * 512;
+      if (c < N) {
+        const T* rt = reinterpret_cast<const T*>(&rv[u]);
+        const float a[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
+        T y[4];
+        float yf[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          y[q] = Tr<T>::r(Tr<T>::f(rt[q]) + Tr<T>::rr(a[q]));           // residual + T(Wx), rounded (the new residual stream)
+          yf[q] = Tr<T>::f(y[q]);
+          ss = fmaf(yf[q], yf[q], ss);
+        }
+        *reinterpret_cast<uint2*>(orow + c) = *reinterpret_cast<const uint2*>(y);
+        *reinterpret_cast<float4*>(srow + c) = make_float4(yf[0], yf[1], yf[2], yf[3]);
+      }
+    }
+  }
+  if (p.fin_norm_w == nullptr) return;
+  ss = warp_sum(ss);
+  if (lane == 0) sred[w4] = ss;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const float tot = ((sred[0] + sred[1]) + sred[2]) + sred[3];
+  const float rs = 1.0f / sqrtf(tot / (float)N + p.fin_eps);            // torch.rsqrt(variance + eps), fp32
+  const T* nw = reinterpret_cast<const T*>(p.fin_norm_w);
+  T* xrow = reinterpret_cast<T*>(p.fin_xn) + (int64_t)m * N;
+  for (int c = e * 4; c < N; c += 512) {
+    const float4 yv = *reinterpret_cast<const float4*>(srow + c);
+    const uint2 wv = *reinterpret_cast<const uint2*>(nw + c);
+    const T* wt = reinterpret_cast<const T*>(&wv);
+    const float yf[4] = {yv.x, yv.y, yv.z, yv.w};
+    T o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = Tr<T>::r(Tr<T>::f(wt[q]) * Tr<T>::rr(yf[q] * rs));   // weight * T(x * rstd)
+    *reinterpret_cast<uint2*>(xrow + c) = *reinterpret_cast<const uint2*>(o);
+  }
+}
 
 template <class T, int NT, bool SWIGLU>
 __global__ void __launch_bounds__(TC_THREADS, (NT <= 64) ? 2 : 1)
@@ -472,7 +560,7 @@ _Pragma("unroll")
       // while the weight stream runs: pull the residual values this thread will add and the lora_t rows of the tile
       T* res_s = reinterpret_cast<T*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
       T* lt_s = res_s + NT * BLOCK_N;
-      if (p.epi_mode == EPI_RES1 && n < p.N && (p.splits == 1 || p.cluster)) {
+      if (p.epi_mode == EPI_RES1 && n < p.N && (p.splits == 1 || p.cluster) && !p.fin) {
         const int j0 = p.splits == 1 ? 0 : split, jstep = p.splits == 1 ? 1 : p.splits;
         for (int jb = j0; jb < m_valid; jb += 8 * jstep) {
           T tmp[8];
@@ -566,6 +654,46 @@ _Pragma("unroll")
               *reinterpret_cast<uint2*>(outb + (int64_t)(m0 + m) * p.ldo) = *reinterpret_cast<const uint2*>(y);
             }
           }
+        }
+      }
+    } else if (NT <= 32 && !SWIGLU && p.fin) {
+      // ---- finisher split-K: publish the fp32 partial tile (a warp stores 128 contiguous bytes per token), take a ticket ----
+      float* part = p.ws_part + (int64_t)split * NT * p.N;
+      for (int c = 0; c < m_valid; c += 16) {
+        uint32_t r[16];
+        tc_ld16(taddr + c, r);
+        tc_wait_ld();
+        if (n < p.N) {
+_Pragma("unroll")
+          for (int j = 0; j < 16; ++j)
+            if (c + j < m_valid) __stcg(part + (int64_t)(c + j) * p.N + n, __uint_as_float(r[j]));
+        }
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) { *flag_smem = atomicAdd(p.fin_ctr, 1u); trace_stamp(p.trace, 8); }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t total = gridDim.x * gridDim.z;
+      const uint32_t nfin = total < (uint32_t)m_valid ? total : (uint32_t)m_valid;      // finishers: the last nfin CTAs to arrive
+      const int first = (int)*flag_smem - (int)(total - nfin);
+      if (first >= 0) {
+        // all CTAs of the grid are co-resident (one wave), so the rest arrive without our help
+        if (threadIdx.x == 64) {
+          while (ld_acquire_u32(p.fin_ctr) < total) __nanosleep(32);
+          trace_stamp(p.trace, 9);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        __threadfence();
+        float* srow = reinterpret_cast<float*>(smem);                  // the pipeline smem is idle: all MMAs have completed
+        for (int row = first; row < m_valid; row += (int)nfin) {
+          finish_row<T>(p, out, m0 + row, NT, srow, s_norm);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (threadIdx.x == 64) {
+          trace_stamp(p.trace, 10);
+          __threadfence();
+          const uint32_t prev = atomicAdd(p.fin_ctr + 1, 1u);
+          if (prev == nfin - 1) { p.fin_ctr[1] = 0; p.fin_ctr[0] = 0; __threadfence(); }   // re-arm for the next launch
         }
       }
     } else if (p.splits == 1) {
@@ -868,8 +996,21 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
                  "rd_linear_tc_fused: sum-of-squares output needs the residual epilogue, N %% 128 == 0 and no workspace split-K");
       p.ssq_out = f.ssq_out;
     }
+    if (f.fin_ctr != nullptr) {
+      RD_REQUIRE(!SWIGLU && p.epi_mode == EPI_RES1 && N % 4 == 0 && ldo % 4 == 0 && epi.ld_res % 4 == 0 &&
+                 (int64_t)N * 4 <= (int64_t)Cfg::STAGES * Cfg::STAGE_BYTES,
+                 "rd_linear_tc_fused: the finisher split-K needs the residual epilogue, N %% 4 == 0 and a token row that fits the pipeline smem");
+      const int one_wave = resident_capacity<T, NT, SWIGLU>(1);
+      RD_REQUIRE(n_tiles * splits <= one_wave, "rd_linear_tc_fused: finisher split-K needs a single-wave grid");
+      const int64_t need = 256 + (int64_t)splits * NT * N * 4;
+      RD_REQUIRE(ws != nullptr && ws_bytes >= need, "rd_linear_tc_fused: workspace too small for the partial slabs (%lld < %lld)", (long long)ws_bytes, (long long)need);
+      p.fin = 1; p.fin_ctr = f.fin_ctr; p.fin_norm_w = f.fin_norm_w; p.fin_xn = f.fin_xn; p.fin_eps = f.fin_eps;
+      p.ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 256);
+      p.cluster = 0;
+    }
   }
-  if (splits > 1 && !use_cluster) {
+  const bool cluster_launch = use_cluster && !p.fin;
+  if (splits > 1 && !use_cluster && !p.fin) {
     const int64_t part_bytes = (int64_t)splits * n_tiles * m_tiles * Cfg::ACCS * NT * BLOCK_N * 4;
     const int64_t need = part_bytes + ((int64_t)n_tiles * m_tiles * 4 + 255) / 256 * 256;
     RD_REQUIRE(ws != nullptr && ws_bytes >= need, "rd_linear: split-K workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
@@ -885,7 +1026,7 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (use_cluster) {
+  if (cluster_launch) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = (unsigned)splits;
     ++na;

@@ -116,6 +116,7 @@ class LlamaForCausalLM:
         self.mega = False     # persistent all-layers decode kernel (experimental)
         self.fused_norm = False   # RMSNorm inside the decode GEMMs (experimental)
         self.streamk = False  # stream-K decode GEMMs with fused RMSNorm (experimental)
+        self.fused_tail = True    # o_proj / down_proj finisher split-K with the residual add + following RMSNorm fused (default)
         self.use_cuda_graph = True
         self.last_stats: Dict[str, float] = {}
 
@@ -299,6 +300,7 @@ class LlamaForCausalLM:
         _lib.check(self._lib.rd_llm_set_mega(h, 1 if self.mega else 0), "set_mega")
         _lib.check(self._lib.rd_llm_set_streamk(h, 1 if self.streamk else 0), "set_streamk")
         _lib.check(self._lib.rd_llm_set_fused_norm(h, 1 if self.fused_norm else 0), "set_fused_norm")
+        _lib.check(self._lib.rd_llm_set_fused_tail(h, 1 if self.fused_tail else 0), "set_fused_tail")
 
     def _bind_img_proj(self):
         lin = self.model.img_proj_layer
@@ -323,6 +325,14 @@ class LlamaForCausalLM:
         self._graphs = {}
         if self._h is not None:
             _lib.check(self._lib.rd_llm_set_fused_norm(self._h, 1 if on else 0), "set_fused_norm")
+
+    def set_fused_tail(self, on: bool):
+        """Single-token steps: o_proj / down_proj as finisher split-K GEMMs with the residual add and the following RMSNorm
+        fused (default, 5 launches per layer), or cluster split-K GEMMs + separate norm kernels (7 launches per layer)."""
+        self.fused_tail = bool(on)
+        self._graphs = {}
+        if self._h is not None:
+            _lib.check(self._lib.rd_llm_set_fused_tail(self._h, 1 if on else 0), "set_fused_tail")
 
     def set_streamk(self, on: bool):
         """Decode GEMMs as stream-K kernels with fused RMSNorm, or (default) tile x split-K kernels + norm kernels."""
