@@ -121,6 +121,13 @@ int rd_attention_decode(const void* qkv_dev, int64_t ldq, const int32_t* pos_dev
                         void* out_dev, int B, int nh, int hd, int cmax, int ctx_lower_bound, const void* lora_b_dev,
                         int lora_r, float lora_scale, int dtype, void* stream);
 
+/* rd_attention_decode with q/k/v (+ the LoRA t columns) handed over as the QKV GEMM's fp32 split-K partials
+ * qkv_part_dev[n_part][part_stride] (row b at b*ldq): summed in split order and rounded once, T(Wx), as they are read. */
+int rd_attention_decode_partials(const float* qkv_part_dev, int n_part, long long part_stride, int64_t ldq, const int32_t* pos_dev,
+                                 const void* cos_dev, const void* sin_dev, void* kcache_dev, void* vcache_dev,
+                                 const uint8_t* keymask_dev, const int32_t* ctx_len_dev, void* out_dev, int B, int nh, int hd, int cmax,
+                                 int ctx_lower_bound, const void* lora_b_dev, int lora_r, float lora_scale, int dtype, void* stream);
+
 /* LlamaModel.forward splice (modeling_llama_imgemb.py:571-594, split_at_img :498-520): out[b,t,:] = img[b,t-p,:]
  * for t in [p,p+32) where p = first index of 32000 in row b (0 if none), else embed[ids[b,t]].  img may be NULL
  * (plain embedding).                                                                                            */
@@ -180,11 +187,11 @@ int rd_llm_set_streamk(rd_llm* h, int on);
  * QKV / gate|up GEMMs (row statistics from sum-of-squares partials written by the o_proj / down_proj epilogues) instead of
  * by separate kernels.  on = 1 / 0 (default).  Bit-identical results (tests/test_gpu_llm.py).                    */
 int rd_llm_set_fused_norm(rd_llm* h, int on);
-/* Single-token steps with B <= 32 (default ON): o_proj and down_proj run a "finisher" split-K - every CTA stores its fp32
- * partial tile to an L2-resident slab, the last CTAs to arrive each finish whole token rows: out = T(res + T(Wx)) and, fused,
- * the LlamaRMSNorm that follows in LlamaDecoderLayer.forward (modeling_llama_imgemb.py:287,305; model.norm :658 after the last
- * layer).  A layer is then 5 launches instead of 7.  Same rounding contract; 0 = cluster split-K + separate norm kernels. */
-int rd_llm_set_fused_tail(rd_llm* h, int on);
+/* Single-token steps with B <= 32 (default ON): the QKV GEMM (q_proj|k_proj|v_proj (+lora_A), modeling_llama_imgemb.py:178-181)
+ * leaves its fp32 split-K partials in an L2-resident slab and the attention kernel sums them in split order and applies the
+ * single rounding T(Wx) while reading q/k/v - the GEMM has no cross-CTA reduction tail.  0 = the GEMM reduces them itself
+ * (thread-block cluster + distributed shared memory).  Same rounding contract and the same summation order either way.  */
+int rd_llm_set_qkv_partials(rd_llm* h, int on);
 /* Decode step: bytes of W_qkv / W_o / W_gate|up that the (latency-bound, HBM-idle) norm and attention kernels pull into
  * the 126 MB L2 with cp.async.bulk.prefetch ahead of the GEMM that streams them; 0,0,0 turns it off. */
 int rd_llm_set_l2_prefetch(rd_llm* h, long long qkv_bytes, long long o_bytes, long long gate_up_bytes);

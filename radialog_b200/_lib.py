@@ -60,6 +60,7 @@ SIGNATURES = {
     "rd_rope_kv_store": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _i, _p]),
     "rd_attention": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "rd_attention_decode": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _i, _p]),
+    "rd_attention_decode_partials": (_i, [_p, _i, C.c_longlong, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _i, _p]),
     "rd_embed_splice": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "rd_llm_create": (_i, [C.POINTER(LlmConfig), C.POINTER(_p)]),
     "rd_llm_destroy": (None, [_p]),
@@ -68,7 +69,7 @@ SIGNATURES = {
     "rd_llm_set_mega": (_i, [_p, _i]),
     "rd_llm_set_streamk": (_i, [_p, _i]),
     "rd_llm_set_fused_norm": (_i, [_p, _i]),
-    "rd_llm_set_fused_tail": (_i, [_p, _i]),
+    "rd_llm_set_qkv_partials": (_i, [_p, _i]),
     "rd_llm_set_l2_prefetch": (_i, [_p, C.c_longlong, C.c_longlong, C.c_longlong]),
     "rd_llm_prefill": (_i, [_p, _p, _p, _i, _i, _p, _i, _p]),
     "rd_llm_truncate": (_i, [_p, _i, _p, _p]),

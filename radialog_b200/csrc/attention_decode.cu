@@ -52,7 +52,8 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
                         const uint8_t* __restrict__ keymask, const int32_t* __restrict__ ctx_len_p, T* __restrict__ out, int nh,
                         int cmax, const int32_t* __restrict__ pos, const T* __restrict__ cos_t, const T* __restrict__ sin_t,
                         int prefetch_keys, const T* __restrict__ lora_b, int lora_r, float lora_scale,
-                        const void* pf0, long long pf0_bytes, const void* pf1, long long pf1_bytes) {
+                        const void* pf0, long long pf0_bytes, const void* pf1, long long pf1_bytes,
+                        const float* __restrict__ qkv_part, int n_part, long long part_stride) {
   constexpr int GROUPS = THREADS / 16;
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -118,16 +119,32 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
     const int H = nh * HD;
     const T* row = qkv + (int64_t)b * ldq;
     const int64_t slot_off = (((int64_t)b * nh + h) * cmax + ctx) * HD;
+    // q/k/v (and the LoRA t columns) of this row: either the QKV GEMM's rounded output, or - split-K GEMM without a reduction
+    // pass - its fp32 partial slabs [n_part][rows][ldq], summed here in split order and rounded once: T(Wx) either way
+    const float* prow = qkv_part != nullptr ? qkv_part + (int64_t)b * ldq : nullptr;
+    auto ldv = [&](int col) -> float {
+      if (prow == nullptr) return Tr<T>::f(row[col]);
+      float a = 0.f;
+      for (int s = 0; s < n_part; ++s) a += __ldcg(prow + (int64_t)s * part_stride + col);
+      return Tr<T>::rr(a);
+    };
     // peft LoRA (unmerged): the GEMM wrote t = T(lora_A . xn) after the 3H projection columns (q's r values, then v's)
-    auto lora = [&](float y, int n_row, const T* t) {
+    auto lora = [&](float y, int n_row, int tcol) {
       const T* brow = lora_b + (int64_t)n_row * lora_r;
       float sdot = 0.f;
-      if (lora_r == 8) {        // the reference's adapter rank (finetune.py:167): two 128-bit loads instead of 16 scalar ones
-        const Vec8<T> bv = ld16(brow), tv = ld16(t);
+      if (lora_r == 8 && prow == nullptr) {   // the reference's adapter rank (finetune.py:167): two 128-bit loads instead of 16 scalar ones
+        const Vec8<T> bv = ld16(brow), tv = ld16(row + tcol);
 #pragma unroll
         for (int i = 0; i < 8; ++i) sdot = fmaf(Tr<T>::f(bv.v[i]), Tr<T>::f(tv.v[i]), sdot);
+      } else if (lora_r == 8) {
+        const Vec8<T> bv = ld16(brow);
+        float tv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tv[i] = ldv(tcol + i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sdot = fmaf(Tr<T>::f(bv.v[i]), tv[i], sdot);
       } else {
-        for (int i = 0; i < lora_r; ++i) sdot = fmaf(Tr<T>::f(brow[i]), Tr<T>::f(t[i]), sdot);
+        for (int i = 0; i < lora_r; ++i) sdot = fmaf(Tr<T>::f(brow[i]), ldv(tcol + i), sdot);
       }
       return Tr<T>::rr(y + Tr<T>::rr(lora_scale * Tr<T>::rr(sdot)));
     };
@@ -135,21 +152,21 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
       const int d = tid, p = pos[b];
       const float c_lo = Tr<T>::f(cos_t[(int64_t)p * HD + d]), c_hi = Tr<T>::f(cos_t[(int64_t)p * HD + d + half]);
       const float s_lo = Tr<T>::f(sin_t[(int64_t)p * HD + d]), s_hi = Tr<T>::f(sin_t[(int64_t)p * HD + d + half]);
-      float lo = Tr<T>::f(row[h * HD + d]), hi = Tr<T>::f(row[h * HD + d + half]);
-      if (lora_r > 0) { lo = lora(lo, h * HD + d, row + 3 * H); hi = lora(hi, h * HD + d + half, row + 3 * H); }
+      float lo = ldv(h * HD + d), hi = ldv(h * HD + d + half);
+      float klo = ldv(H + h * HD + d), khi = ldv(H + h * HD + d + half);
+      if (lora_r > 0) { lo = lora(lo, h * HD + d, 3 * H); hi = lora(hi, h * HD + d + half, 3 * H); }
       s_q[d] = Tr<T>::rr(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
       s_q[d + half] = Tr<T>::rr(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
-      lo = Tr<T>::f(row[H + h * HD + d]); hi = Tr<T>::f(row[H + h * HD + d + half]);
-      const float k_lo = Tr<T>::rr(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
-      const float k_hi = Tr<T>::rr(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
+      const float k_lo = Tr<T>::rr(Tr<T>::rr(klo * c_lo) + Tr<T>::rr(-khi * s_lo));
+      const float k_hi = Tr<T>::rr(Tr<T>::rr(khi * c_hi) + Tr<T>::rr(klo * s_hi));
       s_k[d] = k_lo; s_k[d + half] = k_hi;
       kc[slot_off + d] = Tr<T>::r(k_lo); kc[slot_off + d + half] = Tr<T>::r(k_hi);
     } else if (tid < 2 * half) {
       const int d = tid - half;
-      float v_lo = Tr<T>::f(row[2 * H + h * HD + d]), v_hi = Tr<T>::f(row[2 * H + h * HD + d + half]);
+      float v_lo = ldv(2 * H + h * HD + d), v_hi = ldv(2 * H + h * HD + d + half);
       if (lora_r > 0) {
-        v_lo = lora(v_lo, H + h * HD + d, row + 3 * H + lora_r);
-        v_hi = lora(v_hi, H + h * HD + d + half, row + 3 * H + lora_r);
+        v_lo = lora(v_lo, H + h * HD + d, 3 * H + lora_r);
+        v_hi = lora(v_hi, H + h * HD + d + half, 3 * H + lora_r);
       }
       s_v[d] = v_lo; s_v[d + half] = v_hi;
       vc[slot_off + d] = Tr<T>::r(v_lo); vc[slot_off + d + half] = Tr<T>::r(v_hi);
@@ -295,12 +312,13 @@ extern "C" int rd_attention_decode_set_prefetch(int on) { g_attn_prefetch = on; 
 
 // Single-token decode: RoPE + KV append + attention in one launch (rd_rope_kv_store + rd_attention with q_len == 1).
 // ctx_lower_bound: a host-known lower bound of ctx_len[0] (0 if unknown); only used to size the early prefetch.
-extern "C" int rd_attention_decode(const void* qkv, int64_t ldq, const int32_t* pos, const void* cos_t, const void* sin_t,
-                                   void* kc, void* vc, const uint8_t* keymask, const int32_t* ctx_len, void* out, int B, int nh,
-                                   int hd, int cmax, int ctx_lower_bound, const void* lora_b, int lora_r, float lora_scale,
-                                   int dtype, void* stream) {
+static int attention_decode_impl(const void* qkv, int64_t ldq, const int32_t* pos, const void* cos_t, const void* sin_t,
+                                 void* kc, void* vc, const uint8_t* keymask, const int32_t* ctx_len, void* out, int B, int nh,
+                                 int hd, int cmax, int ctx_lower_bound, const void* lora_b, int lora_r, float lora_scale,
+                                 const float* qkv_part, int n_part, long long part_stride, int dtype, void* stream) {
   RD_REQUIRE(hd == 128, "rd_attention_decode: head_dim must be 128 (Vicuna-7B); got %d", hd);
   RD_REQUIRE(B > 0 && nh > 0 && cmax > 0, "rd_attention_decode: bad shape");
+  RD_REQUIRE(qkv_part == nullptr || (n_part >= 1 && n_part <= 16), "rd_attention_decode: bad partial count %d", n_part);
   const bool wide = (int64_t)B * nh <= 296;          // few (sequence, head) pairs: more threads per pair
   const int ring = wide ? 4 : 3;                     // 128-thread CTAs: 7 resident per SM so that B=32 x 32 heads is one wave
   const size_t smem = (size_t)ring * CHUNK_BYTES + ((size_t)(cmax + 1) * 4 + 127) / 128 * 128;
@@ -311,14 +329,34 @@ extern "C" int rd_attention_decode(const void* qkv, int64_t ldq, const int32_t* 
       RD_SMEM_ATTR_ONCE(200 * 1024, attention_decode_kernel<T, 512, 4>);
       RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 512, 4>, dim3(nh, B), dim3(512), smem, (cudaStream_t)stream, rd_pdl_enabled(),
                               (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
-                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes));
+                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes, qkv_part, n_part, part_stride));
     } else {
       RD_SMEM_ATTR_ONCE(200 * 1024, attention_decode_kernel<T, 128, 3>);
       RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 128, 3>, dim3(nh, B), dim3(128), smem, (cudaStream_t)stream, rd_pdl_enabled(),
                               (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
-                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes));
+                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes, qkv_part, n_part, part_stride));
     }
     g_pf0 = nullptr; g_pf1 = nullptr; g_pf0_bytes = 0; g_pf1_bytes = 0;
     return RD_OK;
   });
+}
+
+extern "C" int rd_attention_decode(const void* qkv, int64_t ldq, const int32_t* pos, const void* cos_t, const void* sin_t,
+                                   void* kc, void* vc, const uint8_t* keymask, const int32_t* ctx_len, void* out, int B, int nh,
+                                   int hd, int cmax, int ctx_lower_bound, const void* lora_b, int lora_r, float lora_scale,
+                                   int dtype, void* stream) {
+  RD_REQUIRE(qkv != nullptr, "rd_attention_decode: null qkv");
+  return attention_decode_impl(qkv, ldq, pos, cos_t, sin_t, kc, vc, keymask, ctx_len, out, B, nh, hd, cmax, ctx_lower_bound, lora_b,
+                               lora_r, lora_scale, nullptr, 0, 0, dtype, stream);
+}
+
+// Same, with q/k/v (+ LoRA t columns) handed over as the QKV GEMM's fp32 split-K partials [n_part][part_stride] (row b at
+// b * ldq): the sum over the splits (fixed order) and the single rounding T(Wx) happen here instead of in a reduction pass.
+extern "C" int rd_attention_decode_partials(const float* qkv_part, int n_part, long long part_stride, int64_t ldq, const int32_t* pos,
+                                            const void* cos_t, const void* sin_t, void* kc, void* vc, const uint8_t* keymask,
+                                            const int32_t* ctx_len, void* out, int B, int nh, int hd, int cmax, int ctx_lower_bound,
+                                            const void* lora_b, int lora_r, float lora_scale, int dtype, void* stream) {
+  RD_REQUIRE(qkv_part != nullptr, "rd_attention_decode_partials: null partials");
+  return attention_decode_impl(nullptr, ldq, pos, cos_t, sin_t, kc, vc, keymask, ctx_len, out, B, nh, hd, cmax, ctx_lower_bound, lora_b,
+                               lora_r, lora_scale, qkv_part, n_part, part_stride, dtype, stream);
 }

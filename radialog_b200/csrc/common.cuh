@@ -240,12 +240,17 @@ struct TcFuse {
   int norm_tiles;
   float norm_eps;
   float* ssq_out;
-  // finisher split-K (see TcParams::fin in linear_tc.cu): fp32 partial slabs + the last CTAs finish whole token rows, with the
-  // following RMSNorm fused: out = T(res + T(Wx)), fin_xn = T(fin_norm_w * T(out * rstd)).  fin_ctr: 2 zero-initialised words.
-  uint32_t* fin_ctr = nullptr;
-  const void* fin_norm_w = nullptr;
-  void* fin_xn = nullptr;
-  float fin_eps = 0.f;
+  // partials-out split-K (see TcParams::part_out in linear_tc.cu): the GEMM leaves its fp32 split-K partials in
+  // part_out[splits][NT][N] for the consumer to sum; splits_out[0..1] receives the split count and the slab's row count NT.
+  float* part_out = nullptr;
+  int64_t part_bytes = 0;
+  int* splits_out = nullptr;
+  // L2 prefetch of the head of the NEXT decode GEMM's weights (see TcParams::pf_p): next_w [next_N (x2 if SwiGLU), next_K],
+  // about next_bytes of it, issued by this GEMM's producer warps once their own loads are in flight.
+  const void* next_w = nullptr;
+  int64_t next_ldw = 0;
+  int next_N = 0, next_K = 0, next_swiglu = 0;
+  int64_t next_bytes = 0;
 };
 int rd_linear_tc_fused(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
                        const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, const TcFuse* fuse, cudaStream_t st);

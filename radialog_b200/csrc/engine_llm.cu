@@ -10,6 +10,8 @@
 
 extern "C" int rd_attention_decode(const void*, int64_t, const int32_t*, const void*, const void*, void*, void*, const uint8_t*,
                                    const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
+extern "C" int rd_attention_decode_partials(const float*, int, long long, int64_t, const int32_t*, const void*, const void*, void*, void*,
+                                            const uint8_t*, const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
 extern "C" int rd_rmsnorm_prefetch(const void*, const void*, void*, int, int, float, const void*, long long, int, void*);
 extern "C" int rd_attention_decode_set_l2_prefetch(const void*, long long, const void*, long long);
 extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const int32_t*, int, int, int, int, void*);
@@ -46,12 +48,11 @@ struct rd_llm {
   // Off by default: bit-identical results, but normalising the token tile inside a 3-5 stage W+X pipeline lengthens every
   // stage (measured B=32: 4.23 vs 3.77 ms per step; B=1: 3.01 vs 2.92 ms).
   int fuse_norm = 0;
-  // single-token steps with B <= 32 (default ON): o_proj / down_proj run the "finisher" split-K of linear_tc.cu - fp32 partial
-  // slabs, the last CTAs to arrive finish whole token rows (residual add) AND apply the RMSNorm that follows, so a layer is
-  // 5 launches (qkv, attention, o+norm2, gate|up, down+norm1') instead of 7 and no GEMM of the pair waits on a cluster reduction.
-  int fuse_tail = 1;
-  bool tail_ran = false;         // the layer loop of the current step took the fused-tail path (set by run_layers)
-  uint32_t* fin_ctr = nullptr;   // [o_proj pair, down_proj pair] ticket / done counters (zero-initialised, self re-arming)
+  // single-token steps with B <= 32 (default ON): the QKV GEMM leaves its fp32 split-K partials in `qkv_part` and the attention
+  // kernel sums them (fixed order, one rounding) when it reads q/k/v - no cross-CTA reduction pass in the GEMM's tail.
+  int qkv_partials = 1;
+  float* qkv_part = nullptr;
+  int64_t qkv_part_bytes = 0;
   // L2 weight prefetch from the norm / attention kernels: mechanism kept, OFF by default (A/B runs on B200 showed no
   // gain at B=32 beyond run-to-run noise and a loss at B=1, where the norm kernel is a single CTA)
   bool l2_prefetch = false;
@@ -116,7 +117,8 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
   A((char**)&h->ctx_len, 16); A((char**)&h->n_gen, 16); A((char**)&h->done_ctr, 16);
   A((char**)&h->cur_tok, Bm * 8); A((char**)&h->gen, Bm * C * 8);
   A((char**)&h->ssq, (H / 128 + 1) * 32 * 4);
-  A((char**)&h->fin_ctr, 64);
+  h->qkv_part_bytes = (int64_t)16 * 32 * (3 * H + 64) * 4;          // <= 16 splits x 32 tokens x (3H + 2r) fp32
+  A((char**)&h->qkv_part, h->qkv_part_bytes);
   int64_t ws = 0;
   const int Ms[2] = {(int)Bm, 256};
   for (int mi = 0; mi < 2; ++mi) {
@@ -126,8 +128,6 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
                        rd_linear_tc_workspace_bytes(M, cfg->vocab, H)};
     for (int i = 0; i < 5; ++i) ws = cand[i] > ws ? cand[i] : ws;
   }
-  const int64_t slab = 256 + (int64_t)16 * 32 * H * 4 + 256;      // finisher split-K: <= 16 splits x 32 tokens x H fp32 partials
-  if (slab > ws) ws = slab;
   h->ws_bytes = ws;
   A(&h->ws, ws);
   if (r != RD_OK) { rd_llm_destroy(h); return r; }
@@ -144,7 +144,7 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
   rd_mega_destroy(h->mega);
   rd_sk_destroy(h->sk);
   if (h->ssq) cudaFree(h->ssq);
-  if (h->fin_ctr) cudaFree(h->fin_ctr);
+  if (h->qkv_part) cudaFree(h->qkv_part);
   delete h;
 }
 
@@ -339,7 +339,6 @@ static int linear_fused(rd_llm* h, int cls, const void* x, int64_t ldx, const vo
 static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStream_t st) {
   const rd_llm_config& c = h->c;
   const int H = c.hidden, I = c.inter, M = B * q_len, nh = c.heads, hd = H / nh, dt = c.dtype;
-  h->tail_ran = h->fuse_tail && !h->fuse_norm && q_len == 1 && M <= 32 && h->algo == 0 && H % 4 == 0;
   for (int l = 0; l < c.layers; ++l) {
     const LayerW& w = h->L[l];
     char* kc = h->kc + (int64_t)l * h->kv_layer_bytes;
@@ -354,23 +353,34 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     const bool fuse = h->fuse_norm && q_len == 1 && M <= 32 && h->algo == 0 && H % 128 == 0;
     TcFuse f_in1{h->ssq, w.ln1, H / 128, c.rms_eps, nullptr}, f_in2{h->ssq, w.ln2, H / 128, c.rms_eps, nullptr};
     TcFuse f_out{nullptr, nullptr, 0, 0.f, h->ssq};
-    // fused tails (decode, B <= 32): the previous layer's down_proj already wrote xn = RMSNorm_ln1(x) of this layer
-    const bool tail = h->fuse_tail && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && H % 4 == 0;
+    // decode, B <= 32: QKV split-K partials go straight to the attention kernel (no reduction pass in the GEMM)
+    const bool qpart = h->qkv_partials && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && (3 * H + R2) % 4 == 0;
+    int qsplit[2] = {0, 0};
     if (fuse && l > 0) {
       RD_CHECK(linear_fused(h, C_QKV, h->x, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &f_in1, st));
     } else {
-      if (!(tail && l > 0)) {
-        ProfScope ps(h, st, C_RMSNORM);
+      { ProfScope ps(h, st, C_RMSNORM);
         // decode: the norm kernels are latency bound and leave HBM idle -> they pull the next GEMM's weights into L2
-        RD_CHECK(rd_rmsnorm_prefetch(h->x, w.ln1, h->xn, M, H, c.rms_eps, decode ? w.qkv : nullptr, decode ? std::min(qkv_bytes, h->pf_qkv) : 0, dt, st));
+        RD_CHECK(rd_rmsnorm_prefetch(h->x, w.ln1, h->xn, M, H, c.rms_eps, decode ? w.qkv : nullptr, decode ? std::min(qkv_bytes, h->pf_qkv) : 0, dt, st)); }
+      if (qpart) {
+        TcFuse tq{};
+        tq.part_out = h->qkv_part; tq.part_bytes = h->qkv_part_bytes; tq.splits_out = qsplit;
+        RD_CHECK(linear_fused(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &tq, st));
+      } else {
+        RD_CHECK(linear(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, st));
       }
-      RD_CHECK(linear(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, st));
     }
     if (q_len == 1) {      // decode: RoPE + KV append + attention fused in one launch
       ProfScope ps(h, st, C_ATTN);
       if (decode) rd_attention_decode_set_l2_prefetch(w.o, std::min(o_bytes, h->pf_o), w.gate_up, std::min(gu_bytes, h->pf_gu));
-      RD_CHECK(rd_attention_decode(h->qkv, ldq, pos, h->cos, h->sin, kc, vc, h->keymask, h->ctx_len, h->att, B, nh, hd, c.max_ctx,
-                                   h->ctx_host, c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st));
+      if (qpart && qsplit[0] > 0) {
+        RD_CHECK(rd_attention_decode_partials(h->qkv_part, qsplit[0], (long long)qsplit[1] * ldq, ldq, pos, h->cos, h->sin, kc, vc, h->keymask,
+                                              h->ctx_len, h->att, B, nh, hd, c.max_ctx, h->ctx_host, c.lora_r ? w.lora_b : nullptr, c.lora_r,
+                                              c.lora_scale, dt, st));
+      } else {
+        RD_CHECK(rd_attention_decode(h->qkv, ldq, pos, h->cos, h->sin, kc, vc, h->keymask, h->ctx_len, h->att, B, nh, hd, c.max_ctx,
+                                     h->ctx_host, c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st));
+      }
     } else {
       { ProfScope ps(h, st, C_ROPE);
         RD_CHECK(rd_rope_kv_store(h->qkv, ldq, pos, h->ctx_len, h->cos, h->sin, kc, vc, B, q_len, nh, hd, c.max_ctx,
@@ -386,17 +396,6 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
       eg.act = RD_ACT_SWIGLU;
       RD_CHECK(linear_fused(h, C_GATEUP, h->x, H, w.gate_up, H, h->mid, I, M, I, H, &eg, &f_in2, st));
       RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, &f_out, st));
-    } else if (tail) {
-      // o_proj + residual + post_attention_layernorm, then gate|up, then down_proj + residual + the NEXT norm on the path
-      // (input_layernorm of layer l+1, or model.norm after the last layer: modeling_llama_imgemb.py:287,305,658)
-      TcFuse t_o{}, t_d{};
-      t_o.fin_ctr = h->fin_ctr; t_o.fin_norm_w = w.ln2; t_o.fin_xn = h->xn; t_o.fin_eps = c.rms_eps;
-      t_d.fin_ctr = h->fin_ctr + 2; t_d.fin_norm_w = (l + 1 < c.layers) ? h->L[l + 1].ln1 : h->final_norm; t_d.fin_xn = h->xn; t_d.fin_eps = c.rms_eps;
-      RD_CHECK(linear_fused(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, &t_o, st));
-      rd_epilogue eg{};
-      eg.act = RD_ACT_SWIGLU;
-      RD_CHECK(linear(h, C_GATEUP, h->xn, H, w.gate_up, H, h->mid, I, M, I, H, &eg, st));
-      RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, &t_d, st));
     } else {
       RD_CHECK(linear(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, st));
       { ProfScope ps(h, st, C_RMSNORM);
@@ -428,12 +427,8 @@ static int head_and_select(rd_llm* h, int B, int q_len, void* all_logits, cudaSt
                                       (size_t)H * 2, B, cudaMemcpyDeviceToDevice, st));
       xin = h->xl;
     }
-    // decode with fused tails: the last layer's down_proj finisher already wrote xn = model.norm(x)
-    const bool normed = q_len == 1 && h->fuse_tail && !h->fuse_norm && B <= 32 && h->algo == 0 && H % 4 == 0 && h->tail_ran;
-    if (!normed) {
-      ProfScope ps(h, st, C_RMSNORM);
-      RD_CHECK(rd_rmsnorm(xin, h->final_norm, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st));
-    }
+    { ProfScope ps(h, st, C_RMSNORM);
+      RD_CHECK(rd_rmsnorm(xin, h->final_norm, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
     RD_CHECK(linear(h, C_LMHEAD, h->xn, H, h->lm_head, H, h->logits, h->vpad, B, V, H, nullptr, st));
     logits = h->logits; ld = h->vpad;
   }
@@ -520,7 +515,6 @@ extern "C" int rd_llm_decode_step(rd_llm* h, void* stream) {
   const rd_llm_config& c = h->c;
   { ProfScope ps(h, st, C_EMBED);
     RD_CHECK(rd_embed_splice(h->cur_tok, h->embed, nullptr, h->x, h->B, 1, c.hidden, c.vocab, c.dtype, st)); }
-  h->tail_ran = false;
   if (mega_wanted(h, h->B) && h->mega != nullptr) RD_CHECK(run_layers_mega(h, h->B, h->pos_cur, st));
   else if (sk_wanted(h, h->B) && h->sk != nullptr) RD_CHECK(run_layers_sk(h, h->B, h->pos_cur, st));
   else RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
@@ -547,11 +541,11 @@ extern "C" int rd_llm_set_fused_norm(rd_llm* h, int on) {
   return RD_OK;
 }
 
-// 1 (default): single-token steps with B <= 32 run o_proj / down_proj as finisher split-K GEMMs with the residual add and the
-// following RMSNorm fused (5 launches per layer); 0: cluster split-K GEMMs + separate norm kernels (7 launches per layer).
-extern "C" int rd_llm_set_fused_tail(rd_llm* h, int on) {
-  RD_REQUIRE(h, "rd_llm_set_fused_tail: null handle");
-  h->fuse_tail = on ? 1 : 0;
+// 1 (default): in single-token steps with B <= 32 the QKV GEMM hands its fp32 split-K partials to the attention kernel, which
+// sums them in split order and rounds once (T(Wx)) as it reads q/k/v; 0: the GEMM reduces them itself (cluster + DSMEM).
+extern "C" int rd_llm_set_qkv_partials(rd_llm* h, int on) {
+  RD_REQUIRE(h, "rd_llm_set_qkv_partials: null handle");
+  h->qkv_partials = on ? 1 : 0;
   return RD_OK;
 }
 

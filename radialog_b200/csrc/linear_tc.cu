@@ -259,102 +259,23 @@ struct TcParams {
   int norm_tiles;
   float norm_eps;
   float* ssq_out;              // EPI_RES1 (N % 128 == 0): sum_n out[m,n]^2 of this 128-row tile -> ssq_out[tile][m]
-  // "finisher" split-K (decode o_proj / down_proj, m_tiles == 1, EPI_RES1): every CTA stores its fp32 partial tile to the slab
-  // ws_part[split][NT][N] and takes a ticket; the LAST m_valid CTAs to arrive each finish one token row once all partials are
-  // in: out[m,:] = T(res + T(sum over splits, fixed order)) and, fused, the RMSNorm that follows in LlamaDecoderLayer.forward
-  // (modeling_llama_imgemb.py:85-93,287,305): fin_xn[m,:] = T(w * T(out * rsqrt(mean(out^2) + eps))).  No cluster, no DSMEM,
-  // no separate norm launch.
-  int fin;
-  uint32_t* fin_ctr;           // [2] arrival tickets, finished rows (re-armed by the last finisher)
-  const void* fin_norm_w;      // [N] norm weight, or nullptr = no norm (fin_xn unused)
-  void* fin_xn;                // [M, N]
-  float fin_eps;
+  // "partials out" split-K (decode QKV GEMM, m_tiles == 1, plain epilogue): every CTA stores its fp32 partial tile to the slab
+  // part_out[split][NT][N] and is done - no cluster, no DSMEM, no reduction pass.  The consumer (attention_decode_kernel) sums
+  // the splits in fixed order and applies the single rounding T(Wx) when it reads q/k/v.
+  float* part_out;
+  // Weight prefetch for the NEXT GEMM of the decode step (m_tiles == 1): once this CTA's own loads are all issued, its producer
+  // warp requests (cp.async.bulk.prefetch.tensor -> L2) boxes of the next GEMM's weight stream: the first pf_p k-blocks of each
+  // of its (tile, split) CTAs, dealt round-robin over this grid.  HBM then keeps streaming through this kernel's reduction tail
+  // and the launch boundary instead of idling, and the next kernel's first loads hit L2.
+  int pf_p, pf_tiles, pf_splits, pf_halves, pf_kb_total, pf_n;
   int wide_epi;                // NT >= 64: transposed epilogue through shared memory (coalesced residual loads / stores)
   EpiParams epi;
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// One token row of the finisher split-K (see TcParams::fin), run by the 128 epilogue threads of a finisher CTA.
-// `srow` = N floats of (idle) pipeline smem, `sred` = 8 floats.  Rounding points: T(Wx) once, the fp16 residual add, then
-// LlamaRMSNorm's fp32 statistics over the ROUNDED row, T(x * rstd), T(w * .).
-template <class T>
-__device__ __noinline__ void finish_row(const TcParams& p, T* __restrict__ out, int m, int nt, float* srow, float* sred) {
-  const int e = threadIdx.x - 64, lane = e & 31, w4 = e >> 5;
-  const int N = p.N, splits = p.splits;
-  const float* slab = p.ws_part + (int64_t)m * N;
-  const int64_t slab_stride = (int64_t)nt * N;
-  const T* res = reinterpret_cast<const T*>(p.epi.residual) + (int64_t)m * p.epi.ld_res;
-  T* orow = out + (int64_t)m * p.ldo;
-  float ss = 0.f;
-  for (int c0 = e * 4; c0 < N; c0 += 2 * 512) {
-    // two column groups per round: 2 x splits independent 16-byte L2 loads in flight per thread
-    float4 acc[2];
-    uint2 rv[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = c0 + u * 512;
-      acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < N) {
-        float4 v[8];
-        for (int s0 = 0; s0 < splits; s0 += 8) {
-#pragma unroll
-          for (int s = 0; s < 8; ++s)
-            if (s0 + s < splits) v[s] = __ldcg(reinterpret_cast<const float4*>(slab + (int64_t)(s0 + s) * slab_stride + c));
-#pragma unroll
-          for (int s = 0; s < 8; ++s)
-            if (s0 + s < splits) { acc[u].x += v[s].x; acc[u].y += v[s].y; acc[u].z += v[s].z; acc[u].w += v[s].w; }
-        }
-        rv[u] = *reinterpret_cast<const uint2*>(res + c);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = c0 + u * 512;
-      if (c < N) {
-        const T* rt = reinterpret_cast<const T*>(&rv[u]);
-        const float a[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
-        T y[4];
-        float yf[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          y[q] = Tr<T>::r(Tr<T>::f(rt[q]) + Tr<T>::rr(a[q]));           // residual + T(Wx), rounded (the new residual stream)
-          yf[q] = Tr<T>::f(y[q]);
-          ss = fmaf(yf[q], yf[q], ss);
-        }
-        *reinterpret_cast<uint2*>(orow + c) = *reinterpret_cast<const uint2*>(y);
-        *reinterpret_cast<float4*>(srow + c) = make_float4(yf[0], yf[1], yf[2], yf[3]);
-      }
-    }
-  }
-  if (p.fin_norm_w == nullptr) return;
-  ss = warp_sum(ss);
-  if (lane == 0) sred[w4] = ss;
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  const float tot = ((sred[0] + sred[1]) + sred[2]) + sred[3];
-  const float rs = 1.0f / sqrtf(tot / (float)N + p.fin_eps);            // torch.rsqrt(variance + eps), fp32
-  const T* nw = reinterpret_cast<const T*>(p.fin_norm_w);
-  T* xrow = reinterpret_cast<T*>(p.fin_xn) + (int64_t)m * N;
-  for (int c = e * 4; c < N; c += 512) {
-    const float4 yv = *reinterpret_cast<const float4*>(srow + c);
-    const uint2 wv = *reinterpret_cast<const uint2*>(nw + c);
-    const T* wt = reinterpret_cast<const T*>(&wv);
-    const float yf[4] = {yv.x, yv.y, yv.z, yv.w};
-    T o[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = Tr<T>::r(Tr<T>::f(wt[q]) * Tr<T>::rr(yf[q] * rs));   // weight * T(x * rstd)
-    *reinterpret_cast<uint2*>(xrow + c) = *reinterpret_cast<const uint2*>(o);
-  }
-}
-
 template <class T, int NT, bool SWIGLU>
 __global__ void __launch_bounds__(TC_THREADS, (NT <= 64) ? 2 : 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, T* __restrict__ out,
-                 const TcParams p) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                 const __grid_constant__ CUtensorMap map_next, T* __restrict__ out, const TcParams p) {
   using Cfg = TcCfg<NT, SWIGLU>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -444,6 +365,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+    if (p.pf_p > 0) {
+      // all of this CTA's loads are in flight: pull the head of the next GEMM's weight stream into L2 (nothing waits on it)
+      const int G = gridDim.x * gridDim.z, g = blockIdx.z * gridDim.x + blockIdx.x;
+      const int per_i = p.pf_tiles * p.pf_splits * p.pf_halves, total = per_i * p.pf_p;
+      for (int b = g + lane * G; b < total; b += 32 * G) {
+        const int i = b / per_i;
+        int r = b - i * per_i;
+        const int half = r % p.pf_halves; r /= p.pf_halves;
+        const int z = r % p.pf_splits, t = r / p.pf_splits;
+        const int kb = (int)(((int64_t)p.pf_kb_total * z) / p.pf_splits) + i;
+        if (kb < (int)(((int64_t)p.pf_kb_total * (z + 1)) / p.pf_splits))
+          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                       ::"l"(reinterpret_cast<uint64_t>(&map_next)), "r"(kb * BLOCK_K), "r"(t * BLOCK_N + half * p.pf_n) : "memory");
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
@@ -560,7 +496,7 @@ _Pragma("unroll")
       // while the weight stream runs: pull the residual values this thread will add and the lora_t rows of the tile
       T* res_s = reinterpret_cast<T*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
       T* lt_s = res_s + NT * BLOCK_N;
-      if (p.epi_mode == EPI_RES1 && n < p.N && (p.splits == 1 || p.cluster) && !p.fin) {
+      if (p.epi_mode == EPI_RES1 && n < p.N && (p.splits == 1 || p.cluster)) {
         const int j0 = p.splits == 1 ? 0 : split, jstep = p.splits == 1 ? 1 : p.splits;
         for (int jb = j0; jb < m_valid; jb += 8 * jstep) {
           T tmp[8];
@@ -656,9 +592,9 @@ _Pragma("unroll")
           }
         }
       }
-    } else if (NT <= 32 && !SWIGLU && p.fin) {
-      // ---- finisher split-K: publish the fp32 partial tile (a warp stores 128 contiguous bytes per token), take a ticket ----
-      float* part = p.ws_part + (int64_t)split * NT * p.N;
+    } else if (NT <= 32 && !SWIGLU && p.part_out != nullptr) {
+      // ---- partials out: publish the fp32 partial tile (a warp stores 128 contiguous bytes per token) and leave ----
+      float* part = p.part_out + (int64_t)split * NT * p.N;
       for (int c = 0; c < m_valid; c += 16) {
         uint32_t r[16];
         tc_ld16(taddr + c, r);
@@ -667,33 +603,6 @@ _Pragma("unroll")
 _Pragma("unroll")
           for (int j = 0; j < 16; ++j)
             if (c + j < m_valid) __stcg(part + (int64_t)(c + j) * p.N + n, __uint_as_float(r[j]));
-        }
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) { *flag_smem = atomicAdd(p.fin_ctr, 1u); trace_stamp(p.trace, 8); }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const uint32_t total = gridDim.x * gridDim.z;
-      const uint32_t nfin = total < (uint32_t)m_valid ? total : (uint32_t)m_valid;      // finishers: the last nfin CTAs to arrive
-      const int first = (int)*flag_smem - (int)(total - nfin);
-      if (first >= 0) {
-        // all CTAs of the grid are co-resident (one wave), so the rest arrive without our help
-        if (threadIdx.x == 64) {
-          while (ld_acquire_u32(p.fin_ctr) < total) __nanosleep(32);
-          trace_stamp(p.trace, 9);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        __threadfence();
-        float* srow = reinterpret_cast<float*>(smem);                  // the pipeline smem is idle: all MMAs have completed
-        for (int row = first; row < m_valid; row += (int)nfin) {
-          finish_row<T>(p, out, m0 + row, NT, srow, s_norm);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        if (threadIdx.x == 64) {
-          trace_stamp(p.trace, 10);
-          __threadfence();
-          const uint32_t prev = atomicAdd(p.fin_ctr + 1, 1u);
-          if (prev == nfin - 1) { p.fin_ctr[1] = 0; p.fin_ctr[0] = 0; __threadfence(); }   // re-arm for the next launch
         }
       }
     } else if (p.splits == 1) {
@@ -940,6 +849,12 @@ int choose_splits(int tiles, int kb) {
   return best;
 }
 
+// split count launch_tc would pick for a decode GEMM with `tiles` weight tiles of `kb` k-blocks (smem budget does not depend on T)
+int decode_splits(int nt, bool swiglu, int tiles, int kb) {
+  if (nt <= 16) return swiglu ? choose_splits<__half, 16, true>(tiles, kb) : choose_splits<__half, 16, false>(tiles, kb);
+  return swiglu ? choose_splits<__half, 32, true>(tiles, kb) : choose_splits<__half, 32, false>(tiles, kb);
+}
+
 // set by rd_linear_tc_fused for the launch it wraps (single-threaded use per handle, like the rest of the library)
 static const TcFuse* g_fuse = nullptr;
 
@@ -996,21 +911,20 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
                  "rd_linear_tc_fused: sum-of-squares output needs the residual epilogue, N %% 128 == 0 and no workspace split-K");
       p.ssq_out = f.ssq_out;
     }
-    if (f.fin_ctr != nullptr) {
-      RD_REQUIRE(!SWIGLU && p.epi_mode == EPI_RES1 && N % 4 == 0 && ldo % 4 == 0 && epi.ld_res % 4 == 0 &&
-                 (int64_t)N * 4 <= (int64_t)Cfg::STAGES * Cfg::STAGE_BYTES,
-                 "rd_linear_tc_fused: the finisher split-K needs the residual epilogue, N %% 4 == 0 and a token row that fits the pipeline smem");
-      const int one_wave = resident_capacity<T, NT, SWIGLU>(1);
-      RD_REQUIRE(n_tiles * splits <= one_wave, "rd_linear_tc_fused: finisher split-K needs a single-wave grid");
-      const int64_t need = 256 + (int64_t)splits * NT * N * 4;
-      RD_REQUIRE(ws != nullptr && ws_bytes >= need, "rd_linear_tc_fused: workspace too small for the partial slabs (%lld < %lld)", (long long)ws_bytes, (long long)need);
-      p.fin = 1; p.fin_ctr = f.fin_ctr; p.fin_norm_w = f.fin_norm_w; p.fin_xn = f.fin_xn; p.fin_eps = f.fin_eps;
-      p.ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 256);
+    if (f.part_out != nullptr) {
+      const bool plain = !SWIGLU && p.epi_mode == EPI_PLAIN;
+      const int64_t need = (int64_t)splits * NT * N * 4;
+      if (!plain || f.part_bytes < need) {
+        rd_set_error("rd_linear_tc_fused: partials-out needs a plain epilogue and a slab of %lld bytes (got %lld)", (long long)need, (long long)f.part_bytes);
+        return RD_ERR_INVALID;
+      }
+      p.part_out = f.part_out;
       p.cluster = 0;
+      if (f.splits_out != nullptr) { f.splits_out[0] = splits; f.splits_out[1] = NT; }
     }
   }
-  const bool cluster_launch = use_cluster && !p.fin;
-  if (splits > 1 && !use_cluster && !p.fin) {
+  const bool cluster_launch = use_cluster && p.part_out == nullptr;
+  if (splits > 1 && !use_cluster && p.part_out == nullptr) {
     const int64_t part_bytes = (int64_t)splits * n_tiles * m_tiles * Cfg::ACCS * NT * BLOCK_N * 4;
     const int64_t need = part_bytes + ((int64_t)n_tiles * m_tiles * 4 + 255) / 256 * 256;
     RD_REQUIRE(ws != nullptr && ws_bytes >= need, "rd_linear: split-K workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
@@ -1032,7 +946,22 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<T, NT, SWIGLU>, map_w, map_x, (T*)out, p));
+  CUtensorMap map_next = map_w;         // a valid descriptor even when nothing is prefetched
+  if (g_fuse != nullptr && g_fuse->next_w != nullptr && g_fuse->next_bytes > 0 && m_tiles == 1 && NT <= 32) {
+    const TcFuse& f = *g_fuse;
+    const bool nsw = f.next_swiglu != 0;
+    const int nt_n = (f.next_N + BLOCK_N - 1) / BLOCK_N, kb_n = (f.next_K + BLOCK_K - 1) / BLOCK_K;
+    int sp_n = decode_splits(NT, nsw, nt_n, kb_n);
+    if (sp_n > kb_n) sp_n = kb_n;
+    const int halves = nsw ? 2 : 1;
+    const int64_t per_i = (int64_t)nt_n * sp_n * halves * BLOCK_N * BLOCK_K * 2;
+    int pp = (int)(f.next_bytes / per_i);
+    const int kb_per = (kb_n + sp_n - 1) / sp_n;
+    pp = pp < 1 ? 1 : (pp > kb_per ? kb_per : pp);
+    RD_CHECK(make_map(&map_next, f.next_w, f.next_ldw, nsw ? 2 * f.next_N : f.next_N, f.next_K, BLOCK_N, dtype));
+    p.pf_p = pp; p.pf_tiles = nt_n; p.pf_splits = sp_n; p.pf_halves = halves; p.pf_kb_total = kb_n; p.pf_n = f.next_N;
+  }
+  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<T, NT, SWIGLU>, map_w, map_x, map_next, (T*)out, p));
   return RD_OK;
 }
 

@@ -116,7 +116,7 @@ class LlamaForCausalLM:
         self.mega = False     # persistent all-layers decode kernel (experimental)
         self.fused_norm = False   # RMSNorm inside the decode GEMMs (experimental)
         self.streamk = False  # stream-K decode GEMMs with fused RMSNorm (experimental)
-        self.fused_tail = True    # o_proj / down_proj finisher split-K with the residual add + following RMSNorm fused (default)
+        self.qkv_partials = True  # QKV GEMM hands its fp32 split-K partials to the attention kernel (default)
         self.use_cuda_graph = True
         self.last_stats: Dict[str, float] = {}
 
@@ -300,7 +300,7 @@ class LlamaForCausalLM:
         _lib.check(self._lib.rd_llm_set_mega(h, 1 if self.mega else 0), "set_mega")
         _lib.check(self._lib.rd_llm_set_streamk(h, 1 if self.streamk else 0), "set_streamk")
         _lib.check(self._lib.rd_llm_set_fused_norm(h, 1 if self.fused_norm else 0), "set_fused_norm")
-        _lib.check(self._lib.rd_llm_set_fused_tail(h, 1 if self.fused_tail else 0), "set_fused_tail")
+        _lib.check(self._lib.rd_llm_set_qkv_partials(h, 1 if self.qkv_partials else 0), "set_qkv_partials")
 
     def _bind_img_proj(self):
         lin = self.model.img_proj_layer
@@ -326,13 +326,13 @@ class LlamaForCausalLM:
         if self._h is not None:
             _lib.check(self._lib.rd_llm_set_fused_norm(self._h, 1 if on else 0), "set_fused_norm")
 
-    def set_fused_tail(self, on: bool):
-        """Single-token steps: o_proj / down_proj as finisher split-K GEMMs with the residual add and the following RMSNorm
-        fused (default, 5 launches per layer), or cluster split-K GEMMs + separate norm kernels (7 launches per layer)."""
-        self.fused_tail = bool(on)
+    def set_qkv_partials(self, on: bool):
+        """Single-token steps: the QKV GEMM leaves fp32 split-K partials for the attention kernel to sum (default), or reduces
+        them itself over a thread-block cluster."""
+        self.qkv_partials = bool(on)
         self._graphs = {}
         if self._h is not None:
-            _lib.check(self._lib.rd_llm_set_fused_tail(self._h, 1 if on else 0), "set_fused_tail")
+            _lib.check(self._lib.rd_llm_set_qkv_partials(self._h, 1 if on else 0), "set_qkv_partials")
 
     def set_streamk(self, on: bool):
         """Decode GEMMs as stream-K kernels with fused RMSNorm, or (default) tile x split-K kernels + norm kernels."""

@@ -302,33 +302,30 @@ def test_rmsnorm_fused_into_decode_gemms_matches_separate_norm_kernels(cuda_dev,
     assert_ids_match(b.sequences.cpu(), o_ids, o_scores, prompts.shape[1], dtype, f"fused norm {dtype_name} B={B}", min_exact_rows=0.75)
 
 
-@pytest.mark.parametrize("dtype_name,B,layers", [("float16", 3, 2), ("bfloat16", 32, 3), ("float16", 1, 2), ("bfloat16", 17, 2), ("float16", 32, 4)])
-def test_fused_tail_decode_matches_separate_norm_kernels(cuda_dev, dtype_name, B, layers):
-    """Default decode path (o_proj / down_proj as finisher split-K GEMMs: fp32 partial slabs, the last CTAs finish whole token
-    rows with the residual add and the following RMSNorm fused) against cluster split-K GEMMs + separate norm kernels and the
-    oracle.  Same rounding contract and the same split order, so the residual stream is bit-identical; only the fp32 order of
-    the norm's sum of squares differs."""
+@pytest.mark.parametrize("dtype_name,B,layers,lora", [("float16", 3, 2, True), ("bfloat16", 32, 3, True), ("float16", 1, 2, True),
+                                                      ("bfloat16", 17, 2, False), ("float16", 32, 4, True)])
+def test_qkv_partials_to_attention_bit_identical_to_gemm_side_reduction(cuda_dev, dtype_name, B, layers, lora):
+    """Default decode path (the QKV GEMM leaves its fp32 split-K partials in a slab, the attention kernel sums them in split
+    order and rounds once as it reads q/k/v and the LoRA t columns) against the GEMM-side cluster reduction: same partials,
+    same order, same single rounding, so every logit must be BIT-identical - eager and under CUDA-graph replay."""
     dtype = DT[dtype_name]
     cfg = synth.tiny_llama_cfg(num_hidden_layers=layers)
-    model, orc, _ = build(cfg, dtype, cuda_dev)
+    model, orc, _ = build(cfg, dtype, cuda_dev, lora=lora)
     prompts = synth.make_prompts(B, seed=399 + B, ragged=True)
     img = img_tokens(B, cfg, seed=B + 3)
     n_new = 9
     outs = {}
-    for tail in (False, True):
-        model.set_fused_tail(tail)
+    for part in (False, True):
+        model.set_qkv_partials(part)
         for graph in (False, True):
             model.use_cuda_graph = graph
-            outs[(tail, graph)] = model.generate(prompts.to(cuda_dev), img_embeds=img.to(cuda_dev), max_new_tokens=n_new, suppress_eos=True,
+            outs[(part, graph)] = model.generate(prompts.to(cuda_dev), img_embeds=img.to(cuda_dev), max_new_tokens=n_new, suppress_eos=True,
                                                  return_dict_in_generate=True, output_scores=True)
-    model.set_fused_tail(True)
-    assert torch.equal(outs[(True, False)].sequences, outs[(True, True)].sequences), "graph replay differs from eager launches"
-    a, b = outs[(False, True)], outs[(True, True)]
-    scale = a.scores[1].float().abs().max().item()
-    for s in (1, 2, n_new - 1):
-        err = (a.scores[s].float() - b.scores[s].float()).abs().max().item()
-        tol = (2e-3 if dtype == torch.float16 else 1.6e-2) * scale      # ~2 storage-dtype ulps at the logit scale
-        if torch.equal(a.sequences[:, :prompts.shape[1] + s], b.sequences[:, :prompts.shape[1] + s]):
-            assert err <= tol, f"decode step {s} logits differ between the two paths: {err:.4g} vs scale {scale:.4g}"
+    model.set_qkv_partials(True)
+    ref = outs[(False, False)]
+    for key, o in outs.items():
+        assert torch.equal(o.sequences, ref.sequences), f"ids differ for (partials, graph) = {key}"
+        for s in range(n_new):
+            assert torch.equal(o.scores[s], ref.scores[s]), f"step {s} logits not bit-identical for (partials, graph) = {key}"
     o_ids, o_scores = orc.generate(prompts, img, n_new, suppress_eos=True, return_scores=True)
-    assert_ids_match(b.sequences.cpu(), o_ids, o_scores, prompts.shape[1], dtype, f"fused tail {dtype_name} B={B}", min_exact_rows=0.75)
+    assert_ids_match(ref.sequences.cpu(), o_ids, o_scores, prompts.shape[1], dtype, f"qkv partials {dtype_name} B={B}", min_exact_rows=0.75)
