@@ -122,39 +122,56 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
     // q/k/v (and the LoRA t columns) of this row: either the QKV GEMM's rounded output, or - split-K GEMM without a reduction
     // pass - its fp32 partial slabs [n_part][rows][ldq], summed here in split order and rounded once: T(Wx) either way
     const float* prow = qkv_part != nullptr ? qkv_part + (int64_t)b * ldq : nullptr;
-    auto ldv = [&](int col) -> float {
+    auto ldv = [&](int col) -> float {               // one value (generic path)
       if (prow == nullptr) return Tr<T>::f(row[col]);
       float a = 0.f;
       for (int s = 0; s < n_part; ++s) a += __ldcg(prow + (int64_t)s * part_stride + col);
       return Tr<T>::rr(a);
     };
-    // peft LoRA (unmerged): the GEMM wrote t = T(lora_A . xn) after the 3H projection columns (q's r values, then v's)
-    auto lora = [&](float y, int n_row, int tcol) {
-      const T* brow = lora_b + (int64_t)n_row * lora_r;
-      float sdot = 0.f;
-      if (lora_r == 8 && prow == nullptr) {   // the reference's adapter rank (finetune.py:167): two 128-bit loads instead of 16 scalar ones
-        const Vec8<T> bv = ld16(brow), tv = ld16(row + tcol);
+    // every value this thread needs (2 or 4 projection outputs + the 8 LoRA t columns), requested together: with partial slabs
+    // these are L2 round trips, and one dependent chain per value would cost more than the reduction pass it replaces
+    auto gather = [&](const int* cols, int n, float* o) {
+      if (prow != nullptr && n_part <= 2) {
+        float a[12], c[12];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sdot = fmaf(Tr<T>::f(bv.v[i]), Tr<T>::f(tv.v[i]), sdot);
-      } else if (lora_r == 8) {
-        const Vec8<T> bv = ld16(brow);
-        float tv[8];
+        for (int i = 0; i < 12; ++i) if (i < n) a[i] = __ldcg(prow + cols[i]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tv[i] = ldv(tcol + i);
+        for (int i = 0; i < 12; ++i) c[i] = (i < n && n_part == 2) ? __ldcg(prow + part_stride + cols[i]) : 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sdot = fmaf(Tr<T>::f(bv.v[i]), tv[i], sdot);
+        for (int i = 0; i < 12; ++i) if (i < n) o[i] = Tr<T>::rr(a[i] + c[i]);         // (0 + p0) + p1, split order
       } else {
-        for (int i = 0; i < lora_r; ++i) sdot = fmaf(Tr<T>::f(brow[i]), ldv(tcol + i), sdot);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) if (i < n) o[i] = ldv(cols[i]);
       }
+    };
+    // peft LoRA (unmerged): the GEMM wrote t = T(lora_A . xn) after the 3H projection columns (q's r values, then v's)
+    auto lora8 = [&](float y, int n_row, const float* t) {
+      const Vec8<T> bv = ld16(lora_b + (int64_t)n_row * 8);
+      float sdot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sdot = fmaf(Tr<T>::f(bv.v[i]), t[i], sdot);
       return Tr<T>::rr(y + Tr<T>::rr(lora_scale * Tr<T>::rr(sdot)));
     };
+    auto lora_any = [&](float y, int n_row, int tcol) {
+      const T* brow = lora_b + (int64_t)n_row * lora_r;
+      float sdot = 0.f;
+      for (int i = 0; i < lora_r; ++i) sdot = fmaf(Tr<T>::f(brow[i]), ldv(tcol + i), sdot);
+      return Tr<T>::rr(y + Tr<T>::rr(lora_scale * Tr<T>::rr(sdot)));
+    };
+    const bool l8 = lora_r == 8;
     if (tid < half) {
       const int d = tid, p = pos[b];
       const float c_lo = Tr<T>::f(cos_t[(int64_t)p * HD + d]), c_hi = Tr<T>::f(cos_t[(int64_t)p * HD + d + half]);
       const float s_lo = Tr<T>::f(sin_t[(int64_t)p * HD + d]), s_hi = Tr<T>::f(sin_t[(int64_t)p * HD + d + half]);
-      float lo = ldv(h * HD + d), hi = ldv(h * HD + d + half);
-      float klo = ldv(H + h * HD + d), khi = ldv(H + h * HD + d + half);
-      if (lora_r > 0) { lo = lora(lo, h * HD + d, 3 * H); hi = lora(hi, h * HD + d + half, 3 * H); }
+      int cols[12] = {h * HD + d, h * HD + d + half, H + h * HD + d, H + h * HD + d + half, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cols[4 + i] = 3 * H + i;
+      float v[12];
+      gather(cols, l8 ? 12 : 4, v);
+      float lo = v[0], hi = v[1];
+      const float klo = v[2], khi = v[3];
+      if (l8) { lo = lora8(lo, h * HD + d, v + 4); hi = lora8(hi, h * HD + d + half, v + 4); }
+      else if (lora_r > 0) { lo = lora_any(lo, h * HD + d, 3 * H); hi = lora_any(hi, h * HD + d + half, 3 * H); }
       s_q[d] = Tr<T>::rr(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
       s_q[d + half] = Tr<T>::rr(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
       const float k_lo = Tr<T>::rr(Tr<T>::rr(klo * c_lo) + Tr<T>::rr(-khi * s_lo));
@@ -163,10 +180,16 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
       kc[slot_off + d] = Tr<T>::r(k_lo); kc[slot_off + d + half] = Tr<T>::r(k_hi);
     } else if (tid < 2 * half) {
       const int d = tid - half;
-      float v_lo = ldv(2 * H + h * HD + d), v_hi = ldv(2 * H + h * HD + d + half);
-      if (lora_r > 0) {
-        v_lo = lora(v_lo, H + h * HD + d, 3 * H + lora_r);
-        v_hi = lora(v_hi, H + h * HD + d + half, 3 * H + lora_r);
+      int cols[12] = {2 * H + h * HD + d, 2 * H + h * HD + d + half, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cols[2 + i] = 3 * H + 8 + i;
+      float v[12];
+      gather(cols, l8 ? 10 : 2, v);
+      float v_lo = v[0], v_hi = v[1];
+      if (l8) { v_lo = lora8(v_lo, H + h * HD + d, v + 2); v_hi = lora8(v_hi, H + h * HD + d + half, v + 2); }
+      else if (lora_r > 0) {
+        v_lo = lora_any(v_lo, H + h * HD + d, 3 * H + lora_r);
+        v_hi = lora_any(v_hi, H + h * HD + d + half, 3 * H + lora_r);
       }
       s_v[d] = v_lo; s_v[d + half] = v_hi;
       vc[slot_off + d] = Tr<T>::r(v_lo); vc[slot_off + d + half] = Tr<T>::r(v_hi);

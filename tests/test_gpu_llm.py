@@ -303,7 +303,7 @@ def test_rmsnorm_fused_into_decode_gemms_matches_separate_norm_kernels(cuda_dev,
 
 
 @pytest.mark.parametrize("dtype_name,B,layers,lora", [("float16", 3, 2, True), ("bfloat16", 32, 3, True), ("float16", 1, 2, True),
-                                                      ("bfloat16", 17, 2, False), ("float16", 32, 4, True)])
+                                                      ("float16", 17, 2, False), ("float16", 32, 4, True)])
 def test_qkv_partials_to_attention_bit_identical_to_gemm_side_reduction(cuda_dev, dtype_name, B, layers, lora):
     """Default decode path (the QKV GEMM leaves its fp32 split-K partials in a slab, the attention kernel sums them in split
     order and rounds once as it reads q/k/v and the LoRA t columns) against the GEMM-side cluster reduction: same partials,

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Decode-step time (CUDA graph + PDL, the bench configuration) of the full Vicuna-7B-sized engine under engine switches
+(development tool): QKV partials on/off x next-GEMM weight prefetch budgets.  python tools/decode_sweep.py [B] [NEW]"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from radialog_b200 import _lib, synth  # noqa: E402
+from radialog_b200.llm import LlamaForCausalLM  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+NEW = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+dev = torch.device("cuda:0")
+dtype = torch.bfloat16
+lib = _lib.load()
+lib.rd_set_pdl(1)
+cfg = synth.LlamaCfg()
+sd = synth.make_llama_weights(cfg, seed=0, dtype=dtype, device="cuda:0")
+llm = LlamaForCausalLM.from_state_dict(cfg, sd, torch_dtype=dtype, device=dev)
+del sd
+torch.cuda.empty_cache()
+prompts = synth.make_prompts(B, seed=4321).to(dev)
+img = torch.randn(B, 32, 768, device=dev) * 0.5
+MB = 1 << 20
+variants = [("partials=1 pf=default", True, None)]
+for spec in os.environ.get("PF", "0,0,0,0;34,64,48,64;34,96,64,96;34,32,24,32;0,64,0,64;34,0,48,0").split(";"):
+    variants.append((f"partials=1 pf={spec}", True, tuple(int(float(v) * MB) for v in spec.split(","))))
+variants.append(("partials=0 pf=0,0,0,0", False, (0, 0, 0, 0)))
+variants.append(("partials=0 pf=34,64,48,64", False, (34 * MB, 64 * MB, 48 * MB, 64 * MB)))
+res = []
+for name, part, pf in variants:
+    llm.set_qkv_partials(part)
+    if pf is not None:
+        llm.set_gemm_prefetch(*pf)
+    llm.generate(prompts, img_embeds=img, max_new_tokens=8, suppress_eos=True)
+    best = 1e9
+    for _ in range(2):
+        llm.generate(prompts, img_embeds=img, max_new_tokens=NEW, suppress_eos=True)
+        best = min(best, llm.last_stats["decode_ms"] / (NEW - 1))
+    res.append({"variant": name, "B": B, "ms_per_step": best})
+    print(f"B={B} {name:40s} {best:.3f} ms/step", flush=True)
+if len(sys.argv) > 3:
+    json.dump(res, open(sys.argv[3], "w"), indent=1)
