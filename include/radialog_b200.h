@@ -192,12 +192,6 @@ int rd_llm_set_fused_norm(rd_llm* h, int on);
  * single rounding T(Wx) while reading q/k/v - the GEMM has no cross-CTA reduction tail.  0 = the GEMM reduces them itself
  * (thread-block cluster + distributed shared memory).  Same rounding contract and the same summation order either way.  */
 int rd_llm_set_qkv_partials(rd_llm* h, int on);
-/* Decode step, B <= 32: every GEMM of a layer is HBM-bound but ends in a latency-bound tail (split-K reduction, epilogue) and a
- * launch boundary during which HBM would idle.  Once a GEMM's own weight loads are all in flight its producer warps request
- * (cp.async.bulk.prefetch.tensor -> the 126 MB L2) the head of the NEXT GEMM's weight stream: about this many bytes, the first
- * k-blocks of each of the next kernel's CTAs.  Order: q/k/v -> o_proj, o_proj -> gate|up, gate|up -> down_proj, down_proj ->
- * next layer's q/k/v (lm_head after the last layer).  0 switches a site off.  No effect on results. */
-int rd_llm_set_gemm_prefetch(rd_llm* h, long long qkv_to_o, long long o_to_gate_up, long long gate_up_to_down, long long down_to_qkv);
 /* Decode step: bytes of W_qkv / W_o / W_gate|up that the (latency-bound, HBM-idle) norm and attention kernels pull into
  * the 126 MB L2 with cp.async.bulk.prefetch ahead of the GEMM that streams them; 0,0,0 turns it off. */
 int rd_llm_set_l2_prefetch(rd_llm* h, long long qkv_bytes, long long o_bytes, long long gate_up_bytes);

@@ -139,6 +139,14 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
         for (int i = 0; i < 12; ++i) c[i] = (i < n && n_part == 2) ? __ldcg(prow + part_stride + cols[i]) : 0.f;
 #pragma unroll
         for (int i = 0; i < 12; ++i) if (i < n) o[i] = Tr<T>::rr(a[i] + c[i]);         // (0 + p0) + p1, split order
+      } else if (prow == nullptr && n > 4 - 0 && (n == 12 || n == 10)) {
+        // rounded GEMM output: the 8 LoRA t columns are one aligned 16-byte load
+        const int np = n - 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i < np) o[i] = Tr<T>::f(row[cols[i]]);
+        const Vec8<T> tv = ld16(row + cols[np]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[np + i] = Tr<T>::f(tv.v[i]);
       } else {
 #pragma unroll
         for (int i = 0; i < 12; ++i) if (i < n) o[i] = ldv(cols[i]);

@@ -245,12 +245,6 @@ struct TcFuse {
   float* part_out = nullptr;
   int64_t part_bytes = 0;
   int* splits_out = nullptr;
-  // L2 prefetch of the head of the NEXT decode GEMM's weights (see TcParams::pf_p): next_w [next_N (x2 if SwiGLU), next_K],
-  // about next_bytes of it, issued by this GEMM's producer warps once their own loads are in flight.
-  const void* next_w = nullptr;
-  int64_t next_ldw = 0;
-  int next_N = 0, next_K = 0, next_swiglu = 0;
-  int64_t next_bytes = 0;
 };
 int rd_linear_tc_fused(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
                        const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, const TcFuse* fuse, cudaStream_t st);

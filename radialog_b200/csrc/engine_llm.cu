@@ -51,9 +51,6 @@ struct rd_llm {
   // single-token steps with B <= 32 (default ON): the QKV GEMM leaves its fp32 split-K partials in `qkv_part` and the attention
   // kernel sums them (fixed order, one rounding) when it reads q/k/v - no cross-CTA reduction pass in the GEMM's tail.
   int qkv_partials = 1;
-  // decode GEMMs (B <= 32): bytes of the NEXT GEMM's weights each GEMM's producer warps pull into L2 once their own loads are
-  // in flight (qkv -> o_proj, o_proj -> gate|up, gate|up -> down_proj, down_proj -> next layer's qkv / lm_head); 0 = off
-  long long pf_gemm[4] = {34ll << 20, 64ll << 20, 48ll << 20, 64ll << 20};
   float* qkv_part = nullptr;
   int64_t qkv_part_bytes = 0;
   // L2 weight prefetch from the norm / attention kernels: mechanism kept, OFF by default (A/B runs on B200 showed no
@@ -358,7 +355,6 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     TcFuse f_out{nullptr, nullptr, 0, 0.f, h->ssq};
     // decode, B <= 32: QKV split-K partials go straight to the attention kernel (no reduction pass in the GEMM)
     const bool qpart = h->qkv_partials && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && (3 * H + R2) % 4 == 0;
-    const bool gpf = !fuse && q_len == 1 && M <= 32 && h->algo == 0;      // decode GEMMs prefetch the next GEMM's weights into L2
     int qsplit[2] = {0, 0};
     if (fuse && l > 0) {
       RD_CHECK(linear_fused(h, C_QKV, h->x, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &f_in1, st));
@@ -369,11 +365,6 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
       if (qpart) {
         TcFuse tq{};
         tq.part_out = h->qkv_part; tq.part_bytes = h->qkv_part_bytes; tq.splits_out = qsplit;
-        tq.next_w = w.o; tq.next_ldw = H; tq.next_N = H; tq.next_K = H; tq.next_bytes = h->pf_gemm[0];
-        RD_CHECK(linear_fused(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &tq, st));
-      } else if (gpf) {
-        TcFuse tq{};
-        tq.next_w = w.o; tq.next_ldw = H; tq.next_N = H; tq.next_K = H; tq.next_bytes = h->pf_gemm[0];
         RD_CHECK(linear_fused(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &tq, st));
       } else {
         RD_CHECK(linear(h, C_QKV, h->xn, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, st));
@@ -405,19 +396,6 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
       eg.act = RD_ACT_SWIGLU;
       RD_CHECK(linear_fused(h, C_GATEUP, h->x, H, w.gate_up, H, h->mid, I, M, I, H, &eg, &f_in2, st));
       RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, &f_out, st));
-    } else if (gpf) {
-      TcFuse to{}, tg{}, td{};
-      to.next_w = w.gate_up; to.next_ldw = H; to.next_N = I; to.next_K = H; to.next_swiglu = 1; to.next_bytes = h->pf_gemm[1];
-      tg.next_w = w.down; tg.next_ldw = I; tg.next_N = H; tg.next_K = I; tg.next_bytes = h->pf_gemm[2];
-      if (l + 1 < c.layers) { td.next_w = h->L[l + 1].qkv; td.next_N = 3 * H + R2; } else { td.next_w = h->lm_head; td.next_N = c.vocab; }
-      td.next_ldw = H; td.next_K = H; td.next_bytes = h->pf_gemm[3];
-      RD_CHECK(linear_fused(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, &to, st));
-      { ProfScope ps(h, st, C_RMSNORM);
-        RD_CHECK(rd_rmsnorm(h->x, w.ln2, h->xn, M, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
-      rd_epilogue eg{};
-      eg.act = RD_ACT_SWIGLU;
-      RD_CHECK(linear_fused(h, C_GATEUP, h->xn, H, w.gate_up, H, h->mid, I, M, I, H, &eg, &tg, st));
-      RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, &td, st));
     } else {
       RD_CHECK(linear(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, st));
       { ProfScope ps(h, st, C_RMSNORM);
@@ -560,14 +538,6 @@ extern "C" int rd_llm_set_mega(rd_llm* h, int on) {
 extern "C" int rd_llm_set_fused_norm(rd_llm* h, int on) {
   RD_REQUIRE(h, "rd_llm_set_fused_norm: null handle");
   h->fuse_norm = on ? 1 : 0;
-  return RD_OK;
-}
-
-// Bytes of the next GEMM's weights that each decode GEMM (B <= 32) pulls into L2 from its producer warps once its own loads are
-// in flight: qkv -> o_proj, o_proj -> gate|up, gate|up -> down_proj, down_proj -> next layer's qkv (lm_head after the last layer).
-extern "C" int rd_llm_set_gemm_prefetch(rd_llm* h, long long qkv_to_o, long long o_to_gate_up, long long gate_up_to_down, long long down_to_qkv) {
-  RD_REQUIRE(h, "rd_llm_set_gemm_prefetch: null handle");
-  h->pf_gemm[0] = qkv_to_o; h->pf_gemm[1] = o_to_gate_up; h->pf_gemm[2] = gate_up_to_down; h->pf_gemm[3] = down_to_qkv;
   return RD_OK;
 }
 

@@ -263,19 +263,14 @@ struct TcParams {
   // part_out[split][NT][N] and is done - no cluster, no DSMEM, no reduction pass.  The consumer (attention_decode_kernel) sums
   // the splits in fixed order and applies the single rounding T(Wx) when it reads q/k/v.
   float* part_out;
-  // Weight prefetch for the NEXT GEMM of the decode step (m_tiles == 1): once this CTA's own loads are all issued, its producer
-  // warp requests (cp.async.bulk.prefetch.tensor -> L2) boxes of the next GEMM's weight stream: the first pf_p k-blocks of each
-  // of its (tile, split) CTAs, dealt round-robin over this grid.  HBM then keeps streaming through this kernel's reduction tail
-  // and the launch boundary instead of idling, and the next kernel's first loads hit L2.
-  int pf_p, pf_tiles, pf_splits, pf_halves, pf_kb_total, pf_n;
   int wide_epi;                // NT >= 64: transposed epilogue through shared memory (coalesced residual loads / stores)
   EpiParams epi;
 };
 
 template <class T, int NT, bool SWIGLU>
 __global__ void __launch_bounds__(TC_THREADS, (NT <= 64) ? 2 : 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-                 const __grid_constant__ CUtensorMap map_next, T* __restrict__ out, const TcParams p) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, T* __restrict__ out,
+                 const TcParams p) {
   using Cfg = TcCfg<NT, SWIGLU>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -365,21 +360,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1u; }
-    }
-    if (p.pf_p > 0) {
-      // all of this CTA's loads are in flight: pull the head of the next GEMM's weight stream into L2 (nothing waits on it)
-      const int G = gridDim.x * gridDim.z, g = blockIdx.z * gridDim.x + blockIdx.x;
-      const int per_i = p.pf_tiles * p.pf_splits * p.pf_halves, total = per_i * p.pf_p;
-      for (int b = g + lane * G; b < total; b += 32 * G) {
-        const int i = b / per_i;
-        int r = b - i * per_i;
-        const int half = r % p.pf_halves; r /= p.pf_halves;
-        const int z = r % p.pf_splits, t = r / p.pf_splits;
-        const int kb = (int)(((int64_t)p.pf_kb_total * z) / p.pf_splits) + i;
-        if (kb < (int)(((int64_t)p.pf_kb_total * (z + 1)) / p.pf_splits))
-          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-                       ::"l"(reinterpret_cast<uint64_t>(&map_next)), "r"(kb * BLOCK_K), "r"(t * BLOCK_N + half * p.pf_n) : "memory");
-      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
@@ -849,12 +829,6 @@ int choose_splits(int tiles, int kb) {
   return best;
 }
 
-// split count launch_tc would pick for a decode GEMM with `tiles` weight tiles of `kb` k-blocks (smem budget does not depend on T)
-int decode_splits(int nt, bool swiglu, int tiles, int kb) {
-  if (nt <= 16) return swiglu ? choose_splits<__half, 16, true>(tiles, kb) : choose_splits<__half, 16, false>(tiles, kb);
-  return swiglu ? choose_splits<__half, 32, true>(tiles, kb) : choose_splits<__half, 32, false>(tiles, kb);
-}
-
 // set by rd_linear_tc_fused for the launch it wraps (single-threaded use per handle, like the rest of the library)
 static const TcFuse* g_fuse = nullptr;
 
@@ -946,22 +920,7 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  CUtensorMap map_next = map_w;         // a valid descriptor even when nothing is prefetched
-  if (g_fuse != nullptr && g_fuse->next_w != nullptr && g_fuse->next_bytes > 0 && m_tiles == 1 && NT <= 32) {
-    const TcFuse& f = *g_fuse;
-    const bool nsw = f.next_swiglu != 0;
-    const int nt_n = (f.next_N + BLOCK_N - 1) / BLOCK_N, kb_n = (f.next_K + BLOCK_K - 1) / BLOCK_K;
-    int sp_n = decode_splits(NT, nsw, nt_n, kb_n);
-    if (sp_n > kb_n) sp_n = kb_n;
-    const int halves = nsw ? 2 : 1;
-    const int64_t per_i = (int64_t)nt_n * sp_n * halves * BLOCK_N * BLOCK_K * 2;
-    int pp = (int)(f.next_bytes / per_i);
-    const int kb_per = (kb_n + sp_n - 1) / sp_n;
-    pp = pp < 1 ? 1 : (pp > kb_per ? kb_per : pp);
-    RD_CHECK(make_map(&map_next, f.next_w, f.next_ldw, nsw ? 2 * f.next_N : f.next_N, f.next_K, BLOCK_N, dtype));
-    p.pf_p = pp; p.pf_tiles = nt_n; p.pf_splits = sp_n; p.pf_halves = halves; p.pf_kb_total = kb_n; p.pf_n = f.next_N;
-  }
-  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<T, NT, SWIGLU>, map_w, map_x, map_next, (T*)out, p));
+  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<T, NT, SWIGLU>, map_w, map_x, (T*)out, p));
   return RD_OK;
 }
 

@@ -117,9 +117,6 @@ class LlamaForCausalLM:
         self.fused_norm = False   # RMSNorm inside the decode GEMMs (experimental)
         self.streamk = False  # stream-K decode GEMMs with fused RMSNorm (experimental)
         self.qkv_partials = True  # QKV GEMM hands its fp32 split-K partials to the attention kernel (default)
-        self.gemm_prefetch = None  # bytes of the next GEMM's weights each decode GEMM pulls into L2 (None = engine defaults)
-        if os.environ.get("RD_GEMM_PREFETCH_MB"):              # development aid: "a,b,c,d" MB per site
-            self.gemm_prefetch = tuple(int(float(v) * (1 << 20)) for v in os.environ["RD_GEMM_PREFETCH_MB"].split(","))
         self.use_cuda_graph = True
         self.last_stats: Dict[str, float] = {}
 
@@ -304,8 +301,6 @@ class LlamaForCausalLM:
         _lib.check(self._lib.rd_llm_set_streamk(h, 1 if self.streamk else 0), "set_streamk")
         _lib.check(self._lib.rd_llm_set_fused_norm(h, 1 if self.fused_norm else 0), "set_fused_norm")
         _lib.check(self._lib.rd_llm_set_qkv_partials(h, 1 if self.qkv_partials else 0), "set_qkv_partials")
-        if self.gemm_prefetch is not None:
-            _lib.check(self._lib.rd_llm_set_gemm_prefetch(h, *self.gemm_prefetch), "set_gemm_prefetch")
 
     def _bind_img_proj(self):
         lin = self.model.img_proj_layer
@@ -330,13 +325,6 @@ class LlamaForCausalLM:
         self._graphs = {}
         if self._h is not None:
             _lib.check(self._lib.rd_llm_set_fused_norm(self._h, 1 if on else 0), "set_fused_norm")
-
-    def set_gemm_prefetch(self, qkv_to_o: int, o_to_gate_up: int, gate_up_to_down: int, down_to_qkv: int):
-        """Bytes of the next GEMM's weights each decode GEMM pulls into L2 once its own loads are in flight (0 = off)."""
-        self.gemm_prefetch = (int(qkv_to_o), int(o_to_gate_up), int(gate_up_to_down), int(down_to_qkv))
-        self._graphs = {}
-        if self._h is not None:
-            _lib.check(self._lib.rd_llm_set_gemm_prefetch(self._h, *self.gemm_prefetch), "set_gemm_prefetch")
 
     def set_qkv_partials(self, on: bool):
         """Single-token steps: the QKV GEMM leaves fp32 split-K partials for the attention kernel to sum (default), or reduces

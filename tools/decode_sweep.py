@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Decode-step time (CUDA graph + PDL, the bench configuration) of the full Vicuna-7B-sized engine under engine switches
-(development tool): QKV partials on/off x next-GEMM weight prefetch budgets.  python tools/decode_sweep.py [B] [NEW]"""
+(development tool): QKV partials on/off.  python tools/decode_sweep.py [B] [NEW]"""
 import json
 import os
 import sys
@@ -25,16 +25,10 @@ torch.cuda.empty_cache()
 prompts = synth.make_prompts(B, seed=4321).to(dev)
 img = torch.randn(B, 32, 768, device=dev) * 0.5
 MB = 1 << 20
-variants = [("partials=1 pf=default", True, None)]
-for spec in os.environ.get("PF", "0,0,0,0;34,64,48,64;34,96,64,96;34,32,24,32;0,64,0,64;34,0,48,0").split(";"):
-    variants.append((f"partials=1 pf={spec}", True, tuple(int(float(v) * MB) for v in spec.split(","))))
-variants.append(("partials=0 pf=0,0,0,0", False, (0, 0, 0, 0)))
-variants.append(("partials=0 pf=34,64,48,64", False, (34 * MB, 64 * MB, 48 * MB, 64 * MB)))
+variants = [("partials=1", True, None), ("partials=0", False, None), ("partials=1 (again)", True, None), ("partials=0 (again)", False, None)]
 res = []
 for name, part, pf in variants:
     llm.set_qkv_partials(part)
-    if pf is not None:
-        llm.set_gemm_prefetch(*pf)
     llm.generate(prompts, img_embeds=img, max_new_tokens=8, suppress_eos=True)
     best = 1e9
     for _ in range(2):
