@@ -14,11 +14,51 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
                const T* __restrict__ lora_a, int lora_rows, T* __restrict__ lora_t, const void* pf_ptr, long long pf_bytes) {
   pdl_launch_dependents();
   l2_prefetch_slice(pf_ptr, pf_bytes, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x);     // weights: no dependency on x
-  pdl_wait();
   extern __shared__ float srow[];      // H floats
   __shared__ float sred[8];
   const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T* xr = x + (int64_t)m * H;
+  if (H <= 8 * 256 * 4 && lora_a == nullptr) {
+    // rows of up to 8192 elements (Vicuna: 4096) stay in registers, and the norm weights - which do not depend on the previous
+    // kernel - are requested BEFORE the programmatic-launch wait: one global round trip after the wait instead of two
+    // (same per-thread element order and reduction tree as the general path below: bit-identical results)
+    Vec8<T> wv[4], xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int k = tid * 8 + u * 2048; if (k < H) wv[u] = ld16(w + k); }
+    pdl_wait();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int k = tid * 8 + u * 2048; if (k < H) xv[u] = ld16(xr + k); }
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (tid * 8 + u * 2048 < H) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float f = Tr<T>::f(xv[u].v[e]); ss = fmaf(f, f, ss); }
+      }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) sred[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += sred[i];
+    const float rs = 1.0f / sqrtf(tot / (float)H + eps);       // torch.rsqrt(variance + eps), fp32
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = tid * 8 + u * 2048;
+      if (k < H) {
+        Vec8<T> o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float y = Tr<T>::rr(Tr<T>::f(xv[u].v[e]) * rs);          // .to(weight.dtype)
+          o.v[e] = Tr<T>::r(Tr<T>::f(wv[u].v[e]) * y);                   // weight * hidden_states
+        }
+        *reinterpret_cast<uint4*>(out + (int64_t)m * H + k) = *reinterpret_cast<uint4*>(&o);
+      }
+    }
+    return;
+  }
+  pdl_wait();
   float ss = 0.f;
   for (int k = tid * 8; k < H; k += 256 * 8) {
     Vec8<T> v = ld16(xr + k);
