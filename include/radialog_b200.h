@@ -112,6 +112,11 @@ int rd_attention(const void* qkv_dev, int64_t ldq, const void* kcache_dev, const
                  const uint8_t* keymask_dev, const int32_t* ctx_len_dev, void* out_dev, int B, int q_len, int nh,
                  int hd, int cmax, int dtype, void* stream);
 
+/* q_len >= 4 launches whose keys fit one UMMA tile (ctx + q_len <= 256) run both contractions on the tcgen05 tensor cores
+ * (csrc/attention_prefill_tc.cu: S = Q.K^T and O = P.V as UMMA tiles, the rounding points above applied in the TMEM -> register
+ * pass between them); longer contexts use the SIMT kernels.  Test hook: 0 forces the SIMT kernels, 1 (default) restores. */
+int rd_attention_set_tensor_core(int on);
+
 /* Single-token decode: rd_rope_kv_store + rd_attention (q_len == 1) fused in one launch; pos_dev[B] are the position
  * ids of the new tokens, which are appended at cache slot ctx_len[0].  The KV sweep uses bulk asynchronous copies
  * (cp.async.bulk + mbarrier) through a shared-memory ring.  ctx_lower_bound: host-known lower bound of ctx_len[0]

@@ -59,6 +59,7 @@ SIGNATURES = {
     "rd_layernorm": (_i, [_p, _p, _p, _p, _i, _i, _f, _i, _p]),
     "rd_rope_kv_store": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _i, _p]),
     "rd_attention": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "rd_attention_set_tensor_core": (_i, [_i]),
     "rd_attention_decode": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _i, _p]),
     "rd_attention_decode_partials": (_i, [_p, _i, C.c_longlong, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _i, _p]),
     "rd_embed_splice": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),

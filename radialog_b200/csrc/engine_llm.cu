@@ -12,6 +12,7 @@ extern "C" int rd_attention_decode(const void*, int64_t, const int32_t*, const v
                                    const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
 extern "C" int rd_attention_decode_partials(const float*, int, long long, int64_t, const int32_t*, const void*, const void*, void*, void*,
                                             const uint8_t*, const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
+int rd_attention_bounded(const void*, int64_t, const void*, const void*, const uint8_t*, const int32_t*, int, void*, int, int, int, int, int, int, void*);
 extern "C" int rd_rmsnorm_prefetch(const void*, const void*, void*, int, int, float, const void*, long long, int, void*);
 extern "C" int rd_attention_decode_set_l2_prefetch(const void*, long long, const void*, long long);
 extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const int32_t*, int, int, int, int, void*);
@@ -386,7 +387,7 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
         RD_CHECK(rd_rope_kv_store(h->qkv, ldq, pos, h->ctx_len, h->cos, h->sin, kc, vc, B, q_len, nh, hd, c.max_ctx,
                                   c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st)); }
       { ProfScope ps(h, st, C_ATTN);
-        RD_CHECK(rd_attention(h->qkv, ldq, kc, vc, h->keymask, h->ctx_len, h->att, B, q_len, nh, hd, c.max_ctx, dt, st)); }
+        RD_CHECK(rd_attention_bounded(h->qkv, ldq, kc, vc, h->keymask, h->ctx_len, h->ctx_host, h->att, B, q_len, nh, hd, c.max_ctx, dt, st)); }
     }
     rd_epilogue eo{};
     eo.residual_dev = h->x; eo.ld_res = H; eo.res_mode = 1;

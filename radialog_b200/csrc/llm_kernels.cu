@@ -223,29 +223,17 @@ template <class T, int R>
 __global__ void __launch_bounds__(256)
 rope_kv_store_vec_kernel(T* __restrict__ qkv, int64_t ldq, const int32_t* __restrict__ pos, const int32_t* __restrict__ ctx_len,
                          const T* __restrict__ cos_t, const T* __restrict__ sin_t, T* __restrict__ kc, T* __restrict__ vc,
-                         int q_len, int nh, int cmax, const T* __restrict__ lora_b, float lora_scale) {
+                         int q_len, int nh, int cmax, const T* __restrict__ lora_b, float lora_scale, int M, int tokens_per_cta) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int HD = 128, HALF = 64;
-  const int m = blockIdx.x, b = m / q_len, i = m % q_len;
   const int H = nh * HD;
-  const int slot = ctx_len[0] + i;
-  const int p = pos[m];
-  T* row = qkv + (int64_t)m * ldq;
-  float tq[8], tv[8];
-  if (R == 8) {
-    const Vec8<T> a = ld16(row + 3 * H), bb = ld16(row + 3 * H + 8);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) { tq[r] = Tr<T>::f(a.v[r]); tv[r] = Tr<T>::f(bb.v[r]); }
-  }
+  const int ctx0 = ctx_len[0];
+  const int m_begin = blockIdx.x * tokens_per_cta, m_end = min(M, m_begin + tokens_per_cta);
   for (int it = threadIdx.x; it < nh * 8; it += blockDim.x) {
     const int h = it >> 3, d0 = (it & 7) * 8;
-    const Vec8<T> c_lo = ld16(cos_t + (int64_t)p * HD + d0), c_hi = ld16(cos_t + (int64_t)p * HD + d0 + HALF);
-    const Vec8<T> s_lo = ld16(sin_t + (int64_t)p * HD + d0), s_hi = ld16(sin_t + (int64_t)p * HD + d0 + HALF);
-    T* qp = row + h * HD + d0;
-    const T* kp = row + H + h * HD + d0;
-    const T* vp = row + 2 * H + h * HD + d0;
-    const Vec8<T> q_lo = ld16(qp), q_hi = ld16(qp + HALF), k_lo = ld16(kp), k_hi = ld16(kp + HALF), v_lo = ld16(vp), v_hi = ld16(vp + HALF);
+    // the 32 lora_B rows of this thread's (head, dim chunk) are loaded ONCE and reused for every token of the CTA's group
+    // (one CTA per token re-read all 128 KB of lora_B from L2 per token: 268 MB per layer at B x T = 2048)
     Vec8<T> bq_lo[R == 8 ? 8 : 1], bq_hi[R == 8 ? 8 : 1], bv_lo[R == 8 ? 8 : 1], bv_hi[R == 8 ? 8 : 1];
     if (R == 8) {
       const T* bq = lora_b + (int64_t)(h * HD + d0) * 8;
@@ -262,29 +250,47 @@ rope_kv_store_vec_kernel(T* __restrict__ qkv, int64_t ldq, const int32_t* __rest
       for (int r = 0; r < 8; ++r) sdot = fmaf(Tr<T>::f(brow.v[r]), t[r], sdot);
       return Tr<T>::rr(y + Tr<T>::rr(lora_scale * Tr<T>::rr(sdot)));
     };
-    Vec8<T> oq_lo, oq_hi, ok_lo, ok_hi, ov_lo, ov_hi;
+    for (int m = m_begin; m < m_end; ++m) {
+      const int b = m / q_len, i = m % q_len;
+      const int slot = ctx0 + i;
+      const int p = pos[m];
+      T* row = qkv + (int64_t)m * ldq;
+      float tq[8], tv[8];
+      if (R == 8) {
+        const Vec8<T> a = ld16(row + 3 * H), bb = ld16(row + 3 * H + 8);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float cl = Tr<T>::f(c_lo.v[e]), ch = Tr<T>::f(c_hi.v[e]), sl = Tr<T>::f(s_lo.v[e]), sh = Tr<T>::f(s_hi.v[e]);
-      float lo = Tr<T>::f(q_lo.v[e]), hi = Tr<T>::f(q_hi.v[e]);
-      if (R == 8) { lo = lora(lo, bq_lo[e], tq); hi = lora(hi, bq_hi[e], tq); }
-      oq_lo.v[e] = Tr<T>::r(Tr<T>::rr(lo * cl) + Tr<T>::rr(-hi * sl));       // q*cos + rotate_half(q)*sin
-      oq_hi.v[e] = Tr<T>::r(Tr<T>::rr(hi * ch) + Tr<T>::rr(lo * sh));
-      lo = Tr<T>::f(k_lo.v[e]); hi = Tr<T>::f(k_hi.v[e]);
-      ok_lo.v[e] = Tr<T>::r(Tr<T>::rr(lo * cl) + Tr<T>::rr(-hi * sl));
-      ok_hi.v[e] = Tr<T>::r(Tr<T>::rr(hi * ch) + Tr<T>::rr(lo * sh));
-      lo = Tr<T>::f(v_lo.v[e]); hi = Tr<T>::f(v_hi.v[e]);
-      if (R == 8) { lo = lora(lo, bv_lo[e], tv); hi = lora(hi, bv_hi[e], tv); }
-      ov_lo.v[e] = Tr<T>::r(lo);
-      ov_hi.v[e] = Tr<T>::r(hi);
+        for (int r = 0; r < 8; ++r) { tq[r] = Tr<T>::f(a.v[r]); tv[r] = Tr<T>::f(bb.v[r]); }
+      }
+      const Vec8<T> c_lo = ld16(cos_t + (int64_t)p * HD + d0), c_hi = ld16(cos_t + (int64_t)p * HD + d0 + HALF);
+      const Vec8<T> s_lo = ld16(sin_t + (int64_t)p * HD + d0), s_hi = ld16(sin_t + (int64_t)p * HD + d0 + HALF);
+      T* qp = row + h * HD + d0;
+      const T* kp = row + H + h * HD + d0;
+      const T* vp = row + 2 * H + h * HD + d0;
+      const Vec8<T> q_lo = ld16(qp), q_hi = ld16(qp + HALF), k_lo = ld16(kp), k_hi = ld16(kp + HALF), v_lo = ld16(vp), v_hi = ld16(vp + HALF);
+      Vec8<T> oq_lo, oq_hi, ok_lo, ok_hi, ov_lo, ov_hi;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float cl = Tr<T>::f(c_lo.v[e]), ch = Tr<T>::f(c_hi.v[e]), sl = Tr<T>::f(s_lo.v[e]), sh = Tr<T>::f(s_hi.v[e]);
+        float lo = Tr<T>::f(q_lo.v[e]), hi = Tr<T>::f(q_hi.v[e]);
+        if (R == 8) { lo = lora(lo, bq_lo[e], tq); hi = lora(hi, bq_hi[e], tq); }
+        oq_lo.v[e] = Tr<T>::r(Tr<T>::rr(lo * cl) + Tr<T>::rr(-hi * sl));       // q*cos + rotate_half(q)*sin
+        oq_hi.v[e] = Tr<T>::r(Tr<T>::rr(hi * ch) + Tr<T>::rr(lo * sh));
+        lo = Tr<T>::f(k_lo.v[e]); hi = Tr<T>::f(k_hi.v[e]);
+        ok_lo.v[e] = Tr<T>::r(Tr<T>::rr(lo * cl) + Tr<T>::rr(-hi * sl));
+        ok_hi.v[e] = Tr<T>::r(Tr<T>::rr(hi * ch) + Tr<T>::rr(lo * sh));
+        lo = Tr<T>::f(v_lo.v[e]); hi = Tr<T>::f(v_hi.v[e]);
+        if (R == 8) { lo = lora(lo, bv_lo[e], tv); hi = lora(hi, bv_hi[e], tv); }
+        ov_lo.v[e] = Tr<T>::r(lo);
+        ov_hi.v[e] = Tr<T>::r(hi);
+      }
+      const int64_t cache_off = (((int64_t)b * nh + h) * cmax + slot) * HD + d0;
+      *reinterpret_cast<uint4*>(qp) = *reinterpret_cast<const uint4*>(&oq_lo);
+      *reinterpret_cast<uint4*>(qp + HALF) = *reinterpret_cast<const uint4*>(&oq_hi);
+      *reinterpret_cast<uint4*>(kc + cache_off) = *reinterpret_cast<const uint4*>(&ok_lo);
+      *reinterpret_cast<uint4*>(kc + cache_off + HALF) = *reinterpret_cast<const uint4*>(&ok_hi);
+      *reinterpret_cast<uint4*>(vc + cache_off) = *reinterpret_cast<const uint4*>(&ov_lo);
+      *reinterpret_cast<uint4*>(vc + cache_off + HALF) = *reinterpret_cast<const uint4*>(&ov_hi);
     }
-    const int64_t cache_off = (((int64_t)b * nh + h) * cmax + slot) * HD + d0;
-    *reinterpret_cast<uint4*>(qp) = *reinterpret_cast<const uint4*>(&oq_lo);
-    *reinterpret_cast<uint4*>(qp + HALF) = *reinterpret_cast<const uint4*>(&oq_hi);
-    *reinterpret_cast<uint4*>(kc + cache_off) = *reinterpret_cast<const uint4*>(&ok_lo);
-    *reinterpret_cast<uint4*>(kc + cache_off + HALF) = *reinterpret_cast<const uint4*>(&ok_hi);
-    *reinterpret_cast<uint4*>(vc + cache_off) = *reinterpret_cast<const uint4*>(&ov_lo);
-    *reinterpret_cast<uint4*>(vc + cache_off + HALF) = *reinterpret_cast<const uint4*>(&ov_hi);
   }
 }
 
@@ -297,14 +303,19 @@ extern "C" int rd_rope_kv_store(void* qkv, int64_t ldq, const int32_t* pos, cons
   RD_DISPATCH_DTYPE(dtype, T, {
     const int lr = lora_b ? lora_r : 0;
     if (hd == 128 && (lr == 0 || lr == 8) && ldq % 8 == 0) {
+      // token groups: ~2 CTAs per SM when there are enough tokens, never more than 8 tokens (a serial chain) per CTA
+      const int M = B * q_len;
+      int tpc = (M + 295) / 296;
+      tpc = tpc < 1 ? 1 : (tpc > 8 ? 8 : tpc);
+      const int grid = (M + tpc - 1) / tpc;
       if (lr == 8) {
-        RD_CHECK_CUDA(rd_launch(rope_kv_store_vec_kernel<T, 8>, dim3(B * q_len), dim3(256), 0, (cudaStream_t)stream, rd_pdl_enabled(),
+        RD_CHECK_CUDA(rd_launch(rope_kv_store_vec_kernel<T, 8>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, rd_pdl_enabled(),
                                 (T*)qkv, ldq, pos, ctx_len, (const T*)cos_t, (const T*)sin_t, (T*)kc, (T*)vc, q_len, nh, cmax,
-                                (const T*)lora_b, lora_scale));
+                                (const T*)lora_b, lora_scale, M, tpc));
       } else {
-        RD_CHECK_CUDA(rd_launch(rope_kv_store_vec_kernel<T, 0>, dim3(B * q_len), dim3(256), 0, (cudaStream_t)stream, rd_pdl_enabled(),
+        RD_CHECK_CUDA(rd_launch(rope_kv_store_vec_kernel<T, 0>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, rd_pdl_enabled(),
                                 (T*)qkv, ldq, pos, ctx_len, (const T*)cos_t, (const T*)sin_t, (T*)kc, (T*)vc, q_len, nh, cmax,
-                                (const T*)lora_b, lora_scale));
+                                (const T*)lora_b, lora_scale, M, tpc));
       }
       return RD_OK;
     }
@@ -623,11 +634,20 @@ attention_prefill_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __rest
   }
 }
 
-extern "C" int rd_attention(const void* qkv, int64_t ldq, const void* kc, const void* vc, const uint8_t* keymask,
-                            const int32_t* ctx_len, void* out, int B, int q_len, int nh, int hd, int cmax, int dtype,
-                            void* stream) {
+int rd_attention_prefill_tc(const void* qkv, int64_t ldq, const void* kc, const void* vc, const uint8_t* keymask, const int32_t* ctx_len,
+                            int ctx_upper_bound, void* out, int B, int q_len, int nh, int cmax, int dtype, cudaStream_t st);
+
+// ctx_upper_bound: host-known upper bound of ctx_len[0] (-1 = unknown: the cache capacity is assumed); it sizes the shared
+// memory / TMEM of the tensor-core kernel, which serves every q_len >= 4 launch whose keys fit one UMMA tile (<= 256).
+int rd_attention_bounded(const void* qkv, int64_t ldq, const void* kc, const void* vc, const uint8_t* keymask,
+                         const int32_t* ctx_len, int ctx_upper_bound, void* out, int B, int q_len, int nh, int hd, int cmax, int dtype,
+                         void* stream) {
   RD_REQUIRE(hd == 128, "rd_attention: head_dim must be 128 (Vicuna-7B); got %d", hd);
   RD_REQUIRE(B > 0 && q_len > 0 && cmax > 0 && cmax * 4 <= 160 * 1024, "rd_attention: bad shape");
+  if (q_len >= 4) {
+    const int r = rd_attention_prefill_tc(qkv, ldq, kc, vc, keymask, ctx_len, ctx_upper_bound, out, B, q_len, nh, cmax, dtype, (cudaStream_t)stream);
+    if (r != 0) return r < 0 ? r : RD_OK;
+  }
   // several query rows per (sequence, head) and a cache that fits shared memory: K / V staged once per CTA
   const size_t atp_smem = (size_t)cmax * 128 * 2 * 2 + (size_t)ATP_WARPS * cmax * 4;
   if (q_len >= 4 && atp_smem <= 200 * 1024) {
@@ -645,6 +665,12 @@ extern "C" int rd_attention(const void* qkv, int64_t ldq, const void* kc, const 
                             (const int32_t*)nullptr, (const T*)nullptr, (const T*)nullptr));
     return RD_OK;
   });
+}
+
+extern "C" int rd_attention(const void* qkv, int64_t ldq, const void* kc, const void* vc, const uint8_t* keymask,
+                            const int32_t* ctx_len, void* out, int B, int q_len, int nh, int hd, int cmax, int dtype,
+                            void* stream) {
+  return rd_attention_bounded(qkv, ldq, kc, vc, keymask, ctx_len, -1, out, B, q_len, nh, hd, cmax, dtype, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
