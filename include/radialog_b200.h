@@ -224,6 +224,11 @@ int rd_llm_decode_step(rd_llm* h, void* stream);
  * finished flags (1 = row has emitted EOS), last-step logits [B, vocab].                                                                */
 int rd_llm_state(rd_llm* h, const int64_t** gen_tokens_dev, const int32_t** finished_dev,
                  const void** last_logits_dev, const void** hidden_dev, int* n_generated_host);
+/* Beam search (generate(num_beams=k), test.py:467,629): LlamaForCausalLM._reorder_cache (modeling_llama_imgemb.py:838-843) on the
+ * flat KV cache - cache row r of every layer becomes cache row beam_idx_dev[r] (int32[B]).  Call outside stream capture and
+ * discard captured decode graphs afterwards (the cache buffers are swapped).  Pair it with rd_llm_force_tokens to feed the
+ * tokens the beam scorer selected.                                                                                          */
+int rd_llm_reorder_cache(rd_llm* h, const int32_t* beam_idx_dev, void* stream);
 /* Teacher forcing for parity tests: the next rd_llm_decode_step consumes toks_dev[B] (int64) instead of the engine's own
  * greedy choice, which stays in the generation record.  Mirrors feeding the reference's `input_ids[:, -1:]`
  * (prepare_inputs_for_generation, modeling_llama_imgemb.py:799-801) with an externally chosen token.               */

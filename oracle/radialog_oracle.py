@@ -232,6 +232,153 @@ class LlamaOracle:
         return (ids, scores) if return_scores else ids
 
 
+def llama_beam_search(orc: "LlamaOracle", input_ids: torch.Tensor, img_embeds: Optional[torch.Tensor], max_new_tokens: int,
+                      num_beams: int, length_penalty: float = 1.0, early_stopping=False, length_norm: str = "full"):
+    """generate(num_beams=k) over the oracle model: the cache rows follow ``_reorder_cache`` (index_select on dim 0).
+    Image rows are expanded with the prompts (the reference's own ``dicom`` list is NOT expanded by HF and its forward then
+    fails on the shape mismatch - SURVEY.md 8f row 4; text-only prompts are the reference's working case)."""
+    cfg = orc.cfg
+    state = {"past": None, "mask": None}
+    img = None if img_embeds is None else img_embeds.repeat_interleave(num_beams, dim=0)
+
+    def step(ids, beam_idx):
+        if state["past"] is None:
+            mask = ids.ne(cfg.pad_token_id).long()
+            logits, past = orc.forward(ids, mask, orc.positions_from_mask(mask), None, img)
+        else:
+            past = [(k.index_select(0, beam_idx), v.index_select(0, beam_idx)) for k, v in state["past"]]
+            mask = torch.cat([state["mask"], state["mask"].new_ones((ids.shape[0], 1))], dim=-1)
+            pos = orc.positions_from_mask(mask)
+            logits, past = orc.forward(ids[:, -1:], mask, pos[:, -1:], past, None)
+        state["past"], state["mask"] = past, mask
+        return logits[:, -1, :]
+
+    return beam_search(step, input_ids, num_beams, input_ids.shape[1] + max_new_tokens, cfg.pad_token_id, cfg.eos_token_id,
+                       length_penalty, early_stopping, length_norm)
+
+
+# ======================================================================================
+# Beam search (transformers==4.28.1 GenerationMixin.beam_search + BeamSearchScorer, third-party, restated;
+# reached through generate(num_beams=...) at test.py:467,629; cache reordering = _reorder_cache,
+# modeling_llama_imgemb.py:838-843)
+# ======================================================================================
+
+class _BeamHypotheses:
+    """transformers 4.28.1 generation/beam_search.py BeamHypotheses (n-best list of finished hypotheses of one batch item)."""
+
+    def __init__(self, num_beams: int, length_penalty: float, early_stopping, max_length: Optional[int], prompt_len: int = 0):
+        self.length_penalty, self.early_stopping, self.max_length, self.num_beams = length_penalty, early_stopping, max_length, num_beams
+        self.beams: List[Tuple[float, torch.Tensor]] = []
+        self.worst_score = 1e9
+        # 4.28.1 (the reference's pin) normalises by the FULL hypothesis length, prompt included; later transformers releases
+        # normalise by the generated length only.  prompt_len > 0 selects the later rule - used ONLY to check this restatement
+        # against the transformers build installed here (oracle/make_golden_beam.py); 0 = the reference's behaviour.
+        self.prompt_len = prompt_len
+
+    def add(self, hyp: torch.Tensor, sum_logprobs: float, eos_counts: bool = False):
+        # (the later rule also counts the EOS token of a finished hypothesis; 4.28.1 stores and measures the hypothesis without it)
+        n = hyp.shape[-1] - self.prompt_len + (1 if (eos_counts and self.prompt_len) else 0)
+        score = sum_logprobs / (n ** self.length_penalty)
+        if len(self.beams) < self.num_beams or score > self.worst_score:
+            self.beams.append((score, hyp))
+            if len(self.beams) > self.num_beams:
+                order = sorted([(sc, idx) for idx, (sc, _) in enumerate(self.beams)])
+                del self.beams[order[0][1]]
+                self.worst_score = order[1][0]
+            else:
+                self.worst_score = min(score, self.worst_score)
+
+    def is_done(self, best_sum_logprobs: float, cur_len: int) -> bool:
+        if len(self.beams) < self.num_beams:
+            return False
+        if self.early_stopping is True:
+            return True
+        if self.early_stopping is False:
+            return self.worst_score >= best_sum_logprobs / (cur_len - self.prompt_len) ** self.length_penalty
+        if self.length_penalty > 0.0:            # "never"
+            return self.worst_score >= best_sum_logprobs / (self.max_length - self.prompt_len) ** self.length_penalty
+        return self.worst_score >= best_sum_logprobs / (cur_len - self.prompt_len) ** self.length_penalty
+
+
+def beam_search(step_logits, input_ids: torch.Tensor, num_beams: int, max_length: int, pad_token_id: int, eos_token_id: int,
+                length_penalty: float = 1.0, early_stopping=False, length_norm: str = "full"):
+    """GenerationMixin.beam_search of transformers 4.28.1 (num_return_sequences = 1, no logits processors), restated.
+
+    ``step_logits(input_ids [B*nb, L], beam_idx or None) -> logits [B*nb, V]`` runs the model on the last position (the whole
+    prompt on the first call) after reordering its cache rows by ``beam_idx`` (``_reorder_cache``).  ``input_ids`` is the
+    UN-expanded prompt [B, T].  Returns (sequences [B, <= max_length], sequence_scores [B])."""
+    B = input_ids.shape[0]
+    ids = input_ids.repeat_interleave(num_beams, dim=0)                       # _expand_inputs_for_generation
+    assert length_norm in ("full", "generated")
+    plen = input_ids.shape[1] if length_norm == "generated" else 0
+    hyps = [_BeamHypotheses(num_beams, length_penalty, early_stopping, max_length, plen) for _ in range(B)]
+    done = [False] * B
+    beam_scores = torch.zeros((B, num_beams), dtype=torch.float)
+    beam_scores[:, 1:] = -1e9
+    beam_scores = beam_scores.view(-1)
+    beam_idx = None
+    while True:
+        logits = step_logits(ids, beam_idx)
+        scores = F.log_softmax(logits, dim=-1)                                 # in the logits dtype, like HF
+        scores = scores.cpu() + beam_scores[:, None]                           # fp32 by type promotion
+        V = scores.shape[-1]
+        top_scores, top_tokens = torch.topk(scores.view(B, num_beams * V), 2 * num_beams, dim=1, largest=True, sorted=True)
+        top_idx = torch.div(top_tokens, V, rounding_mode="floor")
+        top_tokens = top_tokens % V
+        # ---- BeamSearchScorer.process -------------------------------------------------------------------------------
+        cur_len = ids.shape[-1]
+        nxt_scores = torch.zeros((B, num_beams), dtype=top_scores.dtype)
+        nxt_tokens = torch.zeros((B, num_beams), dtype=top_tokens.dtype)
+        nxt_idx = torch.zeros((B, num_beams), dtype=top_idx.dtype)
+        ids_cpu = ids.cpu()
+        for b in range(B):
+            if done[b]:
+                nxt_scores[b, :], nxt_tokens[b, :], nxt_idx[b, :] = 0, pad_token_id, 0
+                continue
+            k = 0
+            for rank in range(2 * num_beams):
+                tok, sc, idx = int(top_tokens[b, rank]), top_scores[b, rank], int(top_idx[b, rank])
+                row = b * num_beams + idx
+                if tok == eos_token_id:
+                    if rank >= num_beams:
+                        continue
+                    hyps[b].add(ids_cpu[row].clone(), float(sc), eos_counts=True)
+                else:
+                    nxt_scores[b, k], nxt_tokens[b, k], nxt_idx[b, k] = sc, tok, row
+                    k += 1
+                if k == num_beams:
+                    break
+            if k < num_beams:
+                raise ValueError(f"At most {num_beams} tokens in the top {2 * num_beams} can be equal to `eos_token_id`")
+            # 4.28.1 passes the length BEFORE this step's token is appended; the generated-length rule of later releases counts it
+            done[b] = done[b] or hyps[b].is_done(float(top_scores[b].max()), cur_len + (1 if plen else 0))
+        beam_scores, beam_tokens, beam_idx = nxt_scores.view(-1), nxt_tokens.view(-1), nxt_idx.view(-1)
+        ids = torch.cat([ids_cpu[beam_idx, :], beam_tokens[:, None]], dim=-1).to(ids.device)
+        if all(done) or ids.shape[-1] >= max_length:
+            break
+    # ---- BeamSearchScorer.finalize -----------------------------------------------------------------------------------
+    ids_cpu = ids.cpu()
+    for b in range(B):
+        if done[b]:
+            continue
+        for k in range(num_beams):
+            hyps[b].add(ids_cpu[b * num_beams + k], float(beam_scores[b * num_beams + k]))
+    best, best_scores = [], torch.zeros(B, dtype=torch.float32)
+    for b in range(B):
+        sc, hyp = sorted(hyps[b].beams, key=lambda x: x[0]).pop()
+        best.append(hyp)
+        best_scores[b] = sc
+    lens = [len(x) for x in best]
+    sent_max_len = min(max(lens) + 1, max_length)
+    decoded = torch.full((B, sent_max_len), pad_token_id, dtype=ids_cpu.dtype) if min(lens) != max(lens) else \
+        torch.zeros((B, sent_max_len), dtype=ids_cpu.dtype)
+    for b, hyp in enumerate(best):
+        decoded[b, : lens[b]] = hyp
+        if lens[b] < sent_max_len:
+            decoded[b, lens[b]] = eos_token_id
+    return decoded, best_scores
+
+
 # ======================================================================================
 # Vision trunk + projector (biovil_t/*, torchvision ResNet-50 v1.5)
 # ======================================================================================

@@ -78,6 +78,7 @@ SIGNATURES = {
     "rd_llm_decode_step": (_i, [_p, _p]),
     "rd_llm_note_replayed_steps": (_i, [_p, _i]),
     "rd_llm_state": (_i, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_i)]),
+    "rd_llm_reorder_cache": (_i, [_p, _p, _p]),
     "rd_llm_force_tokens": (_i, [_p, _p, _p]),
     "rd_llm_done_flag": (_i, [_p, C.POINTER(_p)]),
     "rd_llm_profile": (_i, [_p, _i]),

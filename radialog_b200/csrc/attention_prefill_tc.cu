@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t sw128(int r, int chunk) {
 }
 
 template <class T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 attention_prefill_tc_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __restrict__ kc, const T* __restrict__ vc,
                             const uint8_t* __restrict__ keymask, const int32_t* __restrict__ ctx_len_p, T* __restrict__ out,
                             int q_len, int nh, int cmax, int tmem_cols) {
@@ -44,6 +44,7 @@ attention_prefill_tc_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __r
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_ptr;
   __shared__ int s_first;
+  __shared__ float s_pad[256];                      // additive padding mask per key: 0 or finfo.min (_expand_mask)
 
   const int h = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * QT;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -89,6 +90,7 @@ attention_prefill_tc_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __r
     int first = 0x7fffffff;
     for (int j = tid; j < c_tot; j += 128)
       if (km[j]) { first = j; break; }
+    for (int j = tid; j < keys_pad; j += 128) s_pad[j] = (j < c_tot && km[j]) ? 0.f : Tr<T>::lowest();
     __syncthreads();                                                   // s_first initialised
     if (first != 0x7fffffff) atomicMin(&s_first, first);
   }
@@ -115,12 +117,25 @@ attention_prefill_tc_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __r
 
   // ---- while the first UMMA runs: V^T into shared memory.  A thread takes 8 consecutive keys of one head dim (one 16-byte
   // ---- chunk of the K-major block); a warp covers 32 consecutive dims, so every global load instruction reads 64 contiguous bytes
-  for (int idx = tid; idx < (keys_pad >> 3) * HD; idx += 128) {
-    const int d = idx & (HD - 1), j0 = (idx >> 7) << 3;
-    Vec8<T> v8;
+  {
+    const int d = tid;                                                 // HD == blockDim.x == 128
+    for (int jb = 0; jb < keys_pad; jb += 32) {                        // 4 chunks = 32 independent 2-byte loads in flight
+      Vec8<T> v8[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v8.v[e] = (j0 + e < c_tot) ? vbase[(size_t)(j0 + e) * HD + d] : Tr<T>::r(0.f);
-    *reinterpret_cast<uint4*>(sV + (j0 >> 6) * TILE_BYTES + sw128(d, (j0 & 63) >> 3)) = *reinterpret_cast<const uint4*>(&v8);
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = jb + u * 8 + e;
+          v8[u].v[e] = (j < c_tot) ? vbase[(size_t)j * HD + d] : Tr<T>::r(0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j0 = jb + u * 8;
+        if (j0 < keys_pad)
+          *reinterpret_cast<uint4*>(sV + (j0 >> 6) * TILE_BYTES + sw128(d, (j0 & 63) >> 3)) = *reinterpret_cast<const uint4*>(&v8[u]);
+      }
+    }
   }
 
   // ---- scores -> probabilities, one query row per thread ------------------------------------------------------------------------
@@ -132,51 +147,55 @@ attention_prefill_tc_kernel(const T* __restrict__ qkv, int64_t ldq, const T* __r
   const bool row_ok = tid < q_valid;
   const bool any = first <= jcausal;
   const int jend = row_ok ? (any ? (jcausal + 1) : c_tot) : 0;
-  const uint8_t* km = keymask + (int64_t)b * cmax;
   const float lowest = Tr<T>::lowest();
   const float sqrt_d = 11.313708498984761f;                            // math.sqrt(128)
   const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
   auto score = [&](float acc, int j) {
     float s = Tr<T>::rr(acc);                                          // matmul output in the storage dtype
     s = Tr<T>::rr(s / sqrt_d);                                         // / math.sqrt(head_dim)
-    float madd = km[j] ? 0.f : lowest;                                 // _expand_mask
+    float madd = s_pad[j];                                             // _expand_mask
     if (j > jcausal) madd = Tr<T>::rr(madd + lowest);                  // + _make_causal_mask (may be -inf)
     s = Tr<T>::rr(s + madd);
     return fmaxf(s, lowest);                                           // torch.max(attn_weights, finfo.min)
   };
+  // Pass 1 reads the accumulator row from TMEM, applies the rounding chain once and parks the (storage-dtype exact) scores in
+  // this thread's own row of the P block - the K operand's shared memory, free now that the first UMMA has completed; passes
+  // 2 and 3 work from there.  A thread only ever touches its own row, so no barrier is needed between the passes.
+  __syncthreads();            // every thread is past the first UMMA's completion: the K block may be overwritten
   float mx = -INFINITY;
-  for (int c = 0; c < keys_pad; c += 16) {                             // pass 1: row maximum
+  for (int c = 0; c < keys_pad; c += 16) {                             // pass 1: scores + row maximum
     uint32_t r[16];
     tc_ld16(taddr + c, r);
     tc_wait_ld();
-#pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (c + e < jend) mx = fmaxf(mx, score(__uint_as_float(r[e]), c + e));
-  }
-  float sum = 0.f;
-  for (int c = 0; c < keys_pad; c += 16) {                             // pass 2: denominator
-    uint32_t r[16];
-    tc_ld16(taddr + c, r);
-    tc_wait_ld();
-#pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (c + e < jend) sum += expf(score(__uint_as_float(r[e]), c + e) - mx);
-  }
-  __syncthreads();            // every thread is past the first UMMA's completion: the K block may be overwritten by P
-  for (int c = 0; c < keys_pad; c += 16) {                             // pass 3: p = T(exp / sum) -> A operand of the second UMMA
-    uint32_t r[16];
-    tc_ld16(taddr + c, r);
-    tc_wait_ld();
-    Vec8<T> p16[2];
+    Vec8<T> s16[2];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-      float pv = 0.f;
-      if (c + e < jend) pv = expf(score(__uint_as_float(r[e]), c + e) - mx) / sum;
-      p16[e >> 3].v[e & 7] = Tr<T>::r(pv);                             // softmax(fp32).to(dtype)
+      float sv = lowest;
+      if (c + e < jend) { sv = score(__uint_as_float(r[e]), c + e); mx = fmaxf(mx, sv); }
+      s16[e >> 3].v[e & 7] = Tr<T>::r(sv);
     }
     uint8_t* blk = sKP + (c >> 6) * TILE_BYTES;
-    *reinterpret_cast<uint4*>(blk + sw128(tid, (c & 63) >> 3)) = *reinterpret_cast<const uint4*>(&p16[0]);
-    *reinterpret_cast<uint4*>(blk + sw128(tid, ((c & 63) >> 3) + 1)) = *reinterpret_cast<const uint4*>(&p16[1]);
+    *reinterpret_cast<uint4*>(blk + sw128(tid, (c & 63) >> 3)) = *reinterpret_cast<const uint4*>(&s16[0]);
+    *reinterpret_cast<uint4*>(blk + sw128(tid, ((c & 63) >> 3) + 1)) = *reinterpret_cast<const uint4*>(&s16[1]);
+  }
+  float sum = 0.f;
+  for (int c = 0; c < keys_pad; c += 8) {                              // pass 2: denominator
+    const Vec8<T> s8 = *reinterpret_cast<const Vec8<T>*>(sKP + (c >> 6) * TILE_BYTES + sw128(tid, (c & 63) >> 3));
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (c + e < jend) sum += expf(Tr<T>::f(s8.v[e]) - mx);
+  }
+  for (int c = 0; c < keys_pad; c += 8) {                              // pass 3: p = T(exp / sum) -> A operand of the second UMMA
+    uint4* slot = reinterpret_cast<uint4*>(sKP + (c >> 6) * TILE_BYTES + sw128(tid, (c & 63) >> 3));
+    const Vec8<T> s8 = *reinterpret_cast<const Vec8<T>*>(slot);
+    Vec8<T> p8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float pv = 0.f;
+      if (c + e < jend) pv = expf(Tr<T>::f(s8.v[e]) - mx) / sum;
+      p8.v[e] = Tr<T>::r(pv);                                          // softmax(fp32).to(dtype)
+    }
+    *slot = *reinterpret_cast<const uint4*>(&p8);
   }
   fence_proxy_async_smem();
   tc_fence_before();

@@ -13,6 +13,7 @@ extern "C" int rd_attention_decode(const void*, int64_t, const int32_t*, const v
 extern "C" int rd_attention_decode_partials(const float*, int, long long, int64_t, const int32_t*, const void*, const void*, void*, void*,
                                             const uint8_t*, const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
 int rd_attention_bounded(const void*, int64_t, const void*, const void*, const uint8_t*, const int32_t*, int, void*, int, int, int, int, int, int, void*);
+int rd_kv_reorder(const void*, const void*, void*, void*, const int32_t*, const int32_t*, int, int, int, int, int, int64_t, int, void*);
 extern "C" int rd_rmsnorm_prefetch(const void*, const void*, void*, int, int, float, const void*, long long, int, void*);
 extern "C" int rd_attention_decode_set_l2_prefetch(const void*, long long, const void*, long long);
 extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const int32_t*, int, int, int, int, void*);
@@ -65,6 +66,7 @@ struct rd_llm {
        *img = nullptr, *lora_t = nullptr, *ws = nullptr;
   int64_t ws_bytes = 0;
   char *kc = nullptr, *vc = nullptr;     // [layers][B, nh, cmax, hd]
+  char *kc_alt = nullptr, *vc_alt = nullptr;   // second cache, allocated on the first rd_llm_reorder_cache (beam search only)
   int64_t kv_layer_bytes = 0;
   uint8_t* keymask = nullptr;
   int32_t *pos = nullptr, *pos_cur = nullptr, *npos = nullptr, *finished = nullptr, *ctx_len = nullptr, *n_gen = nullptr;
@@ -146,6 +148,8 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
   rd_sk_destroy(h->sk);
   if (h->ssq) cudaFree(h->ssq);
   if (h->qkv_part) cudaFree(h->qkv_part);
+  if (h->kc_alt) cudaFree(h->kc_alt);
+  if (h->vc_alt) cudaFree(h->vc_alt);
   delete h;
 }
 
@@ -576,6 +580,27 @@ extern "C" int rd_llm_state(rd_llm* h, const int64_t** gen, const int32_t** fini
   if (last_logits) *last_logits = h->logits;
   if (hidden) *hidden = h->x;
   if (n_generated) *n_generated = h->n_generated;
+  return RD_OK;
+}
+
+// Beam search: LlamaForCausalLM._reorder_cache (modeling_llama_imgemb.py:838-843): cache row r <- cache row beam_idx[r] for every
+// layer (gather into a second buffer, then the two are swapped).  Beams of one batch item share prompt, padding and length, so
+// the per-row mask / position state needs no reordering.  Eager only: call it outside stream capture (it may allocate), and
+// drop any captured decode graph afterwards (the cache pointers change).
+extern "C" int rd_llm_reorder_cache(rd_llm* h, const int32_t* beam_idx_dev, void* stream) {
+  RD_REQUIRE(h && beam_idx_dev && h->B > 0, "rd_llm_reorder_cache: no generation in flight");
+  RD_REQUIRE(h->mega == nullptr, "rd_llm_reorder_cache: not available with the persistent decode kernel (its tables hold the cache pointers)");
+  const rd_llm_config& c = h->c;
+  const int64_t bytes = h->kv_layer_bytes * c.layers;
+  if (h->kc_alt == nullptr) {
+    RD_CHECK_CUDA(cudaMalloc((void**)&h->kc_alt, (size_t)bytes));
+    RD_CHECK_CUDA(cudaMalloc((void**)&h->vc_alt, (size_t)bytes));
+  }
+  RD_CHECK(rd_kv_reorder(h->kc, h->vc, h->kc_alt, h->vc_alt, beam_idx_dev, h->ctx_len, h->B, c.heads, c.max_ctx, c.hidden / c.heads, c.layers,
+                         h->kv_layer_bytes / 2, c.dtype, stream));
+  h->launches++;
+  std::swap(h->kc, h->kc_alt);
+  std::swap(h->vc, h->vc_alt);
   return RD_OK;
 }
 

@@ -827,3 +827,36 @@ extern "C" int rd_argmax_step(const void* logits, int64_t ld, int V, int64_t* cu
     return RD_OK;
   });
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Beam search: LlamaForCausalLM._reorder_cache (modeling_llama_imgemb.py:838-843) on the flat KV cache
+// new_cache[row r] = old_cache[beam_idx[r]] for every layer; only the ctx_len[0] cached tokens are moved.
+// grid (heads, rows, layers); src and dst are distinct buffers (the engine swaps them afterwards).
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+kv_reorder_kernel(const T* __restrict__ src_k, const T* __restrict__ src_v, T* __restrict__ dst_k, T* __restrict__ dst_v,
+                  const int32_t* __restrict__ beam_idx, const int32_t* __restrict__ ctx_len, int nh, int cmax, int hd,
+                  int64_t layer_elems) {
+  const int h = blockIdx.x, r = blockIdx.y, l = blockIdx.z;
+  const int src = beam_idx[r];
+  const int64_t n16 = (int64_t)ctx_len[0] * hd * (int64_t)sizeof(T) / 16;
+  const int64_t so = (int64_t)l * layer_elems + ((int64_t)src * nh + h) * cmax * hd;
+  const int64_t dof = (int64_t)l * layer_elems + ((int64_t)r * nh + h) * cmax * hd;
+  const uint4* sk = reinterpret_cast<const uint4*>(src_k + so);
+  const uint4* sv = reinterpret_cast<const uint4*>(src_v + so);
+  uint4* dk = reinterpret_cast<uint4*>(dst_k + dof);
+  uint4* dv = reinterpret_cast<uint4*>(dst_v + dof);
+  for (int64_t i = threadIdx.x; i < n16; i += blockDim.x) { dk[i] = sk[i]; dv[i] = sv[i]; }
+}
+
+int rd_kv_reorder(const void* src_k, const void* src_v, void* dst_k, void* dst_v, const int32_t* beam_idx, const int32_t* ctx_len,
+                  int rows, int nh, int cmax, int hd, int layers, int64_t layer_elems, int dtype, void* stream) {
+  RD_REQUIRE(rows > 0 && layers > 0 && (hd * 2) % 16 == 0, "rd_kv_reorder: bad shape");
+  RD_DISPATCH_DTYPE(dtype, T, {
+    RD_CHECK_CUDA(rd_launch(kv_reorder_kernel<T>, dim3(nh, rows, layers), dim3(256), 0, (cudaStream_t)stream, false, (const T*)src_k,
+                            (const T*)src_v, (T*)dst_k, (T*)dst_v, beam_idx, ctx_len, nh, cmax, hd, layer_elems));
+    return RD_OK;
+  });
+}

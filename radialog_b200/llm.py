@@ -51,6 +51,44 @@ class GreedySearchDecoderOnlyOutput:
     scores: Optional[Tuple[torch.Tensor, ...]] = None
 
 
+@dataclass
+class BeamSearchDecoderOnlyOutput:
+    """``generate(num_beams=k, return_dict_in_generate=True)``: best hypothesis per row, its length-normalised score, and (with
+    ``output_scores``) the per-step log-probabilities of all B*k beams."""
+    sequences: torch.Tensor
+    sequences_scores: Optional[torch.Tensor] = None
+    scores: Optional[Tuple[torch.Tensor, ...]] = None
+
+
+class _BeamHypotheses:
+    """n-best list of finished hypotheses of one batch item (transformers 4.28.1 ``BeamHypotheses``: score = sum of log-probs /
+    len(hypothesis, prompt included) ** length_penalty; ``is_done`` compares the worst kept score with the best still attainable)."""
+
+    def __init__(self, num_beams, length_penalty, early_stopping, max_length):
+        self.num_beams, self.length_penalty, self.early_stopping, self.max_length = num_beams, length_penalty, early_stopping, max_length
+        self.beams: List[Tuple[float, torch.Tensor]] = []
+        self.worst_score = 1e9
+
+    def add(self, hyp: torch.Tensor, sum_logprobs: float):
+        score = sum_logprobs / (hyp.shape[-1] ** self.length_penalty)
+        if len(self.beams) < self.num_beams or score > self.worst_score:
+            self.beams.append((score, hyp))
+            if len(self.beams) > self.num_beams:
+                ranked = sorted((s, i) for i, (s, _) in enumerate(self.beams))
+                del self.beams[ranked[0][1]]
+                self.worst_score = ranked[1][0]
+            else:
+                self.worst_score = min(score, self.worst_score)
+
+    def is_done(self, best_sum_logprobs: float, cur_len: int) -> bool:
+        if len(self.beams) < self.num_beams:
+            return False
+        if self.early_stopping is True:
+            return True
+        ref_len = self.max_length if (self.early_stopping not in (True, False) and self.length_penalty > 0.0) else cur_len
+        return self.worst_score >= best_sum_logprobs / ref_len ** self.length_penalty
+
+
 def rope_tables(head_dim: int, max_pos: int, base: float = 10000.0):
     """LlamaRotaryEmbedding.__init__ (modeling_llama_imgemb.py:97-109): fp32 tables built on the host."""
     inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2).float() / head_dim))
@@ -530,7 +568,109 @@ class LlamaForCausalLM:
 
     def _beam_search(self, ids, img_embeds, num_beams, max_new_tokens, return_dict_in_generate, output_scores, length_penalty,
                      early_stopping):
-        raise NotImplementedError("beam search is not built yet (SURVEY.md section 8f row 4)")
+        """``generate(num_beams=k)`` (test.py:467,629): transformers 4.28.1 ``beam_search`` + ``BeamSearchScorer`` semantics
+        (num_return_sequences = 1, no logits processors).  The model forward, the cache reordering (``_reorder_cache``,
+        modeling_llama_imgemb.py:838-843 -> ``rd_llm_reorder_cache``) and the token hand-over run in the native engine; the
+        scorer's bookkeeping over the 2k candidates per row is host logic like in transformers.  Image rows are expanded with
+        the prompts (the reference's ``dicom`` list is not expanded by transformers, so its own forward fails for k > 1)."""
+        B, T = ids.shape
+        nb, V = int(num_beams), self.cfg.vocab_size
+        pad, eos = self.cfg.pad_token_id, self.cfg.eos_token_id
+        max_length = T + max_new_tokens
+        ids_x = ids.repeat_interleave(nb, dim=0).contiguous()                       # _expand_inputs_for_generation
+        if img_embeds is not None:
+            img = img_embeds if img_embeds.dim() == 3 else img_embeds[None]
+            if img.shape[0] == 1 and B > 1:
+                img = img.expand(B, -1, -1)
+            img_embeds = img.repeat_interleave(nb, dim=0)
+        BB = B * nb
+        self.reserve(BB, max(max_length + 1, 128))
+        self._graphs = {}
+        st = _lib.current_stream()
+        with torch.cuda.device(self.device):
+            img = self._prep_img(ids_x, img_embeds)
+            _lib.check(self._lib.rd_llm_prefill(self._h, _lib.ptr(ids_x), _lib.ptr(img), BB, T, None, 0, st), "prefill")
+            _, _, logits_p, _, _ = self._state()
+            vpad = (V + 63) // 64 * 64
+            logits_t = self._wrap(logits_p, (self._cap[0], vpad), self.dtype)
+            hyps = [_BeamHypotheses(nb, length_penalty, early_stopping, max_length) for _ in range(B)]
+            done = [False] * B
+            beam_scores = torch.zeros((B, nb), dtype=torch.float32, device=self.device)
+            beam_scores[:, 1:] = -1e9
+            beam_scores = beam_scores.view(-1)
+            seqs = ids_x
+            scores_out = []
+            while True:
+                step_scores = torch.log_softmax(logits_t[:BB, :V], dim=-1)            # in the logits dtype, like transformers
+                if output_scores:
+                    scores_out.append(step_scores.clone())
+                cand = step_scores + beam_scores[:, None]                             # float32 by type promotion
+                top_scores, top_tokens = torch.topk(cand.view(B, nb * V), 2 * nb, dim=1, largest=True, sorted=True)
+                top_idx = torch.div(top_tokens, V, rounding_mode="floor")
+                top_tokens = top_tokens % V
+                # ---- BeamSearchScorer.process on the host: B x 2k candidates ------------------------------------------
+                ts, tt, ti = top_scores.cpu(), top_tokens.cpu(), top_idx.cpu()
+                seqs_cpu = None
+                cur_len = seqs.shape[-1]
+                nxt_scores = torch.zeros((B, nb), dtype=torch.float32)
+                nxt_tokens = torch.zeros((B, nb), dtype=torch.int64)
+                nxt_idx = torch.zeros((B, nb), dtype=torch.int64)
+                for b in range(B):
+                    if done[b]:
+                        nxt_tokens[b, :] = pad
+                        continue
+                    k = 0
+                    for rank in range(2 * nb):
+                        tok, row = int(tt[b, rank]), b * nb + int(ti[b, rank])
+                        if tok == eos:
+                            if rank >= nb:
+                                continue
+                            if seqs_cpu is None:
+                                seqs_cpu = seqs.cpu()
+                            hyps[b].add(seqs_cpu[row].clone(), float(ts[b, rank]))
+                        else:
+                            nxt_scores[b, k], nxt_tokens[b, k], nxt_idx[b, k] = ts[b, rank], tok, row
+                            k += 1
+                        if k == nb:
+                            break
+                    if k < nb:
+                        raise ValueError(f"At most {nb} tokens in {tt[b].tolist()} can be equal to `eos_token_id: {eos}`. "
+                                         "Make sure they are trained correctly.")
+                    done[b] = done[b] or hyps[b].is_done(float(ts[b].max()), cur_len)
+                beam_scores = nxt_scores.view(-1).to(self.device)
+                beam_tokens = nxt_tokens.view(-1).to(self.device)
+                beam_idx = nxt_idx.view(-1).to(self.device)
+                seqs = torch.cat([seqs[beam_idx, :], beam_tokens[:, None]], dim=-1)
+                if all(done) or seqs.shape[-1] >= max_length:
+                    break
+                _lib.check(self._lib.rd_llm_reorder_cache(self._h, _lib.ptr(beam_idx.to(torch.int32).contiguous()), st), "reorder_cache")
+                _lib.check(self._lib.rd_llm_force_tokens(self._h, _lib.ptr(beam_tokens.contiguous()), st), "force_tokens")
+                _lib.check(self._lib.rd_llm_decode_step(self._h, st), "decode_step")
+            # ---- BeamSearchScorer.finalize ---------------------------------------------------------------------------
+            seqs_cpu, bs_cpu = seqs.cpu(), beam_scores.cpu()
+            for b in range(B):
+                if not done[b]:
+                    for k in range(nb):
+                        hyps[b].add(seqs_cpu[b * nb + k], float(bs_cpu[b * nb + k]))
+            best, best_scores = [], torch.zeros(B, dtype=torch.float32)
+            for b in range(B):
+                sc, hyp = sorted(hyps[b].beams, key=lambda x: x[0]).pop()
+                best.append(hyp)
+                best_scores[b] = sc
+            lens = [int(x.shape[-1]) for x in best]
+            sent_max_len = min(max(lens) + 1, max_length)
+            decoded = torch.full((B, sent_max_len), pad, dtype=torch.int64)
+            for b, hyp in enumerate(best):
+                decoded[b, : lens[b]] = hyp
+                if lens[b] < sent_max_len:
+                    decoded[b, lens[b]] = eos
+        self._graphs = {}
+        self._cached_ids = None
+        sequences = decoded.to(self.device)
+        if return_dict_in_generate:
+            return BeamSearchDecoderOnlyOutput(sequences=sequences, sequences_scores=best_scores.to(self.device),
+                                               scores=tuple(scores_out) if output_scores else None)
+        return sequences
 
     def _events(self):
         if self._timing_events is None:

@@ -100,3 +100,37 @@ def test_prompter_matches_reference_behaviour(tmp_path, monkeypatch):
         f.write('{"description": "d", "prompt_input": "<{instruction}|{input}>", "prompt_no_input": "<{instruction}>", "response_split": "##"}')
     c = Prompter("custom")
     assert c.generate_prompt("a", "b") == "<a|b>" and c.get_response("x ## y") == "y"
+
+
+def test_beam_search_restatement_against_transformers_own_beam_search(golden_dir):
+    """oracle.beam_search restates transformers 4.28.1 GenerationMixin.beam_search + BeamSearchScorer (third-party, absent from the
+    reference tree; reached via generate(num_beams=k), test.py:467,629).  Pin: the fixture holds what the beam search of the
+    transformers build in the build container produced on the same seeded tiny LLaMA (oracle/make_golden_beam.py).  That build
+    normalises hypothesis scores by the GENERATED length (EOS included) where 4.28.1 uses the full length - with that one rule
+    switched (length_norm="generated") the restatement must reproduce sequences AND scores exactly; the 4.28.1 rule is then
+    checked for what it changes: only the normalisation, hence possibly which finished hypothesis wins."""
+    import numpy as np
+    z = np.load(os.path.join(golden_dir, "beam_tiny_f32.npz"))
+    cfg = synth.tiny_llama_cfg()
+    sd = synth.make_llama_weights(cfg, seed=int(z["seed"]), dtype=torch.float32, lora=False)
+    sd["lm_head.weight"][cfg.eos_token_id] *= float(z["eos_boost"])
+    orc = O.LlamaOracle(cfg, sd, torch.float32, use_lora=False)
+    for n in ("a", "b"):
+        ids = torch.from_numpy(z[f"{n}_prompts"])
+        nb, new = (int(x) for x in z[f"{n}_cfg"])
+        T = ids.shape[1]
+        seq, sc = O.llama_beam_search(orc, ids, None, new, nb, length_norm="generated")
+        ref = torch.from_numpy(z[f"{n}_sequences"])
+        for b in range(ids.shape[0]):
+            r, o = ref[b, T:].tolist(), seq[b, T:].tolist()
+            r = r[: r.index(2) + 1] if 2 in r else r
+            o = o[: o.index(2) + 1] if 2 in o else o
+            assert r == o, f"case {n} row {b}: {o} != {r}"
+        assert np.allclose(sc.numpy(), z[f"{n}_scores"], rtol=0, atol=2e-5)
+        # the reference's rule (4.28.1): same search, scores = sum_logprobs / full length
+        seq_f, sc_f = O.llama_beam_search(orc, ids, None, new, nb, length_norm="full")
+        assert seq_f.shape[0] == ids.shape[0] and torch.equal(seq_f[:, :T], ids)
+        for b in range(ids.shape[0]):
+            if 2 not in seq_f[b, T:].tolist() and 2 not in ref[b, T:].tolist():     # no finished hypothesis involved: identical beams
+                assert torch.equal(seq_f[b], ref[b])
+                assert abs(float(sc_f[b]) * seq_f.shape[1] - float(z[f"{n}_scores"][b]) * new) < 1e-3
