@@ -22,6 +22,25 @@ def build(cfg, dtype, dev, seed, eos_boost=1.0, lora=True):
     return LlamaForCausalLM.from_state_dict(cfg, sd, torch_dtype=dtype, device=dev), O.LlamaOracle(cfg, sd, dtype)
 
 
+def oracle_sequence_scores(orc, prompts, img, seqs, eos):
+    """Length-normalised log-probability (transformers 4.28.1 rule: sum of token log-probs incl. a closing EOS, divided by the
+    hypothesis length without it, prompt included) that the ORACLE model assigns to each returned sequence."""
+    T = prompts.shape[1]
+    out = []
+    for b in range(seqs.shape[0]):
+        gen = seqs[b, T:].tolist()
+        n = gen.index(eos) + 1 if eos in gen else len(gen)
+        full = seqs[b:b + 1, :T + n]
+        mask = full.ne(0).long()
+        mask[:, T:] = 1
+        logits, _ = orc.forward(full[:, :-1], mask[:, :-1], orc.positions_from_mask(mask[:, :-1]), None, None if img is None else img[b:b + 1])
+        lp = torch.log_softmax(logits[0, T - 1:, :], dim=-1).float()            # in the logits dtype like generate, then accumulated in fp32
+        tok = full[0, T:]
+        total = lp.gather(1, tok[:, None]).sum().item()
+        out.append(total / (T + n - (1 if eos in gen else 0)))
+    return torch.tensor(out)
+
+
 @pytest.mark.parametrize("nb,eos_boost,with_img", [(3, 1.0, False), (4, 4.0, False), (2, 1.0, True), (3, 4.0, True)])
 def test_beam_search_matches_oracle(cuda_dev, nb, eos_boost, with_img):
     dtype = torch.float16
@@ -44,8 +63,15 @@ def test_beam_search_matches_oracle(cuda_dev, nb, eos_boost, with_img):
     # accumulated log-prob noise: ~1e-2 per step in fp16 at this logit scale, normalised by the full length
     tol = 1e-2 * new / prompts.shape[1]
     assert torch.allclose(sc, o_sc, atol=tol, rtol=0), f"best-hypothesis scores differ: {sc.tolist()} vs {o_sc.tolist()}"
-    same_rows = sum(int(seq.shape == o_seq.shape and torch.equal(seq[b], o_seq[b])) for b in range(B))
-    assert same_rows >= B - 1, f"only {same_rows}/{B} rows equal the oracle's beams:\n{seq}\n{o_seq}"
+    # the returned hypotheses themselves: equal to the oracle's, or - where accumulated fp16 noise reordered candidates whose
+    # scores are closer than that noise - at least as good as the oracle's best when scored by the oracle model itself
+    re_scored = oracle_sequence_scores(orc, prompts, img, seq, cfg.eos_token_id)
+    for b in range(B):
+        if seq.shape == o_seq.shape and torch.equal(seq[b], o_seq[b]):
+            continue
+        assert re_scored[b] >= o_sc[b] - tol, (f"row {b}: the returned hypothesis scores {re_scored[b]:.5f} under the oracle model, "
+                                                f"the oracle's best hypothesis {o_sc[b]:.5f}:\n{seq[b]}\n{o_seq[b]}")
+        assert abs(re_scored[b] - sc[b]) <= tol, f"row {b}: reported score {sc[b]:.5f} vs oracle re-score {re_scored[b]:.5f}"
     # a greedy call afterwards must still work (captured graphs were dropped, the cache buffers were swapped)
     greedy = model.generate(prompts.to(cuda_dev), img_embeds=None if img is None else img.to(cuda_dev), max_new_tokens=6, suppress_eos=True)
     o_greedy = orc.generate(prompts, img, 6, suppress_eos=True)
