@@ -96,6 +96,24 @@ def golden_vision(tag: str, B: int, image_size: int = 448):
                         image_embeds_sub=ref_e[:, ::7, ::11].numpy().astype(np.float32))
 
 
+def golden_vision_temporal(tag: str, B: int = 1, image_size: int = 448):
+    """Two-image branch: the reference's own MultiImageEncoder + VisionTransformerPooler on (current, previous)."""
+    import transformers.modeling_utils  # noqa: F401  (before the timm import shim: transformers probes timm's module spec)
+    vcfg = synth.VisionCfg(image_size=image_size)
+    sd = synth.make_vision_weights(vcfg, seed=0)
+    cur = synth.make_images(B, size=image_size, seed=1234)
+    prev = synth.make_images(B, size=image_size, seed=4242)
+    im = R.build_ref_image_model(sd)
+    q_emb, q_enc = R.build_ref_qformer(sd, vcfg)
+    ref_q, ref_e = R.ref_forward_image(im, q_emb, q_enc, sd, vcfg, cur, prev)
+    o_q, o_e = O.forward_image(cur, sd, vcfg, prev)
+    single_q, _ = O.forward_image(cur, sd, vcfg)
+    print(f"[{tag}] oracle-vs-ref: max|dq|={(o_q - ref_q).abs().max():.3e} (|q|max {ref_q.abs().max():.3f}) "
+          f"max|dembeds|={(o_e - ref_e).abs().max():.3e}; two-image vs single-image max|dq|={(o_q - single_q).abs().max():.3e}")
+    np.savez_compressed(os.path.join(GOLD, f"vision_{tag}.npz"), image_size=image_size, B=B, seed=0, img_seed=1234, prev_seed=4242,
+                        q_out=ref_q.numpy().astype(np.float32), image_embeds_sub=ref_e[:, ::7, ::11].numpy().astype(np.float32))
+
+
 def main():
     assert R.available(), "reference tree not found (this script only runs in the build container)"
     os.makedirs(GOLD, exist_ok=True)
@@ -108,6 +126,7 @@ def main():
     wide = synth.LlamaCfg(num_hidden_layers=2)
     golden_llm("wide2_f16", wide, "float16", B=2, new_tokens=3, ragged=True)
     golden_vision("r50_448", B=2)
+    golden_vision_temporal("temporal_r50_448", B=1)
 
 
 if __name__ == "__main__":

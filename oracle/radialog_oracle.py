@@ -408,16 +408,70 @@ def resnet_trunk(x: torch.Tensor, sd, cfg, prefix="visual_encoder.encoder.encode
     return x
 
 
-def image_model(x: torch.Tensor, sd, cfg) -> torch.Tensor:
-    """ImageModel.forward biovil_t/model.py:76-91 on the single-image branch of MultiImageEncoder.forward
-    biovil_t/encoder.py:124-130: trunk -> backbone_to_vit 1x1 -> concat(missing_previous_emb broadcast)
-    -> projector MLP (modules.py:43-47).  Returns projected_patch_embeddings [B,J,g,g] (NCHW)."""
+def sine_position_embedding(H: int, W: int, embedding_dim: int, temperature: float = 10000.0) -> torch.Tensor:
+    """SinePositionEmbedding(embedding_dim, normalize=True)(mask=ones[1,H,W]) biovil_t/transformer.py:225-266 -> [1, H*W, 2*dim]."""
+    mask = torch.ones(1, H, W)
+    y_embed, x_embed = mask.cumsum(1, dtype=torch.float32), mask.cumsum(2, dtype=torch.float32)
+    scale = 2 * math.pi
+    y_embed = y_embed / (y_embed[:, -1:, :] + 1e-6) * scale
+    x_embed = x_embed / (x_embed[:, :, -1:] + 1e-6) * scale
+    dim_t = torch.arange(embedding_dim, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / embedding_dim)
+    pos_x, pos_y = x_embed[:, :, :, None] / dim_t, y_embed[:, :, :, None] / dim_t
+    pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).view(1, H * W, embedding_dim * 2)
+
+
+def vit_pooler(cur: torch.Tensor, prev: torch.Tensor, sd, cfg, prefix="visual_encoder.encoder.vit_pooler.") -> torch.Tensor:
+    """VisionTransformerPooler.forward / forward_after_reshape (biovil_t/transformer.py:77-118) in eval mode: tokens of the
+    current and the previous image concatenated, sine position + type embeddings added to the NORMALISED input of every block's
+    attention (Block.forward :213-218: q = k = v = norm1(x) + emb), pre-LN blocks with MultiHeadAttentionLayer (:148-166, scale
+    after QK^T) and timm Mlp (exact GELU); returns the current image's tokens after norm_post, back in [B,C,H,W]."""
+    B, C, H, W = cur.shape
+    L = H * W
+    x = torch.cat([cur.view(B, C, L).transpose(1, 2), prev.view(B, C, L).transpose(1, 2)], dim=1)          # [B, 2L, C]
+    pos = sine_position_embedding(H, W, C // 2).repeat(B, 1, 1)
+    te = sd[prefix + "type_embed"]
+    emb = torch.cat([pos, pos], dim=1) + torch.cat([te[0].expand(B, L, -1), te[1].expand(B, L, -1)], dim=1)
+    nh = cfg.pooler_heads
+    hd = C // nh
+    for i in range(cfg.pooler_blocks):
+        p = prefix + f"blocks.{i}."
+        xe = _ln(x, sd, p + "norm1", cfg.pooler_ln_eps) + emb
+
+        def heads(t):
+            return t.reshape(B, 2 * L, nh, hd).permute(0, 2, 1, 3)
+
+        q = heads(F.linear(xe, sd[p + "attn.proj_q.weight"]))
+        k = heads(F.linear(xe, sd[p + "attn.proj_k.weight"]))
+        v = heads(F.linear(xe, sd[p + "attn.proj_v.weight"]))
+        attn = ((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(dim=-1)
+        o = (attn @ v).transpose(1, 2).reshape(B, 2 * L, C)
+        x = x + _lin(o, sd, p + "attn.proj")
+        h = _ln(x, sd, p + "norm2", cfg.pooler_ln_eps)
+        x = x + _lin(F.gelu(_lin(h, sd, p + "mlp.fc1")), sd, p + "mlp.fc2")
+    x = _ln(x, sd, prefix + "norm_post", cfg.pooler_ln_eps)
+    return x[:, :L].transpose(1, 2).reshape(B, C, H, W)
+
+
+def image_model(x: torch.Tensor, sd, cfg, previous: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ImageModel.forward biovil_t/model.py:76-91 over MultiImageEncoder.forward biovil_t/encoder.py:110-136: trunk ->
+    backbone_to_vit 1x1 -> concat with either the broadcast missing_previous_emb (single image, :124-130) or the
+    VisionTransformerPooler output over (current, previous) (:117-123) -> projector MLP (modules.py:43-47).
+    Returns projected_patch_embeddings [B,J,g,g] (NCHW)."""
     E = "visual_encoder.encoder."
     P = "visual_encoder.projector.model."
-    x = resnet_trunk(x, sd, cfg)
-    patch = F.conv2d(x, sd[E + "backbone_to_vit.weight"])
-    B, _, W, Hh = patch.shape
-    diff = sd[E + "missing_previous_emb"].repeat(B, 1, W, Hh)
+    B = x.shape[0]
+    if previous is not None:
+        assert previous.shape == x.shape
+        both = F.conv2d(resnet_trunk(torch.cat([x, previous], dim=0), sd, cfg), sd[E + "backbone_to_vit.weight"])
+        patch = both[:B]
+        diff = vit_pooler(patch, both[B:], sd, cfg)
+    else:
+        patch = F.conv2d(resnet_trunk(x, sd, cfg), sd[E + "backbone_to_vit.weight"])
+        _, _, W, Hh = patch.shape
+        diff = sd[E + "missing_previous_emb"].repeat(B, 1, W, Hh)
     fused = torch.cat([patch, diff], dim=1)
     h = F.relu(_bn(F.conv2d(fused, sd[P + "0.weight"]), sd, P + "1", cfg.bn_eps))
     return F.conv2d(h, sd[P + "3.weight"], sd[P + "3.bias"])
@@ -470,10 +524,11 @@ def qformer(image_embeds: torch.Tensor, sd, cfg) -> torch.Tensor:
     return h
 
 
-def forward_image(image: torch.Tensor, sd, cfg) -> Tuple[torch.Tensor, torch.Tensor]:
+def forward_image(image: torch.Tensor, sd, cfg, previous_image: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Blip2Qformer.forward_image blip2_qformer.py:467-484 (fp32): the ``reshape(B,-1,1408)`` at :469 is a raw
-    reinterpretation of the NCHW buffer, not a permute; ``ln_vision`` is blip2.py:199-205."""
-    proj = image_model(image.float(), sd, cfg)
+    reinterpretation of the NCHW buffer, not a permute; ``ln_vision`` is blip2.py:199-205.  ``previous_image`` selects the
+    two-image branch of the BioViL-T encoder (the reference's forward_image never passes one: SURVEY.md 8f row 4)."""
+    proj = image_model(image.float(), sd, cfg, None if previous_image is None else previous_image.float())
     image_embeds = proj.reshape(image.shape[0], -1, cfg.joint_feature_size)
     image_embeds = _ln(image_embeds, sd, "ln_vision", cfg.ln_vision_eps)
     return qformer(image_embeds, sd, cfg), image_embeds

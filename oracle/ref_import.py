@@ -182,8 +182,8 @@ def build_ref_image_model(sd, full: bool = True):
     bres.ResNetHIML.load_state_dict = _orig
     own = {k[len("visual_encoder."):]: v for k, v in sd.items() if k.startswith("visual_encoder.")}
     missing, unexpected = m.load_state_dict(own, strict=False)
-    missing = [k for k in missing if not (k.startswith("encoder.vit_pooler") or k.startswith("encoder.encoder.fc")
-                                           or k.endswith("num_batches_tracked"))]
+    missing = [k for k in missing if not (k.startswith("encoder.encoder.fc") or k.endswith("num_batches_tracked") or
+                                           (k.startswith("encoder.vit_pooler") and not any(x.startswith("encoder.vit_pooler") for x in own)))]
     assert not missing and not unexpected, (missing[:5], unexpected[:5])
     return m.eval()
 
@@ -217,10 +217,15 @@ def build_ref_qformer(sd, vcfg):
 
 
 @torch.no_grad()
-def ref_forward_image(image_model, q_emb, q_enc, sd, vcfg, image):
+def ref_forward_image(image_model, q_emb, q_enc, sd, vcfg, image, previous_image=None):
     """blip2_qformer.py:467-484 driven through the imported reference modules (glue lines :469-484 and the
-    fp32 LayerNorm subclass blip2.py:199-205 are the only restated lines)."""
-    proj = image_model(image).projected_patch_embeddings
+    fp32 LayerNorm subclass blip2.py:199-205 are the only restated lines).  With ``previous_image`` the reference's own
+    MultiImageEncoder.forward runs its two-image branch (biovil_t/encoder.py:117-123 -> VisionTransformerPooler)."""
+    if previous_image is None:
+        proj = image_model(image).projected_patch_embeddings
+    else:
+        patch_x, pooled_x = image_model.encoder(image, previous_image=previous_image, return_patch_embeddings=True)
+        proj = image_model.forward_post_encoder(patch_x, pooled_x).projected_patch_embeddings
     x = proj.reshape(image.shape[0], -1, vcfg.joint_feature_size)
     x = torch.nn.functional.layer_norm(x.float(), (vcfg.joint_feature_size,), sd["ln_vision.weight"], sd["ln_vision.bias"],
                                        vcfg.ln_vision_eps)

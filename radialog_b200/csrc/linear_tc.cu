@@ -263,6 +263,7 @@ struct TcParams {
   // part_out[split][NT][N] and is done - no cluster, no DSMEM, no reduction pass.  The consumer (attention_decode_kernel) sums
   // the splits in fixed order and applies the single rounding T(Wx) when it reads q/k/v.
   float* part_out;
+  int m_fast;                  // grid is (m_tiles, n_tiles, splits) instead of (n_tiles, m_tiles, splits)
   int wide_epi;                // NT >= 64: transposed epilogue through shared memory (coalesced residual loads / stores)
   EpiParams epi;
 };
@@ -287,7 +288,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   float* s_ssq4 = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256 + NT * BLOCK_N * 2);    // = lora_t staging area (EPI_RES1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  // raster order: blockIdx.x runs fastest in the hardware's CTA dispatch.  m_fast puts the token tiles there, so that CTAs
+  // running together share one WEIGHT tile and walk the (small, L2-resident) activations - the weights then cross HBM once
+  // instead of once per token tile (prefill: 100-180 MB of weights cycled 8 times through a 126 MB L2 miss almost always)
+  const int n_tile = p.m_fast ? blockIdx.y : blockIdx.x, m_tile = p.m_fast ? blockIdx.x : blockIdx.y, split = blockIdx.z;
+  const int n_tiles_g = p.m_fast ? gridDim.y : gridDim.x;
   const int n0 = n_tile * BLOCK_N, m0 = m_tile * NT;
   const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb_begin = (int)(((int64_t)kb_total * split) / p.splits);
@@ -319,7 +324,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
   const int m_valid = min(NT, p.M - m0);
   const int tiles = gridDim.x * gridDim.y;
-  const int tile_id = m_tile * gridDim.x + n_tile;
+  const int tile_id = m_tile * n_tiles_g + n_tile;
   float* red = reinterpret_cast<float*>(smem);    // cluster split-K: partial tile parked in the pipeline smem
   EpiCtx<T> cx;                                   // epilogue operands hoisted into registers (epilogue warps only)
 
@@ -765,7 +770,43 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
+int encode_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int box_rows, int dtype);
+
+// cuTensorMapEncodeTiled costs a few microseconds of host time; a step re-uses the same few hundred (pointer, shape) pairs
+// (weights, the engine's activation buffers), so the encoded descriptors are kept in a small open-addressing cache.
+struct MapKey { const void* ptr; int64_t ld; int rows, K, box_rows, dtype; };
+struct MapSlot { MapKey k; CUtensorMap m; bool used; };
+constexpr int MAP_CACHE = 4096;
+
 int make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int box_rows, int dtype) {
+  static thread_local MapSlot* cache = nullptr;
+  if (cache == nullptr) cache = static_cast<MapSlot*>(calloc(MAP_CACHE, sizeof(MapSlot)));
+  if (cache == nullptr) return encode_map(map, ptr, ld, rows, K, box_rows, dtype);
+  uint64_t hsh = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull ^ ((uint64_t)ld << 32) ^ ((uint64_t)rows << 17) ^ ((uint64_t)K << 3) ^ (uint64_t)box_rows ^ ((uint64_t)dtype << 60);
+  hsh ^= hsh >> 29;
+  for (int probe = 0; probe < 8; ++probe) {
+    MapSlot& sl = cache[(hsh + probe) & (MAP_CACHE - 1)];
+    if (sl.used && sl.k.ptr == ptr && sl.k.ld == ld && sl.k.rows == rows && sl.k.K == K && sl.k.box_rows == box_rows && sl.k.dtype == dtype) {
+      *map = sl.m;
+      return RD_OK;
+    }
+    if (!sl.used) {
+      RD_CHECK(encode_map(&sl.m, ptr, ld, rows, K, box_rows, dtype));
+      sl.k = MapKey{ptr, ld, rows, K, box_rows, dtype};
+      sl.used = true;
+      *map = sl.m;
+      return RD_OK;
+    }
+  }
+  MapSlot& sl = cache[hsh & (MAP_CACHE - 1)];                         // neighbourhood full: overwrite the home slot
+  RD_CHECK(encode_map(&sl.m, ptr, ld, rows, K, box_rows, dtype));
+  sl.k = MapKey{ptr, ld, rows, K, box_rows, dtype};
+  sl.used = true;
+  *map = sl.m;
+  return RD_OK;
+}
+
+int encode_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int box_rows, int dtype) {
   PFN_encodeTiled enc = get_encode();
   RD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -905,8 +946,10 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
     p.ws_ctr = reinterpret_cast<uint32_t*>(ws);                                   // counters first (zero-initialised by the owner)
     p.ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((int64_t)n_tiles * m_tiles * 4 + 255) / 256 * 256);
   }
+  // the operand that is larger in HBM should be the one consecutive CTAs share (see the kernel's raster-order note)
+  p.m_fast = (m_tiles > 1 && splits == 1 && !p.cluster && (int64_t)(SWIGLU ? 2 : 1) * N > (int64_t)M) ? 1 : 0;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(n_tiles, m_tiles, splits); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = p.m_fast ? dim3(m_tiles, n_tiles, splits) : dim3(n_tiles, m_tiles, splits); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
   if (rd_pdl_enabled()) {

@@ -80,6 +80,10 @@ class VisionCfg:
     q_layers: int = 12
     q_intermediate: int = 3072
     cross_attention_freq: int = 2                 # blip2.py:53
+    pooler_blocks: int = 3                        # VisionTransformerPooler (biovil_t/transformer.py:41-44; encoder.py:104)
+    pooler_heads: int = 8
+    pooler_mlp_ratio: float = 1.0
+    pooler_ln_eps: float = 1e-6                   # partial(nn.LayerNorm, eps=1e-6), transformer.py:45
     ln_vision_eps: float = 1e-5                   # nn.LayerNorm default (blip2.py:86)
     q_ln_eps: float = 1e-12                       # BertConfig.layer_norm_eps
     bn_eps: float = 1e-5
@@ -244,6 +248,22 @@ def make_vision_weights(cfg: VisionCfg, seed: int = 0) -> Dict[str, torch.Tensor
         lin(p + "intermediate_query.dense", Iq, Hq)
         lin(p + "output_query.dense", Hq, Iq)
         ln(p + "output_query.LayerNorm", Hq)
+    # VisionTransformerPooler of the two-image (temporal) branch, biovil_t/transformer.py:28-75 / encoder.py:104: 3 blocks of
+    # dim = backbone_to_vit, 8 heads, mlp_ratio 1, q/k/v without bias.  Drawn LAST so that every tensor above keeps the bits
+    # it had before this branch existed (the committed fixtures depend on them).
+    C = cfg.backbone_to_vit
+    VP = E + "vit_pooler."
+    for i in range(cfg.pooler_blocks):
+        p = VP + f"blocks.{i}."
+        ln(p + "norm1", C)
+        for n in ("proj_q", "proj_k", "proj_v"):
+            sd[p + f"attn.{n}.weight"] = randn(C, C, std=0.02)
+        lin(p + "attn.proj", C, C)
+        ln(p + "norm2", C)
+        lin(p + "mlp.fc1", int(C * cfg.pooler_mlp_ratio), C)
+        lin(p + "mlp.fc2", C, int(C * cfg.pooler_mlp_ratio))
+    ln(VP + "norm_post", C)
+    sd[VP + "type_embed"] = torch.nn.init.trunc_normal_(torch.zeros(2, 1, C), std=0.02, generator=g)
     return sd
 
 

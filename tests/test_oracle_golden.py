@@ -134,3 +134,20 @@ def test_beam_search_restatement_against_transformers_own_beam_search(golden_dir
             if 2 not in seq_f[b, T:].tolist() and 2 not in ref[b, T:].tolist():     # no finished hypothesis involved: identical beams
                 assert torch.equal(seq_f[b], ref[b])
                 assert abs(float(sc_f[b]) * seq_f.shape[1] - float(z[f"{n}_scores"][b]) * new) < 1e-3
+
+
+def test_two_image_temporal_branch_against_reference_fixture(golden_dir):
+    """biovil_t/encoder.py:117-123 + VisionTransformerPooler (biovil_t/transformer.py:28-118): the fixture holds the output of the
+    reference's own modules on (current, previous) images (oracle/make_golden.py::golden_vision_temporal)."""
+    import numpy as np
+    z = np.load(os.path.join(golden_dir, "vision_temporal_r50_448.npz"))
+    cfg = synth.VisionCfg(image_size=int(z["image_size"]))
+    sd = synth.make_vision_weights(cfg, seed=int(z["seed"]))
+    B = int(z["B"])
+    cur = synth.make_images(B, size=cfg.image_size, seed=int(z["img_seed"]))
+    prev = synth.make_images(B, size=cfg.image_size, seed=int(z["prev_seed"]))
+    q, e = O.forward_image(cur, sd, cfg, prev)
+    assert np.abs(q.numpy() - z["q_out"]).max() <= 1e-5
+    assert np.abs(e[:, ::7, ::11].numpy() - z["image_embeds_sub"]).max() <= 1e-5
+    q1, _ = O.forward_image(cur, sd, cfg)
+    assert (q - q1).abs().max() > 1e-3          # the previous image really enters the result
