@@ -258,6 +258,9 @@ typedef struct rd_vision_config {
   float ln_vision_eps, q_ln_eps;
   int dtype;
   int max_batch;
+  /* two-image (temporal) branch, VisionTransformerPooler (biovil_t/transformer.py:28-75): 0 blocks = not configured */
+  int pooler_blocks, pooler_heads, pooler_hidden;
+  float pooler_ln_eps;
 } rd_vision_config;
 
 int rd_vision_create(const rd_vision_config* cfg, rd_vision** out);
@@ -270,6 +273,13 @@ int rd_vision_set_weight(rd_vision* h, const char* name, const void* ptr_dev);
  * [B,196,1408] fp32 (may be NULL).                                                                              */
 int rd_vision_forward(rd_vision* h, const float* images_dev, int B, float* q_out_dev, float* image_embeds_dev,
                       void* stream);
+/* Two-image (temporal) mode - MultiImageEncoder.forward with a previous image (biovil_t/encoder.py:117-123): trunk +
+ * backbone_to_vit on both images, VisionTransformerPooler (biovil_t/transformer.py:28-118) over the 2 x 196 tokens, the current
+ * image's pooled tokens as the second half of the projector input; then as rd_vision_forward.  Extra weights by name:
+ * vp{i}.ln1/.ln2 (.g/.b), vp{i}.qkv.w [3C,C], vp{i}.proj (.w/.b), vp{i}.fc1, vp{i}.fc2, vp.post (.g/.b), vp.pos_type [2P,C]
+ * (sine position + type embedding, storage dtype), proj1f (.w [J,2C] / .b).  Allocates on first use.                       */
+int rd_vision_forward_temporal(rd_vision* h, const float* images_dev, const float* prev_images_dev, int B, float* q_out_dev,
+                               float* image_embeds_dev, void* stream);
 int64_t rd_vision_launch_count(rd_vision* h);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -322,7 +322,10 @@ def beam_search(step_logits, input_ids: torch.Tensor, num_beams: int, max_length
         scores = F.log_softmax(logits, dim=-1)                                 # in the logits dtype, like HF
         scores = scores.cpu() + beam_scores[:, None]                           # fp32 by type promotion
         V = scores.shape[-1]
-        top_scores, top_tokens = torch.topk(scores.view(B, num_beams * V), 2 * num_beams, dim=1, largest=True, sorted=True)
+        # torch.topk leaves the order of EQUAL scores unspecified (and fp16 log-probs tie often); a stable descending sort fixes
+        # it to "lowest flat index first" - one valid instance of the transformers behaviour, and reproducible across devices
+        srt_scores, srt_tokens = torch.sort(scores.view(B, num_beams * V), dim=1, descending=True, stable=True)
+        top_scores, top_tokens = srt_scores[:, : 2 * num_beams], srt_tokens[:, : 2 * num_beams]
         top_idx = torch.div(top_tokens, V, rounding_mode="floor")
         top_tokens = top_tokens % V
         # ---- BeamSearchScorer.process -------------------------------------------------------------------------------

@@ -39,7 +39,8 @@ class VisionConfig(C.Structure):
     _fields_ = [("image_size", C.c_int), ("layers", C.c_int * 4), ("width", C.c_int), ("backbone_to_vit", C.c_int),
                 ("joint", C.c_int), ("num_query", C.c_int), ("q_hidden", C.c_int), ("q_heads", C.c_int),
                 ("q_layers", C.c_int), ("q_inter", C.c_int), ("cross_freq", C.c_int), ("ln_vision_eps", C.c_float),
-                ("q_ln_eps", C.c_float), ("dtype", C.c_int), ("max_batch", C.c_int)]
+                ("q_ln_eps", C.c_float), ("dtype", C.c_int), ("max_batch", C.c_int), ("pooler_blocks", C.c_int), ("pooler_heads", C.c_int),
+                ("pooler_hidden", C.c_int), ("pooler_ln_eps", C.c_float)]
 
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -88,6 +89,7 @@ SIGNATURES = {
     "rd_vision_destroy": (None, [_p]),
     "rd_vision_set_weight": (_i, [_p, C.c_char_p, _p]),
     "rd_vision_forward": (_i, [_p, _p, _i, _p, _p, _p]),
+    "rd_vision_forward_temporal": (_i, [_p, _p, _p, _i, _p, _p, _p]),
     "rd_vision_launch_count": (_i64, [_p]),
     "rd_preproc_create": (_i, [_i, _i, _i, _i, C.POINTER(_p)]),
     "rd_preproc_destroy": (None, [_p]),

@@ -18,6 +18,7 @@ extern "C" int rd_ln_vision_tokens(const void*, const float*, const float*, void
 extern "C" int rd_small_attention(const void*, int64_t, const void*, const void*, int64_t, void*, int64_t, int, int, int, int, int, int, void*);
 extern "C" int rd_broadcast_rows(const void*, void*, int64_t, int, int, void*);
 extern "C" int rd_cast_f32(const void*, float*, int64_t, int, void*);
+extern "C" int rd_add_rows_bcast(const void*, const void*, void*, int64_t, int64_t, int, void*);
 
 static constexpr int STEM_KP = 152;   // 7*7*3 = 147 padded to a multiple of 8
 
@@ -26,6 +27,8 @@ struct rd_vision {
   std::map<std::string, const void*> w;
   char *actA = nullptr, *actB = nullptr, *t1 = nullptr, *t2 = nullptr, *idt = nullptr, *col = nullptr;
   char *emb = nullptr, *kv = nullptr, *hq = nullptr, *qkv = nullptr, *ctx = nullptr, *tmp = nullptr, *ffn = nullptr, *ws = nullptr;
+  // two-image (temporal) branch, allocated on first use: fused [B*P, 2C], pooler token streams [B*2P, C] x3, qkv [B*2P, 3C]
+  char *fused = nullptr, *px = nullptr, *py = nullptr, *pt = nullptr, *pqkv = nullptr;
   int64_t ws_bytes = 0;
   int64_t launches = 0;
 };
@@ -83,7 +86,8 @@ extern "C" int rd_vision_create(const rd_vision_config* cfg, rd_vision** out) {
 
 extern "C" void rd_vision_destroy(rd_vision* h) {
   if (!h) return;
-  void* ptrs[] = {h->actA, h->actB, h->t1, h->t2, h->idt, h->col, h->emb, h->kv, h->hq, h->qkv, h->ctx, h->tmp, h->ffn, h->ws};
+  void* ptrs[] = {h->actA, h->actB, h->t1, h->t2, h->idt, h->col, h->emb, h->kv, h->hq, h->qkv, h->ctx, h->tmp, h->ffn, h->ws,
+                  h->fused, h->px, h->py, h->pt, h->pqkv};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
 }
@@ -129,14 +133,12 @@ struct Ctx {
 };
 }  // namespace
 
-extern "C" int rd_vision_forward(rd_vision* h, const float* images, int B, float* q_out, float* image_embeds, void* stream) {
-  RD_REQUIRE(h && images && q_out, "rd_vision_forward: null argument");
-  RD_REQUIRE(B > 0 && B <= h->c.max_batch, "rd_vision_forward: B=%d out of range (max_batch %d)", B, h->c.max_batch);
+// ResNet-50 trunk + backbone_to_vit of B images: patch tokens [B*P, C] (NHWC) written to patch_out with row pitch ld_patch.
+// Returns through cur/nxt the two ping-pong activation buffers (cur = free to overwrite afterwards).
+static void trunk_b2v(rd_vision* h, Ctx& X, const float* images, int B, void* patch_out, int64_t ld_patch, char** cur_out, char** nxt_out) {
   const rd_vision_config& c = h->c;
-  Ctx X{h, (cudaStream_t)stream, c.dtype};
   const int S = c.image_size, W0 = c.width, dt = c.dtype;
-  void* st = stream;
-
+  void* st = X.st;
   // ---- stem: conv1 7x7/2 + BN + ReLU, max-pool 3x3/2 --------------------------------------------------------------
   int hw = S / 2;
   X.chk(rd_stem_im2col(images, h->col, B, S, STEM_KP, dt, st));
@@ -168,14 +170,21 @@ extern "C" int rd_vision_forward(rd_vision* h, const float* images, int B, float
       hw = ohw; inpl = planes * 4;
     }
   }
-  // ---- backbone_to_vit + projector ------------------------------------------------------------------------------------
-  const int P = hw * hw, J = c.joint, MP = B * P;
-  X.gemm(cur, inpl, "b2v", false, h->t1, c.backbone_to_vit, MP, c.backbone_to_vit, inpl, RD_ACT_NONE);
-  X.gemm(h->t1, c.backbone_to_vit, "proj1", true, nxt, J, MP, J, c.backbone_to_vit, RD_ACT_RELU);
-  X.gemm(nxt, J, "proj2", true, cur, J, MP, J, J, RD_ACT_NONE);
+  X.gemm(cur, inpl, "b2v", false, patch_out, ld_patch, B * hw * hw, c.backbone_to_vit, inpl, RD_ACT_NONE);
+  *cur_out = nxt; *nxt_out = cur;      // both are free now (the trunk output has been consumed by backbone_to_vit)
+}
+
+// projector's second conv -> NCHW-flat token reinterpretation + ln_vision -> Q-Former; `proj1_out` holds ReLU(BN(conv1)) [B*P, J]
+static int tail_from_proj1(rd_vision* h, Ctx& X, char* proj1_out, char* other, int B, float* q_out, float* image_embeds) {
+  const rd_vision_config& c = h->c;
+  const int dt = c.dtype;
+  void* st = X.st;
+  const int g = c.image_size / 32, P = g * g, J = c.joint, MP = B * P;
+  char* cur = other;
+  X.gemm(proj1_out, J, "proj2", true, cur, J, MP, J, J, RD_ACT_NONE);
   if (X.err == RD_OK) {
-    const float* g = (const float*)X.W("ln_vision.g"); const float* bb = (const float*)X.W("ln_vision.b");
-    if (X.err == RD_OK) X.chk(rd_ln_vision_tokens(cur, g, bb, h->emb, image_embeds, B, P, J, c.ln_vision_eps, dt, st));
+    const float* gg = (const float*)X.W("ln_vision.g"); const float* bb = (const float*)X.W("ln_vision.b");
+    if (X.err == RD_OK) X.chk(rd_ln_vision_tokens(cur, gg, bb, h->emb, image_embeds, B, P, J, c.ln_vision_eps, dt, st));
   }
   // ---- Q-Former ---------------------------------------------------------------------------------------------------------
   const int Hq = c.q_hidden, Q = c.num_query, MQ = B * Q, hd = Hq / c.q_heads;
@@ -206,4 +215,74 @@ extern "C" int rd_vision_forward(rd_vision* h, const float* images, int B, float
   }
   if (X.err == RD_OK) X.chk(rd_cast_f32(h->hq, q_out, (int64_t)MQ * Hq, dt, st));
   return X.err;
+}
+
+extern "C" int rd_vision_forward(rd_vision* h, const float* images, int B, float* q_out, float* image_embeds, void* stream) {
+  RD_REQUIRE(h && images && q_out, "rd_vision_forward: null argument");
+  RD_REQUIRE(B > 0 && B <= h->c.max_batch, "rd_vision_forward: B=%d out of range (max_batch %d)", B, h->c.max_batch);
+  const rd_vision_config& c = h->c;
+  Ctx X{h, (cudaStream_t)stream, c.dtype};
+  const int g = c.image_size / 32, MP = B * g * g, J = c.joint;
+  char *cur, *nxt;
+  trunk_b2v(h, X, images, B, h->t1, c.backbone_to_vit, &cur, &nxt);
+  // projector conv1: the constant missing_previous_emb half of its input (encoder.py:128-130) is folded into the bias
+  X.gemm(h->t1, c.backbone_to_vit, "proj1", true, nxt, J, MP, J, c.backbone_to_vit, RD_ACT_RELU);
+  return tail_from_proj1(h, X, nxt, cur, B, q_out, image_embeds);
+}
+
+// Two-image (temporal) mode: MultiImageEncoder.forward with a previous image (biovil_t/encoder.py:117-123) - both images go
+// through the trunk + backbone_to_vit, VisionTransformerPooler (biovil_t/transformer.py:28-118) runs over the 2 x P tokens
+// (pre-LN blocks; the sine position + type embedding is added to the normalised input of every block's attention), and the
+// current image's pooled tokens replace missing_previous_emb as the second half of the projector's input.
+extern "C" int rd_vision_forward_temporal(rd_vision* h, const float* images, const float* prev_images, int B, float* q_out,
+                                          float* image_embeds, void* stream) {
+  RD_REQUIRE(h && images && prev_images && q_out, "rd_vision_forward_temporal: null argument");
+  RD_REQUIRE(B > 0 && B <= h->c.max_batch, "rd_vision_forward_temporal: B=%d out of range (max_batch %d)", B, h->c.max_batch);
+  const rd_vision_config& c = h->c;
+  RD_REQUIRE(c.pooler_blocks > 0 && c.pooler_heads > 0 && c.backbone_to_vit % c.pooler_heads == 0, "rd_vision_forward_temporal: pooler not configured");
+  const int C = c.backbone_to_vit, hdp = C / c.pooler_heads;
+  RD_REQUIRE(hdp == 32 || hdp == 64, "rd_vision_forward_temporal: pooler head_dim must be 32 or 64 (got %d)", hdp);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = c.image_size / 32, P = g * g, J = c.joint, MP = B * P, M2 = B * 2 * P, e = 2;
+  if (h->fused == nullptr) {       // first use: allocate (call outside stream capture)
+    const int64_t Bm = c.max_batch;
+    RD_CHECK(valloc(&h->fused, Bm * P * 2 * C * e)); RD_CHECK(valloc(&h->px, Bm * 2 * P * C * e)); RD_CHECK(valloc(&h->py, Bm * 2 * P * C * e));
+    RD_CHECK(valloc(&h->pt, Bm * 2 * P * std::max(C, c.pooler_hidden) * e)); RD_CHECK(valloc(&h->pqkv, Bm * 2 * P * 3 * C * e));
+  }
+  Ctx X{h, st, c.dtype};
+  char *cur, *nxt;
+  // current image -> first half of the fused projector input AND first P tokens of every image's pooler stream
+  trunk_b2v(h, X, images, B, h->fused, 2 * C, &cur, &nxt);
+  if (X.err != RD_OK) return X.err;
+  for (int b = 0; b < B; ++b)      // fused[b, p, 0:C] -> px[b, p, :]
+    RD_CHECK_CUDA(cudaMemcpy2DAsync(h->px + (int64_t)b * 2 * P * C * e, (size_t)C * e, h->fused + (int64_t)b * P * 2 * C * e, (size_t)2 * C * e,
+                                    (size_t)C * e, P, cudaMemcpyDeviceToDevice, st));
+  // previous image -> tokens P..2P-1 (through a dense scratch, then one strided copy)
+  trunk_b2v(h, X, prev_images, B, h->py, C, &cur, &nxt);
+  if (X.err != RD_OK) return X.err;
+  RD_CHECK_CUDA(cudaMemcpy2DAsync(h->px + (int64_t)P * C * e, (size_t)2 * P * C * e, h->py, (size_t)P * C * e, (size_t)P * C * e, B,
+                                  cudaMemcpyDeviceToDevice, st));
+  // ---- VisionTransformerPooler blocks -------------------------------------------------------------------------------------
+  char* x = h->px; char* y = h->py;
+  const void* emb = X.W("vp.pos_type");
+  if (X.err != RD_OK) return X.err;
+  for (int i = 0; i < c.pooler_blocks; ++i) {
+    const std::string p = "vp" + std::to_string(i);
+    X.ln(x, p + ".ln1", h->pt, M2, C, c.pooler_ln_eps);
+    X.chk(rd_add_rows_bcast(h->pt, emb, h->pt, (int64_t)M2 * C, (int64_t)2 * P * C, c.dtype, st));
+    X.gemm(h->pt, C, p + ".qkv", false, h->pqkv, 3 * C, M2, 3 * C, C, RD_ACT_NONE);
+    if (X.err == RD_OK) X.chk(rd_small_attention(h->pqkv, 3 * C, h->pqkv + (int64_t)C * e, h->pqkv + (int64_t)2 * C * e, 3 * C, h->pt, C, B,
+                                                 c.pooler_heads, hdp, 2 * P, 2 * P, c.dtype, st));
+    X.gemm(h->pt, C, p + ".proj", true, y, C, M2, C, C, RD_ACT_NONE, x, C);                  // x + proj(attn)
+    X.ln(y, p + ".ln2", h->pt, M2, C, c.pooler_ln_eps);
+    X.gemm(h->pt, C, p + ".fc1", true, h->pqkv, c.pooler_hidden, M2, c.pooler_hidden, C, RD_ACT_GELU);
+    X.gemm(h->pqkv, c.pooler_hidden, p + ".fc2", true, x, C, M2, C, c.pooler_hidden, RD_ACT_NONE, y, C);   // y + mlp(norm2(y))
+  }
+  X.ln(x, "vp.post", y, M2, C, c.pooler_ln_eps);
+  if (X.err != RD_OK) return X.err;
+  for (int b = 0; b < B; ++b)      // current image's tokens -> second half of the fused projector input
+    RD_CHECK_CUDA(cudaMemcpy2DAsync(h->fused + (int64_t)b * P * 2 * C * e + (int64_t)C * e, (size_t)2 * C * e, y + (int64_t)b * 2 * P * C * e,
+                                    (size_t)C * e, (size_t)C * e, P, cudaMemcpyDeviceToDevice, st));
+  X.gemm(h->fused, 2 * C, "proj1f", true, nxt, J, MP, J, 2 * C, RD_ACT_RELU);
+  return tail_from_proj1(h, X, nxt, cur, B, q_out, image_embeds);
 }

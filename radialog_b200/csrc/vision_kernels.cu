@@ -301,3 +301,27 @@ extern "C" int rd_cast_f32(const void* src, float* dst, int64_t n, int dtype, vo
     return RD_OK;
   });
 }
+
+// out[i] = T(a[i] + emb[i % period]): the position + type embedding added to the normalised tokens of every pooler block
+// (Block.with_pos_and_type_embed, biovil_t/transformer.py:209-215); 8 elements per thread
+template <class T>
+__global__ void add_rows_bcast_kernel(const T* __restrict__ a, const T* __restrict__ emb, T* __restrict__ out, int64_t n8, int64_t period8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const Vec8<T> x = ld16(a + i * 8), e = ld16(emb + (i % period8) * 8);
+    Vec8<T> o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = Tr<T>::r(Tr<T>::f(x.v[k]) + Tr<T>::f(e.v[k]));
+    *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(&o);
+  }
+}
+extern "C" int rd_add_rows_bcast(const void* a, const void* emb, void* out, int64_t n, int64_t period, int dtype, void* stream) {
+  RD_REQUIRE(n % 8 == 0 && period % 8 == 0 && period > 0, "rd_add_rows_bcast: sizes must be multiples of 8");
+  const int64_t n8 = n / 8;
+  RD_DISPATCH_DTYPE(dtype, T, {
+    RD_CHECK_CUDA(rd_launch(add_rows_bcast_kernel<T>, dim3((unsigned)((n8 + 255) / 256 > 1184 ? 1184 : (n8 + 255) / 256)), dim3(256), 0,
+                            (cudaStream_t)stream, rd_pdl_enabled(), (const T*)a, (const T*)emb, (T*)out, n8, period / 8));
+    return RD_OK;
+  });
+}

@@ -605,7 +605,10 @@ class LlamaForCausalLM:
                 if output_scores:
                     scores_out.append(step_scores.clone())
                 cand = step_scores + beam_scores[:, None]                             # float32 by type promotion
-                top_scores, top_tokens = torch.topk(cand.view(B, nb * V), 2 * nb, dim=1, largest=True, sorted=True)
+                # transformers uses torch.topk, which leaves the order of EQUAL scores unspecified; a stable descending sort pins
+                # it to "lowest flat index first" (one valid instance of that behaviour, reproducible across devices)
+                srt_scores, srt_tokens = torch.sort(cand.view(B, nb * V), dim=1, descending=True, stable=True)
+                top_scores, top_tokens = srt_scores[:, : 2 * nb], srt_tokens[:, : 2 * nb]
                 top_idx = torch.div(top_tokens, V, rounding_mode="floor")
                 top_tokens = top_tokens % V
                 # ---- BeamSearchScorer.process on the host: B x 2k candidates ------------------------------------------

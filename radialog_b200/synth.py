@@ -104,7 +104,7 @@ class VisionCfg:
 def tiny_vision_cfg(**kw) -> VisionCfg:
     """Reduced trunk/Q-Former for fast CPU tests; same op graph as the full model."""
     base = dict(image_size=64, layers=(1, 1, 1, 1), width=8, backbone_to_vit=32, joint_feature_size=64,
-                num_query_token=32, q_hidden=64, q_heads=2, q_layers=2, q_intermediate=128)
+                num_query_token=32, q_hidden=64, q_heads=2, q_layers=2, q_intermediate=128, pooler_blocks=2, pooler_heads=1)
     base.update(kw)
     return VisionCfg(**base)
 

@@ -95,7 +95,43 @@ def pack_vision_weights(cfg: VisionCfg, sd: Dict[str, torch.Tensor], dtype: torc
         out[q + "ffn_ln.b"] = sd[p + "output_query.LayerNorm.bias"].float()
     out["q.cross_kv.w"] = torch.cat(kv_w, 0).to(dtype)      # all cross-attention K/V projections as one GEMM
     out["q.cross_kv.b"] = torch.cat(kv_b, 0)
+    # ---- two-image (temporal) branch: VisionTransformerPooler (biovil_t/transformer.py:28-118), optional in a state dict ----
+    VP = E + "vit_pooler."
+    if (VP + "norm_post.weight") in sd:
+        C = nb
+        for i in range(cfg.pooler_blocks):
+            p, q = VP + f"blocks.{i}.", f"vp{i}."
+            out[q + "ln1.g"], out[q + "ln1.b"] = sd[p + "norm1.weight"].float(), sd[p + "norm1.bias"].float()
+            out[q + "qkv.w"] = torch.cat([sd[p + f"attn.{n}.weight"].float() for n in ("proj_q", "proj_k", "proj_v")], 0).to(dtype)
+            out[q + "proj.w"], out[q + "proj.b"] = sd[p + "attn.proj.weight"].to(dtype), sd[p + "attn.proj.bias"].float()
+            out[q + "ln2.g"], out[q + "ln2.b"] = sd[p + "norm2.weight"].float(), sd[p + "norm2.bias"].float()
+            out[q + "fc1.w"], out[q + "fc1.b"] = sd[p + "mlp.fc1.weight"].to(dtype), sd[p + "mlp.fc1.bias"].float()
+            out[q + "fc2.w"], out[q + "fc2.b"] = sd[p + "mlp.fc2.weight"].to(dtype), sd[p + "mlp.fc2.bias"].float()
+        out["vp.post.g"], out["vp.post.b"] = sd[VP + "norm_post.weight"].float(), sd[VP + "norm_post.bias"].float()
+        # pos_embed is a non-persistent buffer (transformer.py:63-65): recomputed; tokens = [current (type 0) ; previous (type 1)]
+        pos = sine_position_embedding(cfg.grid, cfg.grid, C // 2)[0]
+        te = sd[VP + "type_embed"].float()
+        out["vp.pos_type.w"] = torch.cat([pos + te[0], pos + te[1]], 0).to(dtype)
+        # projector conv1 over cat([patch, pooled difference tokens]): full [J, 2C] weight, BatchNorm folded
+        out["proj1f.w"] = (w1 * scale[:, None]).contiguous().to(dtype)
+        out["proj1f.b"] = (sd[P + "1.bias"].float() - sd[P + "1.running_mean"].float() * scale)
     return {k: v.contiguous() for k, v in out.items()}
+
+
+def sine_position_embedding(H: int, W: int, embedding_dim: int, temperature: float = 10000.0) -> torch.Tensor:
+    """``SinePositionEmbedding(embedding_dim, normalize=True)(mask=ones[1,H,W])`` (biovil_t/transformer.py:225-266) -> [1, H*W, 2*dim]:
+    normalised cumulative row / column indices scaled to 2*pi, interleaved sin / cos over ``temperature ** (2*(i//2)/dim)``."""
+    import math
+    ones = torch.ones(1, H, W)
+    y, x = ones.cumsum(1, dtype=torch.float32), ones.cumsum(2, dtype=torch.float32)
+    y = y / (y[:, -1:, :] + 1e-6) * (2 * math.pi)
+    x = x / (x[:, :, -1:] + 1e-6) * (2 * math.pi)
+    dim_t = torch.arange(embedding_dim, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / embedding_dim)
+    px, py = x[:, :, :, None] / dim_t, y[:, :, :, None] / dim_t
+    px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).flatten(3)
+    py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((py, px), dim=3).view(1, H * W, embedding_dim * 2)
 
 
 class _IncompatibleKeys:
@@ -182,13 +218,15 @@ class Blip2Qformer:
         vc = _lib.VisionConfig(image_size=c.image_size, layers=(C.c_int * 4)(*c.layers), width=c.width, backbone_to_vit=c.backbone_to_vit,
                                joint=c.joint_feature_size, num_query=c.num_query_token, q_hidden=c.q_hidden, q_heads=c.q_heads,
                                q_layers=c.q_layers, q_inter=c.q_intermediate, cross_freq=c.cross_attention_freq,
-                               ln_vision_eps=c.ln_vision_eps, q_ln_eps=c.q_ln_eps, dtype=_lib.dtype_code(self.dtype), max_batch=max_batch)
+                               ln_vision_eps=c.ln_vision_eps, q_ln_eps=c.q_ln_eps, dtype=_lib.dtype_code(self.dtype), max_batch=max_batch,
+                               pooler_blocks=c.pooler_blocks if "vp.post.g" in self._packed else 0, pooler_heads=c.pooler_heads,
+                               pooler_hidden=int(c.backbone_to_vit * c.pooler_mlp_ratio), pooler_ln_eps=c.pooler_ln_eps)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.rd_vision_create(C.byref(vc), C.byref(h)), "rd_vision_create")
         self._h, self._max_batch = h, max_batch
         for name, t in self._packed.items():
-            key = name[:-2] if name == "q.h0.w" else name
+            key = name[:-2] if name in ("q.h0.w", "vp.pos_type.w") else name
             _lib.check(self._lib.rd_vision_set_weight(h, key.encode(), _lib.ptr(t)), f"set_weight {name}")
 
     def _destroy(self):
@@ -204,20 +242,34 @@ class Blip2Qformer:
             pass
 
     @torch.no_grad()
-    def forward_image(self, image: torch.Tensor):
+    def forward_image(self, image: torch.Tensor, previous_image: torch.Tensor = None):
+        """``Blip2Qformer.forward_image`` (blip2_qformer.py:467-484).  ``previous_image`` (same shape) selects the two-image
+        branch of the BioViL-T encoder (biovil_t/encoder.py:117-123: VisionTransformerPooler over current + previous tokens)
+        - an extension: the reference's forward_image never passes a previous image."""
         c = self.cfg
         if image.dim() != 4 or image.shape[1] != 3 or image.shape[2] != c.image_size or image.shape[3] != c.image_size:
             raise ValueError(f"image must be [B,3,{c.image_size},{c.image_size}], got {tuple(image.shape)}")
+        if previous_image is not None:
+            if previous_image.shape != image.shape:
+                raise AssertionError("current_image and previous_image shapes do not match")     # encoder.py:118
+            if "vp.post.g" not in self._packed:
+                raise KeyError("the state dict holds no visual_encoder.encoder.vit_pooler.* weights: two-image mode is unavailable")
         img = image.to(self.device, torch.float32).contiguous()
+        prev = None if previous_image is None else previous_image.to(self.device, torch.float32).contiguous()
         B = img.shape[0]
         q_out = torch.empty(B, c.num_query_token, c.q_hidden, device=self.device, dtype=torch.float32)
         embeds = torch.empty(B, c.num_patches, c.joint_feature_size, device=self.device, dtype=torch.float32)
         done = 0
-        while done < B:      # chunk to the engine's reserved batch
-            n = min(self._max_batch, B - done)
-            _lib.check(self._lib.rd_vision_forward(self._h, img[done:].data_ptr(), n, q_out[done:].data_ptr(), embeds[done:].data_ptr(),
-                                                   _lib.current_stream()), "rd_vision_forward")
-            done += n
+        with torch.cuda.device(self.device):
+            while done < B:      # chunk to the engine's reserved batch
+                n = min(self._max_batch, B - done)
+                if prev is None:
+                    _lib.check(self._lib.rd_vision_forward(self._h, img[done:].data_ptr(), n, q_out[done:].data_ptr(), embeds[done:].data_ptr(),
+                                                           _lib.current_stream()), "rd_vision_forward")
+                else:
+                    _lib.check(self._lib.rd_vision_forward_temporal(self._h, img[done:].data_ptr(), prev[done:].data_ptr(), n, q_out[done:].data_ptr(),
+                                                                    embeds[done:].data_ptr(), _lib.current_stream()), "rd_vision_forward_temporal")
+                done += n
         return q_out, embeds
 
     def launch_count(self) -> int:

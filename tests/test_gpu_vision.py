@@ -59,6 +59,46 @@ def test_full_resnet50_qformer_vs_reference_golden(cuda_dev, golden_dir, dtype, 
     assert rel_err(q1.cpu(), q.cpu()) <= 2e-3
 
 
+def test_two_image_temporal_branch_tiny_vs_oracle(cuda_dev):
+    """biovil_t/encoder.py:117-123 + VisionTransformerPooler (transformer.py:28-118) through rd_vision_forward_temporal.  The
+    previous image moves the output only a little, so besides the usual tolerance the CHANGE it causes (two-image minus
+    single-image output) must itself match the oracle's change."""
+    cfg = synth.tiny_vision_cfg()
+    sd = synth.make_vision_weights(cfg, seed=0)
+    cur = synth.make_images(3, size=cfg.image_size, seed=1234)
+    prev = synth.make_images(3, size=cfg.image_size, seed=4242)
+    o_q2, o_e2 = O.forward_image(cur, sd, cfg, prev)
+    o_q1, o_e1 = O.forward_image(cur, sd, cfg)
+    model = Blip2Qformer.from_state_dict(cfg, sd, torch_dtype=torch.float16, device=cuda_dev, max_batch=2)     # 3 images: chunked 2 + 1
+    q2, e2 = model.forward_image(cur.to(cuda_dev), prev.to(cuda_dev))
+    q1, e1 = model.forward_image(cur.to(cuda_dev))
+    assert rel_err(e2.cpu(), o_e2) <= 1e-2 and rel_err(q2.cpu(), o_q2) <= 1e-2
+    assert rel_err(e1.cpu(), o_e1) <= 1e-2 and rel_err(q1.cpu(), o_q1) <= 1e-2
+    d_ref, d_own = (o_e2 - o_e1), (e2 - e1).cpu()
+    assert d_ref.abs().max() > 1e-3
+    assert rel_err(d_own, d_ref) <= 0.25, f"effect of the previous image differs: {rel_err(d_own, d_ref):.3e}"
+    with pytest.raises(AssertionError):
+        model.forward_image(cur.to(cuda_dev), prev[:2].to(cuda_dev))
+
+
+def test_two_image_temporal_branch_full_size_vs_reference_golden(cuda_dev, golden_dir):
+    """Full ResNet-50 + 3-block pooler (dim 256, 8 heads, 2 x 196 tokens) against the output of the reference's own
+    MultiImageEncoder / VisionTransformerPooler modules (tests/golden/vision_temporal_r50_448.npz)."""
+    z = np.load(os.path.join(golden_dir, "vision_temporal_r50_448.npz"))
+    cfg = synth.VisionCfg(image_size=int(z["image_size"]))
+    sd = synth.make_vision_weights(cfg, seed=int(z["seed"]))
+    B = int(z["B"])
+    cur = synth.make_images(B, size=cfg.image_size, seed=int(z["img_seed"]))
+    prev = synth.make_images(B, size=cfg.image_size, seed=int(z["prev_seed"]))
+    model = Blip2Qformer.from_state_dict(cfg, sd, torch_dtype=torch.float16, device=cuda_dev, max_batch=B)
+    q, e = model.forward_image(cur.to(cuda_dev), prev.to(cuda_dev))
+    ref_q, ref_e = torch.from_numpy(z["q_out"]), torch.from_numpy(z["image_embeds_sub"])
+    assert rel_err(e.cpu()[:, ::7, ::11], ref_e) <= 1e-2, f"image_embeds rel err {rel_err(e.cpu()[:, ::7, ::11], ref_e):.3e}"
+    assert rel_err(q.cpu(), ref_q) <= 1e-2, f"q_out rel err {rel_err(q.cpu(), ref_q):.3e}"
+    q1, _ = model.forward_image(cur.to(cuda_dev))
+    assert (q - q1).abs().max().item() > 1e-3
+
+
 def test_image_shape_is_validated(cuda_dev):
     cfg = synth.tiny_vision_cfg()
     sd = synth.make_vision_weights(cfg, seed=0)

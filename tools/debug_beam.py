@@ -21,23 +21,23 @@ orc = O.LlamaOracle(cfg, sd, torch.float16)
 prompts = synth.make_prompts(3, seed=50 + nb, ragged=True)
 prompts = torch.where(prompts == synth.IMG_TOKEN_ID, torch.full_like(prompts, 77), prompts)
 log = {"o": [], "p": []}
-_topk = torch.topk
+_topk = torch.sort
 
 
 def spy(which):
-    def f(x, k, **kw):
-        r = _topk(x, k, **kw)
+    def f(x, *a, **kw):
+        r = _topk(x, *a, **kw)
         if x.dim() == 2 and x.shape[0] == 3:
-            log[which].append((r.values.detach().cpu().clone(), r.indices.detach().cpu().clone()))
+            log[which].append((r.values[:, :2 * nb].detach().cpu().clone(), r.indices[:, :2 * nb].detach().cpu().clone()))
         return r
     return f
 
 
-torch.topk = spy("o")
+torch.sort = spy("o")
 o_seq, o_sc = O.llama_beam_search(orc, prompts, None, 14, nb)
-torch.topk = spy("p")
+torch.sort = spy("p")
 out = model.generate(prompts.to(dev), max_new_tokens=14, num_beams=nb, return_dict_in_generate=True)
-torch.topk = _topk
+torch.sort = _topk
 print("oracle scores", o_sc.tolist(), "product", out.sequences_scores.tolist())
 V = cfg.vocab_size
 for s in range(min(len(log["o"]), len(log["p"]))):
