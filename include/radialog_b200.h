@@ -80,6 +80,11 @@ int rd_linear_force_splits(int splits);
 /* Split-K reduction: 0 (default) thread-block cluster + distributed shared memory when splits <= 8, 1 always through
  * the global fp32 workspace.  Both reduce in fixed split order (deterministic). */
 int rd_linear_splitk_mode(int mode);
+/* Decode tiles (M <= 32 tokens): 1 (default) parks the weight k-blocks in tensor memory - the epilogue warps copy every weight
+ * tile that lands in shared memory into a ring of TMEM slots (tcgen05.st) and tcgen05.mma reads its A operand from TMEM - so a
+ * CTA buffers ~1.8x more weight bytes ahead of the activations it depends on; 0 = both operands from shared memory.  Same
+ * products, same accumulation order: bit-identical results. */
+int rd_linear_tmem_staging(int on);
 /* Launch every kernel with the programmatic-dependent-launch attribute (prologue of kernel N+1 — barrier init, TMEM
  * allocation, the first weight tiles — overlaps the tail of kernel N).  On by default; 0 switches it off. */
 int rd_set_pdl(int on);

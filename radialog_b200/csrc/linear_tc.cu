@@ -27,6 +27,8 @@ static int g_force_generic_epilogue = 0;   // test hook
 extern "C" int rd_linear_force_generic_epilogue(int on) { g_force_generic_epilogue = on; return RD_OK; }
 static int g_wide_epi = 1;        // test hook: 0 = direct (per-thread strided) epilogue also for wide token tiles
 extern "C" int rd_linear_wide_epilogue(int on) { g_wide_epi = on; return RD_OK; }
+static int g_ts_mode = 1;         // 1: decode tiles (M <= 32) park weight k-blocks in TMEM (A operand from tensor memory)
+extern "C" int rd_linear_tmem_staging(int on) { g_ts_mode = on; return RD_OK; }
 static int g_splitk_mode = 0;     // 0: cluster/DSMEM reduction when possible, 1: always the global workspace
 extern "C" int rd_linear_splitk_mode(int mode) { g_splitk_mode = mode; return RD_OK; }
 
@@ -242,6 +244,30 @@ template <int NT, bool SWIGLU> struct TcCfg {
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
+// TMEM-staged decode tiles (TS): the weight tile is the UMMA A operand, and tcgen05.mma can read A from tensor memory.  The
+// epilogue warps - idle while the weights stream - copy every weight k-block that lands in shared memory into a ring of TMEM
+// slots (thread = weight row, tcgen05.st 32x32b.x32) and free the shared-memory stage at once; the MMAs read A from TMEM and
+// only the small token tile from shared memory.  A CTA then buffers its 64 KB W ring PLUS up to 112 KB of weights in TMEM, all
+// of it fetched BEFORE the activations exist (weights never depend on the previous kernel): the dead time of a decode-step
+// boundary (reduction tail of kernel N + launch + activation load of kernel N+1) is covered by ~1.8x more prefetched bytes.
+template <int NT, bool SWIGLU> struct TsCfg {
+  static constexpr int ACCS = SWIGLU ? 2 : 1;
+  static constexpr int W_STAGE = ACCS * BLOCK_N * BLOCK_K * 2;            // 16 KB (32 KB gate|up) per weight k-block
+  static constexpr int X_STAGE = NT * BLOCK_K * 2;
+  static constexpr int WST = 64 * 1024 / W_STAGE;                         // shared-memory W ring: 64 KB
+  static constexpr int XST = 8;                                           // token-tile ring
+  static constexpr int TMEM_COLS = 256;                                   // two CTAs per SM share the 512 columns
+  static constexpr int ACC_COLS = tmem_cols_for(ACCS * NT);
+  static constexpr int SLOT_COLS = 32 * ACCS;                             // 64 K-elements of a 16-bit tile = 32 packed columns
+  static constexpr int TSLOTS = (TMEM_COLS - ACC_COLS) / SLOT_COLS;       // 7 (3 for gate|up) weight k-blocks parked in TMEM
+  static constexpr int RING_BYTES = WST * W_STAGE + XST * X_STAGE;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr bool STAGE_EPI = (NT <= 32) && !SWIGLU;
+  static constexpr int EXTRA_BYTES = STAGE_EPI ? (NT * BLOCK_N * 2 + NT * 16 * 2) : 640;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + BAR_BYTES + EXTRA_BYTES;
+  static_assert(TSLOTS >= 2 && TSLOTS <= 8 && WST >= 2 && WST <= 8, "TMEM / smem ring sizes");
+};
+
 struct TcParams {
   int M, N, K;
   int64_t ldo;
@@ -268,24 +294,58 @@ struct TcParams {
   EpiParams epi;
 };
 
-template <class T, int NT, bool SWIGLU>
+__device__ __forceinline__ void tc_mma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+        "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <class T, int NT, bool SWIGLU, bool TS = false>
 __global__ void __launch_bounds__(TC_THREADS, (NT <= 64) ? 2 : 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, T* __restrict__ out,
                  const TcParams p) {
   using Cfg = TcCfg<NT, SWIGLU>;
+  using Ts = TsCfg<(NT <= 32 ? NT : 32), SWIGLU>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int RING_BYTES = TS ? Ts::RING_BYTES : STAGES * Cfg::STAGE_BYTES;
+  constexpr int BAR_BYTES = TS ? Ts::BAR_BYTES : 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   uint32_t* flag_smem = tmem_ptr_smem + 1;
   uint64_t* xn_bar = reinterpret_cast<uint64_t*>(flag_smem + 1);     // [STAGES] "token tile normalised" (fused RMSNorm)
-  const bool fuse_norm = NT <= 32 && p.norm_ssq != nullptr;
+  // TS barriers (same area, own layout): W ring full/empty, token ring full/empty, TMEM slot ready/empty, accumulators, misc
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
+  uint64_t* w_empty = w_full + 8;
+  uint64_t* x_full = w_empty + 8;
+  uint64_t* x_empty = x_full + 8;
+  uint64_t* a_ready = x_empty + 8;
+  uint64_t* a_empty = a_ready + 8;
+  if (TS) {
+    tmem_full_bar = a_empty + 8;
+    tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    flag_smem = tmem_ptr_smem + 1;
+  }
+  volatile uint32_t* dep_flag = flag_smem + 1;                       // TS: set once the producing kernel's output may be read
+  const bool fuse_norm = !TS && NT <= 32 && p.norm_ssq != nullptr;
   // rstd[32] + [4][32] scratch of the fused norm / of the sum-of-squares epilogue
-  float* s_norm = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);                       // fused norm (plain epilogues)
-  float* s_ssq4 = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256 + NT * BLOCK_N * 2);    // = lora_t staging area (EPI_RES1)
+  float* s_norm = reinterpret_cast<float*>(smem + RING_BYTES + BAR_BYTES);                       // fused norm (plain epilogues)
+  float* s_ssq4 = reinterpret_cast<float*>(smem + RING_BYTES + BAR_BYTES + NT * BLOCK_N * 2);    // = lora_t staging area (EPI_RES1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // raster order: blockIdx.x runs fastest in the hardware's CTA dispatch.  m_fast puts the token tiles there, so that CTAs
@@ -305,12 +365,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&xn_bar[s], 1); }
+    if (TS) {
+      for (int s = 0; s < 8; ++s) {
+        mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 4); mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1);
+        mbar_init(&a_ready[s], 4); mbar_init(&a_empty[s], 1);
+      }
+      *dep_flag = 0u;
+    } else {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&xn_bar[s], 1); }
+    }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TS ? Ts::TMEM_COLS : Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -328,7 +396,72 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   float* red = reinterpret_cast<float*>(smem);    // cluster split-K: partial tile parked in the pipeline smem
   EpiCtx<T> cx;                                   // epilogue operands hoisted into registers (epilogue warps only)
 
-  if (warp == 0) {
+  if (TS && warp == 0) {
+    // ===================== TS: weight producer - never waits for the previous kernel =====================
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % Ts::WST;
+      if (i >= Ts::WST) mbar_wait(&w_empty[s], (uint32_t)((i / Ts::WST) & 1) ^ 1u, 1);
+      __syncwarp();
+      if (elect_one()) {
+        uint8_t* sp = smem + s * Ts::W_STAGE;
+        mbar_expect_tx(&w_full[s], Ts::W_STAGE);
+        tma_load_2d(sp, &map_w, &w_full[s], (kb_begin + i) * BLOCK_K, n0, p.hint_w);
+        if (SWIGLU) tma_load_2d(sp + Cfg::A_BYTES, &map_w, &w_full[s], (kb_begin + i) * BLOCK_K, p.N + n0, p.hint_w);
+      }
+      __syncwarp();
+    }
+  } else if (TS && warp == 1) {
+    // ===================== TS: token-tile loader + MMA issuer (A from TMEM, B from shared memory) =====================
+    constexpr uint32_t idesc = make_idesc(Tr<T>::umma_fmt, BLOCK_N, NT);
+    uint8_t* xring = smem + Ts::WST * Ts::W_STAGE;
+    auto load_x = [&](int j) {
+      const int sx = j % Ts::XST;
+      mbar_expect_tx(&x_full[sx], Ts::X_STAGE);
+      tma_load_2d(xring + sx * Ts::X_STAGE, &map_x, &x_full[sx], (kb_begin + j) * BLOCK_K, m0, p.hint_x);
+    };
+    pdl_wait();                                  // activations were written by the previous kernel
+    if (lane == 0) *dep_flag = 1u;
+    if (elect_one()) {
+      trace_stamp(p.trace, 2);
+      for (int j = 0; j < nkb && j < Ts::XST; ++j) load_x(j);
+    }
+    __syncwarp();
+    const uint64_t dx0 = make_smem_desc(smem_u32(xring));
+    for (int i = 0; i < nkb; ++i) {
+      const int t = i % Ts::TSLOTS, sx = i % Ts::XST;
+      mbar_wait(&a_ready[t], (uint32_t)((i / Ts::TSLOTS) & 1), 2);
+      mbar_wait(&x_full[sx], (uint32_t)((i / Ts::XST) & 1), 2);
+      tc_fence_after();
+      __syncwarp();
+      if (elect_one()) {
+        if (i == 0) trace_stamp(p.trace, 3);
+        const uint64_t db = dx0 + (uint64_t)((uint32_t)sx * (Ts::X_STAGE >> 4));
+        const uint32_t ta = tmem_base + (uint32_t)(Ts::ACC_COLS + t * Ts::SLOT_COLS);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+          tc_mma_ts_f16(tmem_base, ta + (uint32_t)(k * 8), db + koff, idesc, acc);
+          if (SWIGLU) tc_mma_ts_f16(tmem_base + NT, ta + 32u + (uint32_t)(k * 8), db + koff, idesc, acc);
+        }
+        tc_commit(&a_empty[t]);                   // the TMEM slot and the token stage are free once these MMAs have read them
+        tc_commit(&x_empty[sx]);
+        if (i == nkb - 1) {
+          tc_commit(tmem_full_bar);
+          trace_stamp(p.trace, 4);
+        }
+      }
+      __syncwarp();
+      // refill the token stage released one iteration ago (its MMAs have had a k-block's time to complete)
+      if (i >= 1 && i - 1 + Ts::XST < nkb) {
+        const int j = i - 1;
+        mbar_wait(&x_empty[j % Ts::XST], (uint32_t)((j / Ts::XST) & 1), 2);
+        __syncwarp();
+        if (elect_one()) load_x(j + Ts::XST);
+        __syncwarp();
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
     auto stage_ptr = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
     auto load_w = [&](int s, int kb) {
@@ -399,6 +532,52 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    bool res_staged = false;
+    auto stage_residual = [&]() {
+      // EPI_RES1: the residual values this thread will add, parked in shared memory (thread-private slots: no barrier needed)
+      if (!(Cfg::STAGE_EPI && p.epi_mode == EPI_RES1 && n < p.N && (p.splits == 1 || p.cluster))) return;
+      T* res_s = reinterpret_cast<T*>(smem + RING_BYTES + BAR_BYTES);
+      const T* resp = reinterpret_cast<const T*>(p.epi.residual) + n;
+      const int j0 = p.splits == 1 ? 0 : split, jstep = p.splits == 1 ? 1 : p.splits;
+      for (int jb = j0; jb < m_valid; jb += 8 * jstep) {
+        T tmp[8];
+_Pragma("unroll")
+        for (int t = 0; t < 8; ++t) { const int j = jb + t * jstep; if (j < m_valid) tmp[t] = resp[(int64_t)(m0 + j) * p.epi.ld_res]; }
+_Pragma("unroll")
+        for (int t = 0; t < 8; ++t) { const int j = jb + t * jstep; if (j < m_valid) res_s[j * BLOCK_N + n_local] = tmp[t]; }
+      }
+    };
+    if (TS) {
+      // ---- stagers: weight k-blocks shared memory -> TMEM (thread = weight row), W stage released immediately ----
+      const int wrow = quad * 32 + lane;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Ts::WST, t = i % Ts::TSLOTS;
+        mbar_wait(&w_full[s], (uint32_t)((i / Ts::WST) & 1), 4);
+        if (i >= Ts::TSLOTS) mbar_wait(&a_empty[t], (uint32_t)((i / Ts::TSLOTS) & 1) ^ 1u, 4);
+        tc_fence_after();
+_Pragma("unroll")
+        for (int a = 0; a < Cfg::ACCS; ++a) {
+          const uint8_t* wt = smem + s * Ts::W_STAGE + a * Cfg::A_BYTES + (wrow >> 3) * 1024 + (wrow & 7) * 128;
+          uint32_t r[32];
+_Pragma("unroll")
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(wt + ((c ^ (wrow & 7)) << 4));
+            r[c * 4 + 0] = v.x; r[c * 4 + 1] = v.y; r[c * 4 + 2] = v.z; r[c * 4 + 3] = v.w;
+          }
+          tc_st32(taddr + (uint32_t)(Ts::ACC_COLS + t * Ts::SLOT_COLS + a * 32), r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&a_ready[t]); mbar_arrive(&w_empty[s]); }
+        if (!res_staged && *dep_flag != 0u) {      // the previous kernel is done: fetch the residual while the stream still runs
+          pdl_wait();
+          stage_residual();
+          res_staged = true;
+        }
+        __syncwarp();
+      }
+    }
     pdl_wait();
     if (NT <= 32 && fuse_norm) {
       // ---- RMSNorm fused on the input: statistics from the producer's per-tile partials (fixed order), then every
@@ -479,17 +658,10 @@ _Pragma("unroll")
     cx.res_s = nullptr; cx.lt_s = nullptr; cx.n_local = n_local;
     if (Cfg::STAGE_EPI) {
       // while the weight stream runs: pull the residual values this thread will add and the lora_t rows of the tile
-      T* res_s = reinterpret_cast<T*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+      T* res_s = reinterpret_cast<T*>(smem + RING_BYTES + BAR_BYTES);
       T* lt_s = res_s + NT * BLOCK_N;
       if (p.epi_mode == EPI_RES1 && n < p.N && (p.splits == 1 || p.cluster)) {
-        const int j0 = p.splits == 1 ? 0 : split, jstep = p.splits == 1 ? 1 : p.splits;
-        for (int jb = j0; jb < m_valid; jb += 8 * jstep) {
-          T tmp[8];
-_Pragma("unroll")
-          for (int t = 0; t < 8; ++t) { const int j = jb + t * jstep; if (j < m_valid) tmp[t] = cx.resp[(int64_t)(m0 + j) * cx.ld_res]; }
-_Pragma("unroll")
-          for (int t = 0; t < 8; ++t) { const int j = jb + t * jstep; if (j < m_valid) res_s[j * BLOCK_N + n_local] = tmp[t]; }
-        }
+        if (!res_staged) stage_residual();
         cx.res_s = res_s;
       }
       if (p.epi_mode == EPI_LORA16) {
@@ -748,7 +920,7 @@ _Pragma("unroll")
   if (threadIdx.x == 64) trace_stamp(p.trace, 7);
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS ? Ts::TMEM_COLS : Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -963,6 +1135,18 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
+  if constexpr (NT <= 32) {
+    // TMEM-staged variant: decode tiles with a plain / residual / SwiGLU epilogue (see TsCfg)
+    const bool ts = g_ts_mode && m_tiles == 1 && (p.epi_mode == EPI_PLAIN || p.epi_mode == EPI_RES1) && p.norm_ssq == nullptr &&
+                    p.ssq_out == nullptr && kb_total / splits >= 2;
+    if (ts) {
+      using Ts = TsCfg<NT, SWIGLU>;
+      RD_SMEM_ATTR_ONCE(Ts::SMEM_BYTES, linear_tc_kernel<T, NT, SWIGLU, true>);
+      cfg.dynamicSmemBytes = Ts::SMEM_BYTES;
+      RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<T, NT, SWIGLU, true>, map_w, map_x, (T*)out, p));
+      return RD_OK;
+    }
+  }
   RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_tc_kernel<T, NT, SWIGLU>, map_w, map_x, (T*)out, p));
   return RD_OK;
 }

@@ -172,3 +172,30 @@ def test_vicuna_decode_shapes_tc_vs_gemv_vs_simt(lib, cuda_dev):
             floor = 5e-2 if act else 1e-2
             err = (a.float() - b.float()).abs() / b.float().abs().clamp_min(floor)
             assert err.max().item() <= 4 * eps, f"{name} N={N} K={K}: {err.max().item():.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,act,res", [(32, 4096, 4096, 0, True), (32, 1024, 4096, _lib.ACT_SWIGLU, False), (32, 512, 11008, 0, True),
+                                           (7, 12304, 1024, 0, False), (1, 4096, 4096, 0, True), (17, 2048, 704, _lib.ACT_SWIGLU, False),
+                                           (32, 32001, 512, 0, False)])
+def test_tmem_staged_decode_tiles_bit_identical(cuda_dev, lib, dtype, M, N, K, act, res):
+    """Decode tiles with the weight k-blocks parked in tensor memory (tcgen05.st by the epilogue warps, tcgen05.mma with the A
+    operand from TMEM) against the both-operands-from-shared-memory kernel: same products, same accumulation order, same
+    split-K reduction, so the outputs must be bit-identical - and both must match the fp32 reference."""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    rows = 2 * N if act == _lib.ACT_SWIGLU else N
+    w = (torch.randn(rows, K, generator=g) * 0.05).to(dtype).to(cuda_dev)
+    x = (torch.randn(M, K, generator=g) * 0.5).to(dtype).to(cuda_dev)
+    residual = (torch.randn(M, N, generator=g) * 0.5).to(dtype).to(cuda_dev) if res else None
+    ws = torch.zeros(int(lib.rd_linear_workspace_bytes(M, N, K)) + 256, dtype=torch.uint8, device=cuda_dev)
+    outs = {}
+    for ts in (0, 1):
+        lib.rd_linear_tmem_staging(ts)
+        outs[ts] = [run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, act=act, residual=residual, ws=ws) for _ in range(2)]
+    lib.rd_linear_tmem_staging(1)
+    assert torch.equal(outs[1][0], outs[1][1]), "TMEM-staged kernel is not deterministic run to run"
+    assert torch.equal(outs[0][0], outs[1][0]), f"max diff {(outs[0][0].float() - outs[1][0].float()).abs().max().item():.4g}"
+    ref = ref_linear(x, w, dtype, act=act, residual=residual, N=N)
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    scale = ref.float().abs().max().item()
+    assert (outs[1][0].float() - ref.float()).abs().max().item() <= 2 * ulp * scale

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Decode-step time (CUDA graph + PDL, the bench configuration) of the full Vicuna-7B-sized engine under engine switches
-(development tool): QKV partials on/off.  python tools/decode_sweep.py [B] [NEW]"""
+(development tool): TMEM weight staging on/off.  python tools/decode_sweep.py [B] [NEW]"""
 import json
 import os
 import sys
@@ -25,10 +25,11 @@ torch.cuda.empty_cache()
 prompts = synth.make_prompts(B, seed=4321).to(dev)
 img = torch.randn(B, 32, 768, device=dev) * 0.5
 MB = 1 << 20
-variants = [("partials=1", True, None), ("partials=0", False, None), ("partials=1 (again)", True, None), ("partials=0 (again)", False, None)]
+variants = [("tmem_staging=1", 1), ("tmem_staging=0", 0), ("tmem_staging=1 (again)", 1), ("tmem_staging=0 (again)", 0)]
 res = []
-for name, part, pf in variants:
-    llm.set_qkv_partials(part)
+for name, ts in variants:
+    lib.rd_linear_tmem_staging(ts)
+    llm._graphs = {}
     llm.generate(prompts, img_embeds=img, max_new_tokens=8, suppress_eos=True)
     best = 1e9
     for _ in range(2):
