@@ -19,6 +19,7 @@ LIB = os.path.join(LIBDIR, "libradialog_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcudafe", "--diag_suppress=177"]
+FLAGS += os.environ.get("RD_EXTRA_NVCC_FLAGS", "").split()        # development: tuning macros (-DRD_...) for A/B builds
 
 
 def sources():

@@ -21,13 +21,34 @@
 #include <stdlib.h>
 #include "common.cuh"
 
+// Tuning knobs of the decode tiles (compile-time; defaults = the measured best)
+#ifndef RD_DECODE_SMEM_KB
+#define RD_DECODE_SMEM_KB 0            // 0: 100 KB (108 KB gate|up) of pipeline smem per CTA -> two CTAs per SM
+#endif
+#ifndef RD_DECODE_MIN_CTAS
+#define RD_DECODE_MIN_CTAS 2           // __launch_bounds__ minimum CTAs per SM of the decode tiles (register cap)
+#endif
+#ifndef RD_TS_TMEM_COLS
+#define RD_TS_TMEM_COLS 256
+#endif
+#ifndef RD_TS_W_KB
+#define RD_TS_W_KB 64
+#endif
+#ifndef RD_TS_XST
+#define RD_TS_XST 8
+#endif
+#ifndef RD_TS_DEFAULT
+#define RD_TS_DEFAULT 1
+#endif
+
+
 bool rd_pdl_enabled();
 unsigned long long* rd_linear_trace_buffer();
 static int g_force_generic_epilogue = 0;   // test hook
 extern "C" int rd_linear_force_generic_epilogue(int on) { g_force_generic_epilogue = on; return RD_OK; }
 static int g_wide_epi = 1;        // test hook: 0 = direct (per-thread strided) epilogue also for wide token tiles
 extern "C" int rd_linear_wide_epilogue(int on) { g_wide_epi = on; return RD_OK; }
-static int g_ts_mode = 1;         // 1: decode tiles (M <= 32) park weight k-blocks in TMEM (A operand from tensor memory)
+static int g_ts_mode = RD_TS_DEFAULT;   // 1: decode tiles (M <= 32) park weight k-blocks in TMEM (A operand from tensor memory)
 extern "C" int rd_linear_tmem_staging(int on) { g_ts_mode = on; return RD_OK; }
 static int g_splitk_mode = 0;     // 0: cluster/DSMEM reduction when possible, 1: always the global workspace
 extern "C" int rd_linear_splitk_mode(int mode) { g_splitk_mode = mode; return RD_OK; }
@@ -233,7 +254,8 @@ template <int NT, bool SWIGLU> struct TcCfg {
   // weight stream runs, so the tail after the last MMA does not wait on global loads
   static constexpr bool STAGE_EPI = (NT <= 32) && !SWIGLU;
   static constexpr int EXTRA_BYTES = STAGE_EPI ? (NT * BLOCK_N * 2 + NT * 16 * 2) : 0;     // residual tile + lora_t tile
-  static constexpr int SMEM_BUDGET = (NT <= 64) ? (STAGE_EPI ? 100 * 1024 : 108 * 1024) : 200 * 1024;
+  static constexpr int SMEM_BUDGET = (NT <= 32 && RD_DECODE_SMEM_KB > 0) ? RD_DECODE_SMEM_KB * 1024
+                                     : (NT <= 64) ? (STAGE_EPI ? 100 * 1024 : 108 * 1024) : 200 * 1024;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = tmem_cols_for(ACCS * NT);
@@ -254,9 +276,9 @@ template <int NT, bool SWIGLU> struct TsCfg {
   static constexpr int ACCS = SWIGLU ? 2 : 1;
   static constexpr int W_STAGE = ACCS * BLOCK_N * BLOCK_K * 2;            // 16 KB (32 KB gate|up) per weight k-block
   static constexpr int X_STAGE = NT * BLOCK_K * 2;
-  static constexpr int WST = 64 * 1024 / W_STAGE;                         // shared-memory W ring: 64 KB
-  static constexpr int XST = 8;                                           // token-tile ring
-  static constexpr int TMEM_COLS = 256;                                   // two CTAs per SM share the 512 columns
+  static constexpr int WST = RD_TS_W_KB * 1024 / W_STAGE;                 // shared-memory W ring: 64 KB
+  static constexpr int XST = RD_TS_XST;                                   // token-tile ring
+  static constexpr int TMEM_COLS = RD_TS_TMEM_COLS;                       // two CTAs per SM share the 512 columns
   static constexpr int ACC_COLS = tmem_cols_for(ACCS * NT);
   static constexpr int SLOT_COLS = 32 * ACCS;                             // 64 K-elements of a 16-bit tile = 32 packed columns
   static constexpr int TSLOTS = (TMEM_COLS - ACC_COLS) / SLOT_COLS;       // 7 (3 for gate|up) weight k-blocks parked in TMEM
@@ -265,7 +287,7 @@ template <int NT, bool SWIGLU> struct TsCfg {
   static constexpr bool STAGE_EPI = (NT <= 32) && !SWIGLU;
   static constexpr int EXTRA_BYTES = STAGE_EPI ? (NT * BLOCK_N * 2 + NT * 16 * 2) : 640;
   static constexpr int SMEM_BYTES = RING_BYTES + 1024 + BAR_BYTES + EXTRA_BYTES;
-  static_assert(TSLOTS >= 2 && TSLOTS <= 8 && WST >= 2 && WST <= 8, "TMEM / smem ring sizes");
+  static constexpr bool OK = TSLOTS >= 2 && TSLOTS <= 8 && WST >= 2 && WST <= 8 && XST >= 2 && XST <= 8;
 };
 
 struct TcParams {
@@ -313,7 +335,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <class T, int NT, bool SWIGLU, bool TS = false>
-__global__ void __launch_bounds__(TC_THREADS, (NT <= 64) ? 2 : 1)
+__global__ void __launch_bounds__(TC_THREADS, (NT <= 32) ? RD_DECODE_MIN_CTAS : (NT <= 64) ? 2 : 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, T* __restrict__ out,
                  const TcParams p) {
   using Cfg = TcCfg<NT, SWIGLU>;
@@ -1005,7 +1027,7 @@ int resident_capacity(int cs) {
   if (cs < 1 || cs > 8) return 1;
   if (cache[cs]) return cache[cs];
   const int per_sm = (227 * 1024) / (Cfg::SMEM_BYTES + 1024);
-  const int model = per_sm >= 2 ? (284 / cs) * cs : (148 / cs) * cs;
+  const int model = per_sm >= 2 ? (284 / cs) * cs : (148 / cs) * cs;      // (3+ per SM by smem still counts as 2: registers / TMEM)
   if (getenv("RD_DEBUG_OCC")) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(148, 1, cs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -1137,7 +1159,7 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
   cfg.attrs = attr; cfg.numAttrs = na;
   if constexpr (NT <= 32) {
     // TMEM-staged variant: decode tiles with a plain / residual / SwiGLU epilogue (see TsCfg)
-    const bool ts = g_ts_mode && m_tiles == 1 && (p.epi_mode == EPI_PLAIN || p.epi_mode == EPI_RES1) && p.norm_ssq == nullptr &&
+    const bool ts = TsCfg<NT, SWIGLU>::OK && g_ts_mode && m_tiles == 1 && (p.epi_mode == EPI_PLAIN || p.epi_mode == EPI_RES1) && p.norm_ssq == nullptr &&
                     p.ssq_out == nullptr && kb_total / splits >= 2;
     if (ts) {
       using Ts = TsCfg<NT, SWIGLU>;
