@@ -3,6 +3,7 @@
 // per-step torch.cat at :209-212), device-resident generation state, one host call per decode step that is
 // CUDA-graph capturable.
 #include <algorithm>
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 #include "decode_mega.h"
@@ -364,7 +365,8 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     if (fuse && l > 0) {
       RD_CHECK(linear_fused(h, C_QKV, h->x, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &f_in1, st));
     } else {
-      { ProfScope ps(h, st, C_RMSNORM);
+      if (!(getenv("RD_DEBUG_SKIP_NORM") && q_len == 1 && l > 0)) {       // timing experiment only (wrong results): upper bound of norm fusion
+        ProfScope ps(h, st, C_RMSNORM);
         // decode: the norm kernels are latency bound and leave HBM idle -> they pull the next GEMM's weights into L2
         RD_CHECK(rd_rmsnorm_prefetch(h->x, w.ln1, h->xn, M, H, c.rms_eps, decode ? w.qkv : nullptr, decode ? std::min(qkv_bytes, h->pf_qkv) : 0, dt, st)); }
       if (qpart) {
@@ -403,7 +405,8 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
       RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, &f_out, st));
     } else {
       RD_CHECK(linear(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, st));
-      { ProfScope ps(h, st, C_RMSNORM);
+      if (!(getenv("RD_DEBUG_SKIP_NORM") && q_len == 1)) {
+        ProfScope ps(h, st, C_RMSNORM);
         RD_CHECK(rd_rmsnorm(h->x, w.ln2, h->xn, M, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
       rd_epilogue eg{};
       eg.act = RD_ACT_SWIGLU;

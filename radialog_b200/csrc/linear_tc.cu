@@ -38,7 +38,7 @@
 #define RD_TS_XST 8
 #endif
 #ifndef RD_TS_DEFAULT
-#define RD_TS_DEFAULT 1
+#define RD_TS_DEFAULT 0
 #endif
 
 
