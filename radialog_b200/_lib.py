@@ -73,6 +73,7 @@ SIGNATURES = {
     "rd_llm_set_streamk": (_i, [_p, _i]),
     "rd_llm_set_fused_norm": (_i, [_p, _i]),
     "rd_llm_set_qkv_partials": (_i, [_p, _i]),
+    "rd_llm_set_od_partials": (_i, [_p, _i]),
     "rd_llm_set_l2_prefetch": (_i, [_p, C.c_longlong, C.c_longlong, C.c_longlong]),
     "rd_llm_prefill": (_i, [_p, _p, _p, _i, _i, _p, _i, _p]),
     "rd_llm_truncate": (_i, [_p, _i, _p, _p]),

@@ -15,6 +15,7 @@ extern "C" int rd_attention_decode_partials(const float*, int, long long, int64_
                                             const uint8_t*, const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
 int rd_attention_bounded(const void*, int64_t, const void*, const void*, const uint8_t*, const int32_t*, int, void*, int, int, int, int, int, int, void*);
 int rd_kv_reorder(const void*, const void*, void*, void*, const int32_t*, const int32_t*, int, int, int, int, int, int64_t, int, void*);
+int rd_rmsnorm_partials(const float*, int, int64_t, void*, const void*, void*, int, int, float, int, void*);
 extern "C" int rd_rmsnorm_prefetch(const void*, const void*, void*, int, int, float, const void*, long long, int, void*);
 extern "C" int rd_attention_decode_set_l2_prefetch(const void*, long long, const void*, long long);
 extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const int32_t*, int, int, int, int, void*);
@@ -54,6 +55,13 @@ struct rd_llm {
   // single-token steps with B <= 32 (default ON): the QKV GEMM leaves its fp32 split-K partials in `qkv_part` and the attention
   // kernel sums them (fixed order, one rounding) when it reads q/k/v - no cross-CTA reduction pass in the GEMM's tail.
   int qkv_partials = 1;
+  // single-token steps with B <= 32 (default ON): o_proj and down_proj also leave fp32 split-K partials; the RMSNorm kernel that
+  // follows each of them sums the partials, adds the residual (x = T(x + T(Wx))) and normalises in the same launch - the GEMMs
+  // lose their cluster-reduction tail, the layer keeps its 7 launches.
+  int od_partials = 1;
+  bool xn_ready = false;         // the current step's last layer already produced xn = model.norm(x) for the lm_head
+  float* od_part = nullptr;
+  int64_t od_part_bytes = 0;
   float* qkv_part = nullptr;
   int64_t qkv_part_bytes = 0;
   // L2 weight prefetch from the norm / attention kernels: mechanism kept, OFF by default (A/B runs on B200 showed no
@@ -123,6 +131,8 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
   A((char**)&h->ssq, (H / 128 + 1) * 32 * 4);
   h->qkv_part_bytes = (int64_t)16 * 32 * (3 * H + 64) * 4;          // <= 16 splits x 32 tokens x (3H + 2r) fp32
   A((char**)&h->qkv_part, h->qkv_part_bytes);
+  h->od_part_bytes = (int64_t)16 * 32 * H * 4;                        // <= 16 splits x 32 tokens x H fp32
+  A((char**)&h->od_part, h->od_part_bytes);
   int64_t ws = 0;
   const int Ms[2] = {(int)Bm, 256};
   for (int mi = 0; mi < 2; ++mi) {
@@ -149,6 +159,7 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
   rd_sk_destroy(h->sk);
   if (h->ssq) cudaFree(h->ssq);
   if (h->qkv_part) cudaFree(h->qkv_part);
+  if (h->od_part) cudaFree(h->od_part);
   if (h->kc_alt) cudaFree(h->kc_alt);
   if (h->vc_alt) cudaFree(h->vc_alt);
   delete h;
@@ -345,6 +356,7 @@ static int linear_fused(rd_llm* h, int cls, const void* x, int64_t ldx, const vo
 static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStream_t st) {
   const rd_llm_config& c = h->c;
   const int H = c.hidden, I = c.inter, M = B * q_len, nh = c.heads, hd = H / nh, dt = c.dtype;
+  h->xn_ready = false;
   for (int l = 0; l < c.layers; ++l) {
     const LayerW& w = h->L[l];
     char* kc = h->kc + (int64_t)l * h->kv_layer_bytes;
@@ -361,11 +373,13 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     TcFuse f_out{nullptr, nullptr, 0, 0.f, h->ssq};
     // decode, B <= 32: QKV split-K partials go straight to the attention kernel (no reduction pass in the GEMM)
     const bool qpart = h->qkv_partials && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && (3 * H + R2) % 4 == 0;
+    // decode, B <= 32: o_proj / down_proj partials are finished by the norm kernel that follows them (see od_partials)
+    const bool odp = h->od_partials && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && H <= 8192 && H % 8 == 0;
     int qsplit[2] = {0, 0};
     if (fuse && l > 0) {
       RD_CHECK(linear_fused(h, C_QKV, h->x, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &f_in1, st));
     } else {
-      if (!(getenv("RD_DEBUG_SKIP_NORM") && q_len == 1 && l > 0)) {       // timing experiment only (wrong results): upper bound of norm fusion
+      if (!(odp && l > 0)) {      // with od partials the previous layer's down_proj + this norm ran as one launch already
         ProfScope ps(h, st, C_RMSNORM);
         // decode: the norm kernels are latency bound and leave HBM idle -> they pull the next GEMM's weights into L2
         RD_CHECK(rd_rmsnorm_prefetch(h->x, w.ln1, h->xn, M, H, c.rms_eps, decode ? w.qkv : nullptr, decode ? std::min(qkv_bytes, h->pf_qkv) : 0, dt, st)); }
@@ -403,10 +417,26 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
       eg.act = RD_ACT_SWIGLU;
       RD_CHECK(linear_fused(h, C_GATEUP, h->x, H, w.gate_up, H, h->mid, I, M, I, H, &eg, &f_in2, st));
       RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, &f_out, st));
+    } else if (odp) {
+      // o_proj partials -> [sum + residual + post_attention_layernorm] -> gate|up -> down_proj partials -> [sum + residual + the
+      // NEXT norm on the path: input_layernorm of layer l+1, or model.norm after the last layer (modeling_llama_imgemb.py:658)]
+      int sp[2] = {0, 0};
+      TcFuse to{};
+      to.part_out = h->od_part; to.part_bytes = h->od_part_bytes; to.splits_out = sp;
+      RD_CHECK(linear_fused(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, nullptr, &to, st));
+      { ProfScope ps(h, st, C_RMSNORM);
+        RD_CHECK(rd_rmsnorm_partials(h->od_part, sp[0], (int64_t)sp[1] * H, h->x, w.ln2, h->xn, M, H, c.rms_eps, dt, st)); }
+      rd_epilogue eg{};
+      eg.act = RD_ACT_SWIGLU;
+      RD_CHECK(linear(h, C_GATEUP, h->xn, H, w.gate_up, H, h->mid, I, M, I, H, &eg, st));
+      RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, nullptr, &to, st));
+      const void* next_w = (l + 1 < c.layers) ? h->L[l + 1].ln1 : h->final_norm;
+      { ProfScope ps(h, st, C_RMSNORM);
+        RD_CHECK(rd_rmsnorm_partials(h->od_part, sp[0], (int64_t)sp[1] * H, h->x, next_w, h->xn, M, H, c.rms_eps, dt, st)); }
+      if (l + 1 == c.layers) h->xn_ready = true;
     } else {
       RD_CHECK(linear(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, st));
-      if (!(getenv("RD_DEBUG_SKIP_NORM") && q_len == 1)) {
-        ProfScope ps(h, st, C_RMSNORM);
+      { ProfScope ps(h, st, C_RMSNORM);
         RD_CHECK(rd_rmsnorm(h->x, w.ln2, h->xn, M, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
       rd_epilogue eg{};
       eg.act = RD_ACT_SWIGLU;
@@ -435,7 +465,8 @@ static int head_and_select(rd_llm* h, int B, int q_len, void* all_logits, cudaSt
                                       (size_t)H * 2, B, cudaMemcpyDeviceToDevice, st));
       xin = h->xl;
     }
-    { ProfScope ps(h, st, C_RMSNORM);
+    if (!(q_len == 1 && h->xn_ready)) {       // (decode with od partials: the last down_proj's norm launch already applied model.norm)
+      ProfScope ps(h, st, C_RMSNORM);
       RD_CHECK(rd_rmsnorm(xin, h->final_norm, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
     RD_CHECK(linear(h, C_LMHEAD, h->xn, H, h->lm_head, H, h->logits, h->vpad, B, V, H, nullptr, st));
     logits = h->logits; ld = h->vpad;
@@ -523,6 +554,7 @@ extern "C" int rd_llm_decode_step(rd_llm* h, void* stream) {
   const rd_llm_config& c = h->c;
   { ProfScope ps(h, st, C_EMBED);
     RD_CHECK(rd_embed_splice(h->cur_tok, h->embed, nullptr, h->x, h->B, 1, c.hidden, c.vocab, c.dtype, st)); }
+  h->xn_ready = false;
   if (mega_wanted(h, h->B) && h->mega != nullptr) RD_CHECK(run_layers_mega(h, h->B, h->pos_cur, st));
   else if (sk_wanted(h, h->B) && h->sk != nullptr) RD_CHECK(run_layers_sk(h, h->B, h->pos_cur, st));
   else RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
@@ -546,6 +578,15 @@ extern "C" int rd_llm_set_mega(rd_llm* h, int on) {
 extern "C" int rd_llm_set_fused_norm(rd_llm* h, int on) {
   RD_REQUIRE(h, "rd_llm_set_fused_norm: null handle");
   h->fuse_norm = on ? 1 : 0;
+  return RD_OK;
+}
+
+// 1 (default): in single-token steps with B <= 32 o_proj / down_proj leave fp32 split-K partials and the norm kernel that follows
+// each of them sums the partials, adds the residual and normalises in one launch; 0: the GEMMs reduce over their cluster and add the
+// residual themselves, plain rmsnorm kernels follow.  Bit-identical either way.
+extern "C" int rd_llm_set_od_partials(rd_llm* h, int on) {
+  RD_REQUIRE(h, "rd_llm_set_od_partials: null handle");
+  h->od_partials = on ? 1 : 0;
   return RD_OK;
 }
 

@@ -111,6 +111,104 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
   }
 }
 
+// Split-K partials -> residual stream -> RMSNorm in one launch (decode, o_proj / down_proj).  The GEMM left its fp32 split-K
+// partials in part[splits][slab_rows][H]; this kernel finishes the projection the way the GEMM epilogue would -
+// x[m,:] = T(x[m,:] + T(sum over splits, split order)) - and applies the LlamaRMSNorm that follows in LlamaDecoderLayer.forward
+// (modeling_llama_imgemb.py:85-93,302-305; model.norm after the last layer) to the new row: xn = T(w * T(x * rstd)).
+// Same thread <-> element mapping and reduction tree as rmsnorm_kernel's register path, so xn is bit-identical to
+// "cluster split-K GEMM + rmsnorm_kernel".  One CTA per token row, H <= 8192.
+template <class T>
+__global__ void __launch_bounds__(256)
+rmsnorm_partials_kernel(const float* __restrict__ part, int splits, int64_t slab_stride, T* __restrict__ x, const T* __restrict__ w,
+                        T* __restrict__ out, int H, float eps) {
+  pdl_launch_dependents();
+  __shared__ float sred[8];
+  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Vec8<T> wv[4], xv[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { const int k = tid * 8 + u * 2048; if (k < H) wv[u] = ld16(w + k); }      // no dependency on the GEMM
+  pdl_wait();
+  T* xr = x + (int64_t)m * H;
+  const float* pr = part + (int64_t)m * H;
+  float acc[4][8];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = tid * 8 + u * 2048;
+    if (k < H) {
+      xv[u] = ld16(xr + k);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
+    }
+  }
+  for (int s0 = 0; s0 < splits; s0 += 4) {          // 4 splits x up to 4 column groups x 2 float4 = 32 independent L2 loads in flight
+    float4 v[4][4][2];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = tid * 8 + u * 2048;
+        if (s0 + s < splits && k < H) {
+          const float4* p4 = reinterpret_cast<const float4*>(pr + (int64_t)(s0 + s) * slab_stride + k);
+          v[s][u][0] = __ldcg(p4); v[s][u][1] = __ldcg(p4 + 1);
+        }
+      }
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = tid * 8 + u * 2048;
+        if (s0 + s < splits && k < H) {
+          acc[u][0] += v[s][u][0].x; acc[u][1] += v[s][u][0].y; acc[u][2] += v[s][u][0].z; acc[u][3] += v[s][u][0].w;
+          acc[u][4] += v[s][u][1].x; acc[u][5] += v[s][u][1].y; acc[u][6] += v[s][u][1].z; acc[u][7] += v[s][u][1].w;
+        }
+      }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = tid * 8 + u * 2048;
+    if (k < H) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xv[u].v[e] = Tr<T>::r(Tr<T>::f(xv[u].v[e]) + Tr<T>::rr(acc[u][e]));       // residual + T(Wx), rounded: the new residual stream
+        const float f = Tr<T>::f(xv[u].v[e]);
+        ss = fmaf(f, f, ss);
+      }
+      *reinterpret_cast<uint4*>(xr + k) = *reinterpret_cast<const uint4*>(&xv[u]);
+    }
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) sred[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += sred[i];
+  const float rs = 1.0f / sqrtf(tot / (float)H + eps);       // torch.rsqrt(variance + eps), fp32
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = tid * 8 + u * 2048;
+    if (k < H) {
+      Vec8<T> o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float y = Tr<T>::rr(Tr<T>::f(xv[u].v[e]) * rs);          // .to(weight.dtype)
+        o.v[e] = Tr<T>::r(Tr<T>::f(wv[u].v[e]) * y);                   // weight * hidden_states
+      }
+      *reinterpret_cast<uint4*>(out + (int64_t)m * H + k) = *reinterpret_cast<uint4*>(&o);
+    }
+  }
+}
+
+int rd_rmsnorm_partials(const float* part, int splits, int64_t slab_stride, void* x, const void* w, void* out, int M, int H, float eps,
+                        int dtype, void* stream) {
+  RD_REQUIRE(M > 0 && H > 0 && H % 8 == 0 && H <= 8192 && splits >= 1, "rd_rmsnorm_partials: bad shape M=%d H=%d splits=%d", M, H, splits);
+  RD_DISPATCH_DTYPE(dtype, T, {
+    RD_CHECK_CUDA(rd_launch(rmsnorm_partials_kernel<T>, dim3(M), dim3(256), 0, (cudaStream_t)stream, rd_pdl_enabled(), part, splits, slab_stride,
+                            (T*)x, (const T*)w, (T*)out, H, eps));
+    return RD_OK;
+  });
+}
+
 static int rmsnorm_impl(const void* x, const void* w, void* out, int M, int H, float eps, const void* lora_a,
                         int lora_rows, void* lora_t, const void* pf_ptr, long long pf_bytes, int dtype, void* stream) {
   RD_REQUIRE(M > 0 && H > 0 && H % 8 == 0, "rd_rmsnorm: bad shape M=%d H=%d", M, H);

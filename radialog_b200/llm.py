@@ -155,6 +155,7 @@ class LlamaForCausalLM:
         self.fused_norm = False   # RMSNorm inside the decode GEMMs (experimental)
         self.streamk = False  # stream-K decode GEMMs with fused RMSNorm (experimental)
         self.qkv_partials = True  # QKV GEMM hands its fp32 split-K partials to the attention kernel (default)
+        self.od_partials = True   # o_proj / down_proj partials finished by the norm launch that follows them (default)
         self.use_cuda_graph = True
         self.last_stats: Dict[str, float] = {}
 
@@ -339,6 +340,7 @@ class LlamaForCausalLM:
         _lib.check(self._lib.rd_llm_set_streamk(h, 1 if self.streamk else 0), "set_streamk")
         _lib.check(self._lib.rd_llm_set_fused_norm(h, 1 if self.fused_norm else 0), "set_fused_norm")
         _lib.check(self._lib.rd_llm_set_qkv_partials(h, 1 if self.qkv_partials else 0), "set_qkv_partials")
+        _lib.check(self._lib.rd_llm_set_od_partials(h, 1 if self.od_partials else 0), "set_od_partials")
 
     def _bind_img_proj(self):
         lin = self.model.img_proj_layer
@@ -363,6 +365,14 @@ class LlamaForCausalLM:
         self._graphs = {}
         if self._h is not None:
             _lib.check(self._lib.rd_llm_set_fused_norm(self._h, 1 if on else 0), "set_fused_norm")
+
+    def set_od_partials(self, on: bool):
+        """Single-token steps: o_proj / down_proj leave fp32 split-K partials and the norm launch that follows sums them, adds the
+        residual and normalises (default), or the GEMMs reduce over their cluster and plain norm kernels follow."""
+        self.od_partials = bool(on)
+        self._graphs = {}
+        if self._h is not None:
+            _lib.check(self._lib.rd_llm_set_od_partials(self._h, 1 if on else 0), "set_od_partials")
 
     def set_qkv_partials(self, on: bool):
         """Single-token steps: the QKV GEMM leaves fp32 split-K partials for the attention kernel to sum (default), or reduces

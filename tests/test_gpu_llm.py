@@ -329,3 +329,32 @@ def test_qkv_partials_to_attention_bit_identical_to_gemm_side_reduction(cuda_dev
             assert torch.equal(o.scores[s], ref.scores[s]), f"step {s} logits not bit-identical for (partials, graph) = {key}"
     o_ids, o_scores = orc.generate(prompts, img, n_new, suppress_eos=True, return_scores=True)
     assert_ids_match(ref.sequences.cpu(), o_ids, o_scores, prompts.shape[1], dtype, f"qkv partials {dtype_name} B={B}", min_exact_rows=0.75)
+
+
+@pytest.mark.parametrize("dtype_name,B,layers", [("float16", 3, 2), ("bfloat16", 32, 3), ("float16", 1, 2), ("bfloat16", 17, 2), ("float16", 32, 4)])
+def test_od_partials_finished_by_norm_kernel_bit_identical(cuda_dev, dtype_name, B, layers):
+    """Default decode path (o_proj / down_proj leave fp32 split-K partials; the norm launch that follows sums them in split
+    order, adds the residual and normalises - model.norm after the last layer included) against cluster-reduced GEMMs with
+    residual epilogues + plain norm kernels: same partials, same order, same rounding points and the same reduction tree in
+    the norm, so every logit must be BIT-identical, eager and under CUDA-graph replay."""
+    dtype = DT[dtype_name]
+    cfg = synth.tiny_llama_cfg(num_hidden_layers=layers)
+    model, orc, _ = build(cfg, dtype, cuda_dev)
+    prompts = synth.make_prompts(B, seed=499 + B, ragged=True)
+    img = img_tokens(B, cfg, seed=B + 4)
+    n_new = 9
+    outs = {}
+    for part in (False, True):
+        model.set_od_partials(part)
+        for graph in (False, True):
+            model.use_cuda_graph = graph
+            outs[(part, graph)] = model.generate(prompts.to(cuda_dev), img_embeds=img.to(cuda_dev), max_new_tokens=n_new, suppress_eos=True,
+                                                 return_dict_in_generate=True, output_scores=True)
+    model.set_od_partials(True)
+    ref = outs[(False, False)]
+    for key, o in outs.items():
+        assert torch.equal(o.sequences, ref.sequences), f"ids differ for (od_partials, graph) = {key}"
+        for s in range(n_new):
+            assert torch.equal(o.scores[s], ref.scores[s]), f"step {s} logits not bit-identical for (od_partials, graph) = {key}"
+    o_ids, o_scores = orc.generate(prompts, img, n_new, suppress_eos=True, return_scores=True)
+    assert_ids_match(ref.sequences.cpu(), o_ids, o_scores, prompts.shape[1], dtype, f"od partials {dtype_name} B={B}", min_exact_rows=0.7)

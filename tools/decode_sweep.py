@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Decode-step time (CUDA graph + PDL, the bench configuration) of the full Vicuna-7B-sized engine under engine switches
-(development tool): TMEM weight staging on/off.  python tools/decode_sweep.py [B] [NEW]"""
+(development tool): o_proj / down_proj partials finished by the norm launch on/off.  python tools/decode_sweep.py [B] [NEW]"""
 import json
 import os
 import sys
@@ -25,11 +25,10 @@ torch.cuda.empty_cache()
 prompts = synth.make_prompts(B, seed=4321).to(dev)
 img = torch.randn(B, 32, 768, device=dev) * 0.5
 MB = 1 << 20
-variants = [("tmem_staging=1", 1), ("tmem_staging=0", 0), ("tmem_staging=1 (again)", 1), ("tmem_staging=0 (again)", 0)]
+variants = [("od_partials=1", 1), ("od_partials=0", 0), ("od_partials=1 (again)", 1), ("od_partials=0 (again)", 0)]
 res = []
 for name, ts in variants:
-    lib.rd_linear_tmem_staging(ts)
-    llm._graphs = {}
+    llm.set_od_partials(bool(ts))
     llm.generate(prompts, img_embeds=img, max_new_tokens=8, suppress_eos=True)
     best = 1e9
     for _ in range(2):
