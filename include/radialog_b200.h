@@ -205,7 +205,8 @@ int rd_llm_set_qkv_partials(rd_llm* h, int on);
 /* Single-token steps with B <= 32 (default ON): o_proj and down_proj (modeling_llama_imgemb.py:245,159) leave their fp32 split-K
  * partials in an L2-resident slab; the norm launch that follows each of them sums the partials in split order, adds the residual
  * (x = T(x + T(Wx)), :302,308) and applies the next LlamaRMSNorm (:305; input_layernorm of the next layer :287; model.norm :658).
- * The GEMMs lose their cross-CTA reduction tail; bit-identical to the cluster reduction + rd_rmsnorm.  0 switches it off.   */
+ * The GEMMs lose their cross-CTA reduction tail.  Same rounding points as the cluster reduction + rd_rmsnorm (only the fp32
+ * order of the norm's sum of squares differs: a token row is split over a 4-CTA cluster).  0 switches it off.                */
 int rd_llm_set_od_partials(rd_llm* h, int on);
 /* Decode step: bytes of W_qkv / W_o / W_gate|up that the (latency-bound, HBM-idle) norm and attention kernels pull into
  * the 126 MB L2 with cp.async.bulk.prefetch ahead of the GEMM that streams them; 0,0,0 turns it off. */

@@ -374,7 +374,7 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     // decode, B <= 32: QKV split-K partials go straight to the attention kernel (no reduction pass in the GEMM)
     const bool qpart = h->qkv_partials && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && (3 * H + R2) % 4 == 0;
     // decode, B <= 32: o_proj / down_proj partials are finished by the norm kernel that follows them (see od_partials)
-    const bool odp = h->od_partials && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && H <= 8192 && H % 8 == 0;
+    const bool odp = h->od_partials && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && H <= 16384 && H % 32 == 0;
     int qsplit[2] = {0, 0};
     if (fuse && l > 0) {
       RD_CHECK(linear_fused(h, C_QKV, h->x, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &f_in1, st));
@@ -583,7 +583,7 @@ extern "C" int rd_llm_set_fused_norm(rd_llm* h, int on) {
 
 // 1 (default): in single-token steps with B <= 32 o_proj / down_proj leave fp32 split-K partials and the norm kernel that follows
 // each of them sums the partials, adds the residual and normalises in one launch; 0: the GEMMs reduce over their cluster and add the
-// residual themselves, plain rmsnorm kernels follow.  Bit-identical either way.
+// residual themselves, plain rmsnorm kernels follow.  Same rounding points either way.
 extern "C" int rd_llm_set_od_partials(rd_llm* h, int on) {
   RD_REQUIRE(h, "rd_llm_set_od_partials: null handle");
   h->od_partials = on ? 1 : 0;

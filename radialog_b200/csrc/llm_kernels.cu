@@ -115,96 +115,111 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
 // partials in part[splits][slab_rows][H]; this kernel finishes the projection the way the GEMM epilogue would -
 // x[m,:] = T(x[m,:] + T(sum over splits, split order)) - and applies the LlamaRMSNorm that follows in LlamaDecoderLayer.forward
 // (modeling_llama_imgemb.py:85-93,302-305; model.norm after the last layer) to the new row: xn = T(w * T(x * rstd)).
-// Same thread <-> element mapping and reduction tree as rmsnorm_kernel's register path, so xn is bit-identical to
-// "cluster split-K GEMM + rmsnorm_kernel".  One CTA per token row, H <= 8192.
+// A token row is split over a thread-block cluster of 4 CTAs (a row's partials are 8 x 16 KB of L2 reads: one SM's ~100 GB/s
+// of L2 ingest would make it the slowest kernel of the layer); the four quarter sums of squares meet over distributed shared
+// memory in rank order.  Same rounding points as rd_rmsnorm; only the fp32 order of the sum of squares differs.
+constexpr int RNP_CL = 4, RNP_THREADS = 128, RNP_MAXG = 4;
+
+__device__ __forceinline__ float rnp_ld_dsmem(const float* local, uint32_t rank) {
+  uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
+  return v;
+}
+
 template <class T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RNP_THREADS)
 rmsnorm_partials_kernel(const float* __restrict__ part, int splits, int64_t slab_stride, T* __restrict__ x, const T* __restrict__ w,
                         T* __restrict__ out, int H, float eps) {
   pdl_launch_dependents();
-  __shared__ float sred[8];
-  const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  Vec8<T> wv[4], xv[4];
+  __shared__ float swarp[RNP_THREADS / 32];
+  __shared__ float s_part;
+  const int c = blockIdx.x, m = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Hq = H / RNP_CL, groups = Hq / 8;
+  const int col0 = c * Hq;
+  Vec8<T> wv[RNP_MAXG], xv[RNP_MAXG];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) { const int k = tid * 8 + u * 2048; if (k < H) wv[u] = ld16(w + k); }      // no dependency on the GEMM
+  for (int u = 0; u < RNP_MAXG; ++u) { const int g = tid + u * RNP_THREADS; if (g < groups) wv[u] = ld16(w + col0 + g * 8); }      // no dependency on the GEMM
   pdl_wait();
-  T* xr = x + (int64_t)m * H;
-  const float* pr = part + (int64_t)m * H;
-  float acc[4][8];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int k = tid * 8 + u * 2048;
-    if (k < H) {
-      xv[u] = ld16(xr + k);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
-    }
-  }
-  for (int s0 = 0; s0 < splits; s0 += 4) {          // 4 splits x up to 4 column groups x 2 float4 = 32 independent L2 loads in flight
-    float4 v[4][4][2];
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = tid * 8 + u * 2048;
-        if (s0 + s < splits && k < H) {
-          const float4* p4 = reinterpret_cast<const float4*>(pr + (int64_t)(s0 + s) * slab_stride + k);
-          v[s][u][0] = __ldcg(p4); v[s][u][1] = __ldcg(p4 + 1);
-        }
-      }
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = tid * 8 + u * 2048;
-        if (s0 + s < splits && k < H) {
-          acc[u][0] += v[s][u][0].x; acc[u][1] += v[s][u][0].y; acc[u][2] += v[s][u][0].z; acc[u][3] += v[s][u][0].w;
-          acc[u][4] += v[s][u][1].x; acc[u][5] += v[s][u][1].y; acc[u][6] += v[s][u][1].z; acc[u][7] += v[s][u][1].w;
-        }
-      }
-  }
+  T* xr = x + (int64_t)m * H + col0;
+  const float* pr = part + (int64_t)m * H + col0;
   float ss = 0.f;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int k = tid * 8 + u * 2048;
-    if (k < H) {
+  for (int u = 0; u < RNP_MAXG; ++u) {
+    const int g = tid + u * RNP_THREADS;
+    if (g < groups) {
+      xv[u] = ld16(xr + g * 8);
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s0 = 0; s0 < splits; s0 += 8) {            // 16 independent 16-byte L2 loads in flight per thread
+        float4 v[8][2];
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s0 + s < splits) {
+            const float4* p4 = reinterpret_cast<const float4*>(pr + (int64_t)(s0 + s) * slab_stride + g * 8);
+            v[s][0] = __ldcg(p4); v[s][1] = __ldcg(p4 + 1);
+          }
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s0 + s < splits) {
+            acc[0] += v[s][0].x; acc[1] += v[s][0].y; acc[2] += v[s][0].z; acc[3] += v[s][0].w;
+            acc[4] += v[s][1].x; acc[5] += v[s][1].y; acc[6] += v[s][1].z; acc[7] += v[s][1].w;
+          }
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        xv[u].v[e] = Tr<T>::r(Tr<T>::f(xv[u].v[e]) + Tr<T>::rr(acc[u][e]));       // residual + T(Wx), rounded: the new residual stream
+        xv[u].v[e] = Tr<T>::r(Tr<T>::f(xv[u].v[e]) + Tr<T>::rr(acc[e]));       // residual + T(Wx), rounded: the new residual stream
         const float f = Tr<T>::f(xv[u].v[e]);
         ss = fmaf(f, f, ss);
       }
-      *reinterpret_cast<uint4*>(xr + k) = *reinterpret_cast<const uint4*>(&xv[u]);
+      *reinterpret_cast<uint4*>(xr + g * 8) = *reinterpret_cast<const uint4*>(&xv[u]);
     }
   }
   ss = warp_sum(ss);
-  if (lane == 0) sred[warp] = ss;
+  if (lane == 0) swarp[warp] = ss;
   __syncthreads();
+  if (tid == 0) s_part = ((swarp[0] + swarp[1]) + swarp[2]) + swarp[3];
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   float tot = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) tot += sred[i];
+  for (int r = 0; r < RNP_CL; ++r) tot += rnp_ld_dsmem(&s_part, (uint32_t)r);        // rank order: the same total in all four CTAs
   const float rs = 1.0f / sqrtf(tot / (float)H + eps);       // torch.rsqrt(variance + eps), fp32
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int k = tid * 8 + u * 2048;
-    if (k < H) {
+  for (int u = 0; u < RNP_MAXG; ++u) {
+    const int g = tid + u * RNP_THREADS;
+    if (g < groups) {
       Vec8<T> o;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float y = Tr<T>::rr(Tr<T>::f(xv[u].v[e]) * rs);          // .to(weight.dtype)
         o.v[e] = Tr<T>::r(Tr<T>::f(wv[u].v[e]) * y);                   // weight * hidden_states
       }
-      *reinterpret_cast<uint4*>(out + (int64_t)m * H + k) = *reinterpret_cast<uint4*>(&o);
+      *reinterpret_cast<uint4*>(out + (int64_t)m * H + col0 + g * 8) = *reinterpret_cast<uint4*>(&o);
     }
   }
+  // nobody leaves (and frees its shared memory) while a peer may still be reading its quarter sum
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 int rd_rmsnorm_partials(const float* part, int splits, int64_t slab_stride, void* x, const void* w, void* out, int M, int H, float eps,
                         int dtype, void* stream) {
-  RD_REQUIRE(M > 0 && H > 0 && H % 8 == 0 && H <= 8192 && splits >= 1, "rd_rmsnorm_partials: bad shape M=%d H=%d splits=%d", M, H, splits);
+  RD_REQUIRE(M > 0 && H > 0 && H % (8 * RNP_CL) == 0 && H <= 8 * RNP_CL * RNP_THREADS * RNP_MAXG && splits >= 1,
+             "rd_rmsnorm_partials: bad shape M=%d H=%d splits=%d", M, H, splits);
   RD_DISPATCH_DTYPE(dtype, T, {
-    RD_CHECK_CUDA(rd_launch(rmsnorm_partials_kernel<T>, dim3(M), dim3(256), 0, (cudaStream_t)stream, rd_pdl_enabled(), part, splits, slab_stride,
-                            (T*)x, (const T*)w, (T*)out, H, eps));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(RNP_CL, M); cfg.blockDim = dim3(RNP_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = RNP_CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (rd_pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, rmsnorm_partials_kernel<T>, part, splits, slab_stride, (T*)x, (const T*)w, (T*)out, H, eps));
     return RD_OK;
   });
 }
