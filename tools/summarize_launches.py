@@ -44,9 +44,15 @@ idx_stem = [i for i, x in enumerate(recs) if "stem_im2col" in x[0]]
 out = [f"# ncu launch list summary ({src})", "",
        "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --steps 1 --warmup 1 --new-tokens 4` "
        "(B=32 per GPU, bf16).  Per-launch times are cold-cache and serialised: compare SHARES, not absolutes."]
-# the timed step = 2nd vision pass (warm-up is the first)
-s0 = idx_stem[1]
-p0 = [i for i in idx_prep if i > s0][0]
+# the last vision pass that is followed by a complete prefill + two decode steps inside the capture window
+s0 = p0 = None
+for cand in reversed(idx_stem):
+    nxt = [i for i in idx_prep if i > cand]
+    if nxt and len([i for i in idx_arg if i > nxt[0]]) >= 3:
+        s0, p0 = cand, nxt[0]
+        break
+if s0 is None:
+    sys.exit("no complete vision -> prefill -> decode sequence in the launch list")
 a0 = [i for i in idx_arg if i > p0][0]
 table(recs[s0:p0], "vision (ResNet-50 + Q-Former), B=32", out)
 table(recs[p0:a0 + 1], "prefill, B=32 x T=64", out)
