@@ -312,6 +312,7 @@ struct TcParams {
   // the splits in fixed order and applies the single rounding T(Wx) when it reads q/k/v.
   float* part_out;
   int m_fast;                  // grid is (m_tiles, n_tiles, splits) instead of (n_tiles, m_tiles, splits)
+  int stages;                  // smem pipeline stages of this launch (2 .. TcCfg::STAGES)
   int wide_epi;                // NT >= 64: transposed epilogue through shared memory (coalesced residual loads / stores)
   EpiParams epi;
 };
@@ -340,8 +341,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
                  const TcParams p) {
   using Cfg = TcCfg<NT, SWIGLU>;
   using Ts = TsCfg<(NT <= 32 ? NT : 32), SWIGLU>;
-  constexpr int STAGES = Cfg::STAGES;
-  constexpr int RING_BYTES = TS ? Ts::RING_BYTES : STAGES * Cfg::STAGE_BYTES;
+  // pipeline depth is a launch parameter (<= Cfg::STAGES): a GEMM with one or two k-blocks per CTA (the layer-1 convolutions:
+  // K = 64) asks for one or two stages' worth of shared memory, so several of its latency-bound CTAs fit on an SM
+  const int STAGES = TS ? 1 : p.stages;
+  const int RING_BYTES = TS ? Ts::RING_BYTES : STAGES * Cfg::STAGE_BYTES;
   constexpr int BAR_BYTES = TS ? Ts::BAR_BYTES : 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1014,7 +1017,12 @@ int encode_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, i
   return RD_OK;
 }
 
-int pick_nt(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256; }
+// token-tile width.  Many tokens but only one or two k-blocks (the 1x1 convolutions of ResNet layer1/2, K = 64 / 128): such a CTA
+// is all prologue + epilogue, so it gets the 128-token tile whose parked epilogue tile (64 KB) lets two CTAs share an SM.
+int pick_nt(int M, int K) {
+  if (M > 128 && K <= 2 * BLOCK_K) return 128;
+  return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+}
 
 // Max CTAs of the decode-tile kernel that are co-resident when launched as clusters of (1,1,cs).  Measured on B200
 // (ncu launch__cluster_max_active with two ~110 KB CTAs per SM: 71 clusters of 4 = 284 CTAs; timing sweeps agree:
@@ -1140,10 +1148,22 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
     p.ws_ctr = reinterpret_cast<uint32_t*>(ws);                                   // counters first (zero-initialised by the owner)
     p.ws_part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ((int64_t)n_tiles * m_tiles * 4 + 255) / 256 * 256);
   }
+  // pipeline depth: no deeper than the k-blocks a CTA owns, no shallower than what the epilogue needs to park its tile in
+  {
+    const int kb_cta = (kb_total + splits - 1) / splits;
+    int st_n = kb_cta < 2 ? 2 : kb_cta;
+    int64_t park = 0;
+    if (use_cluster) park = (int64_t)Cfg::ACCS * NT * BLOCK_N * 4;
+    if (p.wide_epi) park = (int64_t)NT * BLOCK_N * 4;
+    const int st_park = (int)((park + Cfg::STAGE_BYTES - 1) / Cfg::STAGE_BYTES);
+    if (st_n < st_park) st_n = st_park;
+    p.stages = st_n > Cfg::STAGES ? Cfg::STAGES : st_n;
+  }
+  const int smem_bytes = Cfg::SMEM_BYTES - (Cfg::STAGES - p.stages) * Cfg::STAGE_BYTES;
   // the operand that is larger in HBM should be the one consecutive CTAs share (see the kernel's raster-order note)
   p.m_fast = (m_tiles > 1 && splits == 1 && !p.cluster && (int64_t)(SWIGLU ? 2 : 1) * N > (int64_t)M) ? 1 : 0;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = p.m_fast ? dim3(m_tiles, n_tiles, splits) : dim3(n_tiles, m_tiles, splits); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = p.m_fast ? dim3(m_tiles, n_tiles, splits) : dim3(n_tiles, m_tiles, splits); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
   if (rd_pdl_enabled()) {
@@ -1200,7 +1220,7 @@ static int g_force_splits = 0;   // test hook: 0 = heuristic
 extern "C" int rd_linear_force_splits(int s) { g_force_splits = s; return RD_OK; }
 
 int64_t rd_linear_tc_workspace_bytes(int M, int N, int K) {
-  const int nt = pick_nt(M);
+  const int nt = pick_nt(M, K);
   const int64_t n_tiles = (N + BLOCK_N - 1) / BLOCK_N, m_tiles = (M + nt - 1) / nt;
   const int64_t splits = 16;      // upper bound of pick_splits / the test hook
   return (n_tiles * m_tiles * 4 + 255) / 256 * 256 + splits * n_tiles * m_tiles * 2 * nt * BLOCK_N * 4 + 256;
@@ -1216,7 +1236,7 @@ int rd_linear_tc_fused(const void* x, int64_t ldx, const void* w, int64_t ldw, v
 
 int rd_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
                  const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  const int nt = pick_nt(M);
+  const int nt = pick_nt(M, K);
   const int splits = g_force_splits > 0 ? g_force_splits : 0;     // 0: chosen per kernel variant from its occupancy
   const bool sw = epi.act == RD_ACT_SWIGLU;
   RD_DISPATCH_DTYPE(dtype, T, {
