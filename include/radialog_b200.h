@@ -80,11 +80,21 @@ int rd_linear_force_splits(int splits);
 /* Split-K reduction: 0 (default) thread-block cluster + distributed shared memory when splits <= 8, 1 always through
  * the global fp32 workspace.  Both reduce in fixed split order (deterministic). */
 int rd_linear_splitk_mode(int mode);
-/* Decode tiles (M <= 32 tokens): 1 (default) parks the weight k-blocks in tensor memory - the epilogue warps copy every weight
+/* Decode tiles (M <= 32 tokens): 1 parks the weight k-blocks in tensor memory - the epilogue warps copy every weight
  * tile that lands in shared memory into a ring of TMEM slots (tcgen05.st) and tcgen05.mma reads its A operand from TMEM - so a
- * CTA buffers ~1.8x more weight bytes ahead of the activations it depends on; 0 = both operands from shared memory.  Same
+ * CTA buffers ~1.8x more weight bytes ahead of the activations it depends on; 0 (default: measured no faster) = both operands
+ * from shared memory.  Same
  * products, same accumulation order: bit-identical results. */
 int rd_linear_tmem_staging(int on);
+/* Wide token counts (M > 128: prefill, convolutions, Q-Former image side): 1 (default) runs GEMMs with at least
+ * rd_linear_wide_min_tiles (default 149 = more tiles than SMs) output tiles on the persistent kernel of linear_wide.cu - one CTA
+ * per SM walks the tiles, two TMEM accumulator buffers so the epilogue of tile i (TMA residual load / TMA store) overlaps the
+ * MMAs of tile i+1; 0 keeps every shape on the one-tile-per-CTA kernel.  Bit-identical results either way.
+ * rd_linear_wide_force_nt: token-tile width of that kernel (multiple of 16, 128..256; 0 = chosen to minimise round quantisation). */
+int rd_linear_wide_persistent(int on);
+int rd_linear_wide_min_tiles(int n);
+int rd_linear_wide_force_nt(int nt);
+int rd_linear_wide_force_stages(int stages);   /* 2..4 pipeline stages (the rest of the 224 KB holds epilogue chunk buffers); 0 = by K */
 /* Launch every kernel with the programmatic-dependent-launch attribute (prologue of kernel N+1 — barrier init, TMEM
  * allocation, the first weight tiles — overlaps the tail of kernel N).  On by default; 0 switches it off. */
 int rd_set_pdl(int on);

@@ -967,54 +967,64 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
-int encode_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int box_rows, int dtype);
-
 // cuTensorMapEncodeTiled costs a few microseconds of host time; a step re-uses the same few hundred (pointer, shape) pairs
 // (weights, the engine's activation buffers), so the encoded descriptors are kept in a small open-addressing cache.
-struct MapKey { const void* ptr; int64_t ld; int rows, K, box_rows, dtype; };
+// Two kinds of 2-D map over a row-major [rows, cols] 16-bit matrix: swizzle128 = 1 is the K-major UMMA operand (box of
+// 64 columns = one 128-byte swizzle row), swizzle128 = 0 a dense box (epilogue tiles: TMA store / residual load).
+struct MapKey { const void* ptr; int64_t ld; int rows, cols, box_rows, box_cols, dtype, swz; };
 struct MapSlot { MapKey k; CUtensorMap m; bool used; };
 constexpr int MAP_CACHE = 4096;
 
-int make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int box_rows, int dtype) {
+int encode_map(CUtensorMap* map, const MapKey& k) {
+  PFN_encodeTiled enc = get_encode();
+  RD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t gdim[2] = {(cuuint64_t)k.cols, (cuuint64_t)k.rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)k.ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)k.box_cols, (cuuint32_t)k.box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, k.dtype == RD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(k.ptr),
+                   gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, k.swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) ptr=%p ld=%lld rows=%d cols=%d box=%dx%d", (int)r, k.ptr, (long long)k.ld,
+             k.rows, k.cols, k.box_rows, k.box_cols);
+  return RD_OK;
+}
+
+int make_map_ex(CUtensorMap* map, const MapKey& key) {
   static thread_local MapSlot* cache = nullptr;
   if (cache == nullptr) cache = static_cast<MapSlot*>(calloc(MAP_CACHE, sizeof(MapSlot)));
-  if (cache == nullptr) return encode_map(map, ptr, ld, rows, K, box_rows, dtype);
-  uint64_t hsh = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull ^ ((uint64_t)ld << 32) ^ ((uint64_t)rows << 17) ^ ((uint64_t)K << 3) ^ (uint64_t)box_rows ^ ((uint64_t)dtype << 60);
+  if (cache == nullptr) return encode_map(map, key);
+  uint64_t hsh = (uint64_t)(uintptr_t)key.ptr * 0x9E3779B97F4A7C15ull ^ ((uint64_t)key.ld << 32) ^ ((uint64_t)key.rows << 17) ^ ((uint64_t)key.cols << 3) ^
+                 (uint64_t)key.box_rows ^ ((uint64_t)key.box_cols << 9) ^ ((uint64_t)key.dtype << 60) ^ ((uint64_t)key.swz << 59);
   hsh ^= hsh >> 29;
+  auto same = [&](const MapKey& a) {
+    return a.ptr == key.ptr && a.ld == key.ld && a.rows == key.rows && a.cols == key.cols && a.box_rows == key.box_rows &&
+           a.box_cols == key.box_cols && a.dtype == key.dtype && a.swz == key.swz;
+  };
   for (int probe = 0; probe < 8; ++probe) {
     MapSlot& sl = cache[(hsh + probe) & (MAP_CACHE - 1)];
-    if (sl.used && sl.k.ptr == ptr && sl.k.ld == ld && sl.k.rows == rows && sl.k.K == K && sl.k.box_rows == box_rows && sl.k.dtype == dtype) {
+    if (sl.used && same(sl.k)) {
       *map = sl.m;
       return RD_OK;
     }
     if (!sl.used) {
-      RD_CHECK(encode_map(&sl.m, ptr, ld, rows, K, box_rows, dtype));
-      sl.k = MapKey{ptr, ld, rows, K, box_rows, dtype};
+      RD_CHECK(encode_map(&sl.m, key));
+      sl.k = key;
       sl.used = true;
       *map = sl.m;
       return RD_OK;
     }
   }
   MapSlot& sl = cache[hsh & (MAP_CACHE - 1)];                         // neighbourhood full: overwrite the home slot
-  RD_CHECK(encode_map(&sl.m, ptr, ld, rows, K, box_rows, dtype));
-  sl.k = MapKey{ptr, ld, rows, K, box_rows, dtype};
+  RD_CHECK(encode_map(&sl.m, key));
+  sl.k = key;
   sl.used = true;
   *map = sl.m;
   return RD_OK;
 }
 
-int encode_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int box_rows, int dtype) {
-  PFN_encodeTiled enc = get_encode();
-  RD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, dtype == RD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
-                   gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) ptr=%p ld=%lld rows=%d K=%d box=%d", (int)r, ptr, (long long)ld, rows, K, box_rows);
-  return RD_OK;
+int make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int box_rows, int dtype) {
+  return make_map_ex(map, MapKey{ptr, ld, rows, K, box_rows, BLOCK_K, dtype, 1});
 }
 
 // token-tile width.  Many tokens but only one or two k-blocks (the 1x1 convolutions of ResNet layer1/2, K = 64 / 128): such a CTA
@@ -1234,8 +1244,20 @@ int rd_linear_tc_fused(const void* x, int64_t ldx, const void* w, int64_t ldw, v
   return r;
 }
 
+int rd_tc_make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int cols, int box_rows, int box_cols, int dtype, int swizzle128) {
+  return make_map_ex(map, MapKey{ptr, ld, rows, cols, box_rows, box_cols, dtype, swizzle128 ? 1 : 0});
+}
+
+int rd_linear_wide_try(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
+                       const EpiParams& epi, int dtype, cudaStream_t st);
+
 int rd_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
                  const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  if (g_fuse == nullptr && g_force_splits <= 0 && !g_force_generic_epilogue) {
+    // wide token counts with enough tiles to overlap: the persistent kernel (linear_wide.cu)
+    const int r = rd_linear_wide_try(x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, st);
+    if (r != 0) return r < 0 ? r : RD_OK;
+  }
   const int nt = pick_nt(M, K);
   const int splits = g_force_splits > 0 ? g_force_splits : 0;     // 0: chosen per kernel variant from its occupancy
   const bool sw = epi.act == RD_ACT_SWIGLU;

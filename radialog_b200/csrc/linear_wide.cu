@@ -1,0 +1,462 @@
+// Persistent tcgen05 GEMM for wide token counts (prefill, the ResNet convolutions, the image-token side of the Q-Former):
+//
+//   out[M,N] = epilogue( x[M,K] . W[N,K]^T ),   M > 128, fp16/bf16, fp32 accumulate            (same contract as linear_tc.cu)
+//
+// linear_tc.cu runs one (128 weight rows x NT tokens) tile per CTA: TMEM alloc, pipeline fill and - above all - the epilogue
+// (128 x 256 outputs per tile) are serial with the tile's MMAs, and with one 200 KB CTA per SM nothing else covers them.  On
+// the prefill shapes that is 25-50 % of a tile's time (o_proj: 28 us of MMA in a 50 us tile); on the K = 64 layer-1
+// convolutions the tile is ALL epilogue.  This kernel keeps the same swap-AB tile (weights = UMMA A, tokens = UMMA B, 128 x NT)
+// but is persistent - one CTA per SM walks a static list of tiles - and splits the work so that all three stages overlap:
+//
+//   warp 0    TMA producer: 2..4-stage ring of (16 KB weight k-block + NT x 128 B token k-block), runs ahead across tiles
+//   warp 1    tcgen05.mma issuer; the 512 TMEM columns hold TWO accumulator buffers, tile i+1 accumulates while
+//   warps 2-5 drain tile i:  tcgen05.ld -> registers -> epilogue arithmetic -> shared memory -> TMA store, in chunks of CR <= 32
+//             tokens.  The residual tile arrives by TMA too (3..15 chunks ahead, same shared-memory buffer the result is
+//             written back into), so the epilogue issues no per-thread global loads or stores at all.
+//
+// SwiGLU (gate|up) tiles hold 64 gate rows + 64 up rows of W in ONE 128-row A tile (two 64-row TMA boxes), so the MMA shape
+// and the single 256-column accumulator are the same as for every other GEMM and double buffering still fits in TMEM; the two
+// lane halves exchange T(g) / T(u) through 8 KB of shared memory and all four epilogue warps share the silu work.
+//
+// The token-tile width NT is a launch parameter (any multiple of 16 up to 256): the host picks the NT that wastes the
+// fewest MMA cycles to round quantisation (tiles / SMs), e.g. 240 instead of 256 for the 2048-token prefill o_proj/down
+// (288 tiles = 1.95 rounds instead of 256 = 1.73 -> 2).
+//
+// Arithmetic and rounding points are those of linear_tc.cu's epilogues (T(Wx) then the residual add, fp32 bias/act, the
+// SwiGLU triple rounding); the k-blocks are accumulated in the same order, so the two kernels agree bit for bit.
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+bool rd_pdl_enabled();
+int rd_tc_make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int cols, int box_rows, int box_cols, int dtype, int swizzle128);
+
+static int g_wide_persistent = 1;    // test hook: 0 = wide shapes stay on linear_tc_kernel
+extern "C" int rd_linear_wide_persistent(int on) { g_wide_persistent = on; return RD_OK; }
+static int g_wide_force_nt = 0;      // test hook: token-tile width (0 = heuristic)
+extern "C" int rd_linear_wide_force_nt(int nt) { g_wide_force_nt = nt; return RD_OK; }
+static int g_wide_force_stages = 0;  // test hook: pipeline stages 2..4 (0 = by K)
+extern "C" int rd_linear_wide_force_stages(int s) { g_wide_force_stages = (s >= 2 && s <= 4) ? s : 0; return RD_OK; }
+static int g_wide_min_tiles = 149;   // below this the one-tile-per-CTA kernel is used (nothing to overlap)
+extern "C" int rd_linear_wide_min_tiles(int n) { g_wide_min_tiles = n; return RD_OK; }
+
+namespace {
+using namespace tcptx;
+
+constexpr int WROWS = 128;                       // weight rows per tile (UMMA M)
+constexpr int BK = 64;                           // 64 x 2 B = one 128-byte swizzle row
+constexpr int UK = 16;
+constexpr int W_BYTES = WROWS * BK * 2;          // 16 KB
+constexpr int X_BYTES_MAX = 256 * BK * 2;        // 32 KB
+constexpr int STAGE_BYTES = W_BYTES + X_BYTES_MAX;
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_NBUF = 16;
+constexpr int BUF_BYTES = 32 * 128 * 2;          // epilogue chunk buffer: CR <= 32 token rows of 128 features (residual in, result out)
+constexpr int RING_EPI_BYTES = MAX_STAGES * STAGE_BYTES + 4 * BUF_BYTES;   // 224 KB split between the pipeline and the chunk buffers:
+                                                 // 4 stages + 4 buffers (deep K), 3 + 10, or 2 + 16 (K <= 128: the tile is all epilogue)
+constexpr int BAR_BYTES = 512;
+constexpr int SMEM_BYTES = RING_EPI_BYTES + BAR_BYTES + 1024;
+constexpr int THREADS = 192;
+constexpr uint64_t HINT_NORMAL = 0x1000000000000000ull;
+
+enum { W_PLAIN = 0, W_RES1 = 1, W_AFFINE = 2 };
+
+struct WideParams {
+  int M, N, K;
+  int NT, CR;                 // token-tile width, epilogue chunk rows (CR divides NT, CR in {16, 32})
+  int m_tiles, n_tiles, tiles;
+  int m_fast;                 // consecutive tiles (= CTAs running together) share the weight tile
+  int mode, act, has_res;
+  int stages, nbuf;           // pipeline stages, 8 KB epilogue chunk buffers
+  const float* bias;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+template <class T, bool SWIGLU>
+__global__ void __launch_bounds__(THREADS, 1)
+linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                   const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const WideParams p) {
+  constexpr int FEATS = SWIGLU ? 64 : 128;                   // output features per tile
+  constexpr int CBUF = SWIGLU ? BUF_BYTES / 2 : BUF_BYTES;   // bytes between chunk buffers
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int STAGES = p.stages;
+  // SwiGLU result rows are 64 features wide: twice as many (half-size) buffers, minus the T(g) / T(u) exchange (2 x 4 KB)
+  const int NBUF = SWIGLU ? (2 * p.nbuf - 2 < MAX_NBUF ? 2 * p.nbuf - 2 : MAX_NBUF) : p.nbuf;
+  uint8_t* epi_s = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_EPI_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull = empty_bar + MAX_STAGES;      // [2] accumulator buffer complete
+  uint64_t* tempty = tfull + 2;                  // [2] accumulator buffer drained (128 epilogue threads arrive)
+  uint64_t* res_full = tempty + 2;               // [NBUF] residual chunk landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full + MAX_NBUF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int NT = p.NT, CR = p.CR;
+  const uint32_t stage_tx = (uint32_t)(W_BYTES + NT * BK * 2);
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
+    if (p.has_res) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_res)) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+    for (int b = 0; b < MAX_NBUF; ++b) mbar_init(&res_full[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_coords = [&](int t, int& m0, int& n0) {
+    int mt, nt;
+    if (p.m_fast) { mt = t % p.m_tiles; nt = t / p.m_tiles; } else { nt = t % p.n_tiles; mt = t / p.n_tiles; }
+    m0 = mt * NT;
+    n0 = nt * FEATS;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    auto load_w = [&](int s, int kb, int n0) {
+      uint8_t* sp = smem + s * STAGE_BYTES;
+      if (SWIGLU) {
+        tma_load_2d(sp, &map_w, &full_bar[s], kb * BK, n0, HINT_NORMAL);                        // 64 gate rows
+        tma_load_2d(sp + W_BYTES / 2, &map_w, &full_bar[s], kb * BK, p.N + n0, HINT_NORMAL);    // 64 up rows
+      } else {
+        tma_load_2d(sp, &map_w, &full_bar[s], kb * BK, n0, HINT_NORMAL);
+      }
+    };
+    // weights never depend on the previous kernel: the first stages' weight k-blocks are requested before the PDL wait
+    int pre = 0;
+    if ((int)blockIdx.x < p.tiles) {
+      int m0, n0;
+      tile_coords(blockIdx.x, m0, n0);
+      pre = kb_total < STAGES ? kb_total : STAGES;
+      if (elect_one()) {
+        for (int i = 0; i < pre; ++i) { mbar_expect_tx(&full_bar[i], stage_tx); load_w(i, i, n0); }
+      }
+      __syncwarp();
+    }
+    pdl_wait();
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      int m0, n0;
+      tile_coords(t, m0, n0);
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1u, 1);        // first pass: the barrier's "previous phase" counts as complete
+        __syncwarp();
+        if (elect_one()) {
+          if (it >= pre) { mbar_expect_tx(&full_bar[s], stage_tx); load_w(s, kb, n0); }
+          tma_load_2d(smem + s * STAGE_BYTES + W_BYTES, &map_x, &full_bar[s], kb * BK, m0, HINT_NORMAL);
+        }
+        __syncwarp();
+        if (it < STAGES) ++it;
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(Tr<T>::umma_fmt, WROWS, NT);
+    const uint64_t d0 = make_smem_desc(smem_u32(smem));
+    int s = 0, tl = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      mbar_wait(&tempty[buf], (uint32_t)((tl >> 1) & 1) ^ 1u, 2);      // epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(&full_bar[s], ph, 3);
+        tc_fence_after();
+        __syncwarp();
+        if (elect_one()) {
+          const uint64_t da = d0 + (uint64_t)((uint32_t)s * (STAGE_BYTES >> 4));
+          const uint64_t db = da + (uint64_t)(W_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t koff = (uint64_t)((k * UK * 2) >> 4);
+            tc_mma_f16(d_tmem, da + koff, db + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);
+          if (kb == kb_total - 1) tc_commit(&tfull[buf]);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 = TMEM lane quadrants 2, 3, 0, 1) =====================
+    const int e = threadIdx.x - 64;
+    const int quad = warp & 3;
+    const int n_local = quad * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int mode = p.mode, act = p.act;
+    const bool has_res = p.has_res != 0;
+    auto n_chunks_of = [&](int t) {
+      int m0, n0;
+      tile_coords(t, m0, n0);
+      const int rows = p.M - m0 < NT ? p.M - m0 : NT;
+      return (rows + CR - 1) / CR;
+    };
+    pdl_wait();                                   // residual reads and every store come after the previous kernel
+    // residual prefetch iterator (thread e == 32): runs D chunks ahead of the chunk being finished
+    int pf_t = blockIdx.x, pf_c = 0, pf_g = 0;
+    auto issue_res = [&]() {
+      if (pf_t >= p.tiles) return;
+      int m0, n0;
+      tile_coords(pf_t, m0, n0);
+      const int b = pf_g % NBUF;
+      mbar_expect_tx(&res_full[b], (uint32_t)(CR * FEATS * 2));
+      tma_load_2d(epi_s + b * CBUF, &map_res, &res_full[b], n0, m0 + pf_c * CR, HINT_NORMAL);
+      ++pf_g;
+      if (++pf_c == n_chunks_of(pf_t)) { pf_c = 0; pf_t += gridDim.x; }
+    };
+    // stores allowed to be still reading their buffer after a new one is committed; the residual of chunk g + D goes into the
+    // buffer chunk g - E - 1 was stored from.  The store side (thread 0) and the residual loads (thread 32) are separate
+    // threads: each chunk's serial path is one TMA issue.
+    const int E = NBUF >= 8 ? 4 : 1, D = NBUF - E - 1;
+    if (has_res && e == 32) {
+      for (int i = 0; i < D; ++i) issue_res();
+    }
+    int g = 0, tl = 0;
+#ifdef RD_WIDE_PROF
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
+#define PROF(i) { const long long _n = clock64(); pf[i] += _n - pt; pt = _n; }
+#else
+#define PROF(i)
+#endif
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
+      int m0, n0;
+      tile_coords(t, m0, n0);
+      const int buf = tl & 1;
+      const int n = n0 + n_local;
+      float bias_n = 0.f;
+      if (!SWIGLU && mode == W_AFFINE && p.bias != nullptr && n < p.N) bias_n = p.bias[n];
+      const int nch = n_chunks_of(t);
+      PROF(0)
+      mbar_wait(&tfull[buf], (uint32_t)((tl >> 1) & 1), 4);
+      tc_fence_after();
+      PROF(1)
+      for (int c = 0; c < nch; ++c, ++g) {
+        const int b = g % NBUF;
+        T* bufp = reinterpret_cast<T*>(epi_s + b * CBUF);
+        epi_bar(1);                               // buffer b and the exchange area are free (thread 0 has waited for the store)
+        PROF(2)
+        if (has_res) {
+          if (e == 32) issue_res();               // chunk g + D
+          mbar_wait(&res_full[b], (uint32_t)((g / NBUF) & 1), 5);
+        }
+        PROF(3)
+        uint32_t r0[16], r1[16];
+        const uint32_t ta = taddr + (uint32_t)(buf * 256 + c * CR);
+        tc_ld16(ta, r0);
+        if (CR == 32) tc_ld16(ta + 16, r1);
+        tc_wait_ld();
+        PROF(4)
+        if (c == nch - 1) {                       // accumulators of this tile are in registers: hand the buffer back
+          tc_fence_before();
+          mbar_arrive(&tempty[buf]);
+        }
+        if (SWIGLU) {
+          // lanes 0..63 hold the gate rows, lanes 64..127 the up rows of the same 64 features: both halves park T(.) of their
+          // accumulators (the reference rounds g and u to the storage type before anything else), then ALL four warps share the
+          // silu / multiply work: thread -> (feature e & 63, half of the chunk's token rows e >> 6)
+          T* exg = reinterpret_cast<T*>(epi_s + NBUF * CBUF);
+          T* exu = exg + 32 * 64;
+          T* mine = (quad >= 2 ? exu : exg) + (n_local & 63);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mine[j * 64] = Tr<T>::r(__uint_as_float(r0[j]));
+          if (CR == 32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mine[(16 + j) * 64] = Tr<T>::r(__uint_as_float(r1[j]));
+          }
+          epi_bar(3);
+          const int f = e & 63, half = CR >> 1, j0 = (e >> 6) * half;
+          if (CR == 32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float gt = Tr<T>::f(exg[(j0 + j) * 64 + f]), u = Tr<T>::f(exu[(j0 + j) * 64 + f]);
+              bufp[(j0 + j) * 64 + f] = Tr<T>::r(Tr<T>::rr(silu_f(gt)) * u);      // T(T(silu(T(g))) * T(u))
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float gt = Tr<T>::f(exg[(j0 + j) * 64 + f]), u = Tr<T>::f(exu[(j0 + j) * 64 + f]);
+              bufp[(j0 + j) * 64 + f] = Tr<T>::r(Tr<T>::rr(silu_f(gt)) * u);
+            }
+          }
+        } else {
+          // the residual values of the 16 rows are read together before the first one is consumed (one shared-memory latency
+          // per 16 elements instead of per element), and the activation switch sits outside the element loop
+          auto finish = [&](const uint32_t (&r)[16], int jb) {
+            T* q = bufp + jb * 128 + n_local;
+            float res[16];
+            if (has_res) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) res[j] = Tr<T>::f(q[j * 128]);
+            }
+            if (mode == W_RES1) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) q[j * 128] = Tr<T>::r(res[j] + Tr<T>::rr(__uint_as_float(r[j])));   // residual add after rounding Wx
+            } else if (mode == W_AFFINE) {
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bias_n;
+              if (has_res) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += res[j];
+              }
+              if (act == RD_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+              } else if (act == RD_ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) q[j * 128] = Tr<T>::r(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) q[j * 128] = Tr<T>::r(__uint_as_float(r[j]));
+            }
+          };
+          finish(r0, 0);
+          if (CR == 32) finish(r1, 16);
+        }
+        fence_proxy_async_smem();
+        PROF(5)
+        epi_bar(2);
+        PROF(6)
+        if (e == 0) {
+          tma_store_2d(&map_out, bufp, n0, m0 + c * CR);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (E == 4) asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");     // stores <= g - E have read their buffers
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        PROF(7)
+      }
+    }
+    if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#ifdef RD_WIDE_PROF
+    if (blockIdx.x == 1 && (e == 0 || e == 37))
+      printf("wide prof e=%d tiles=%d chunks=%d: tile-setup %lld tfull-wait %lld bar1 %lld res-wait %lld tmem-ld %lld compute %lld bar2 %lld store+issue %lld (cycles)\n",
+             e, tl, g, pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7]);
+#endif
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+int sm_count() {
+  static int cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+// token-tile width: the candidate that spends the fewest MMA cycles on round quantisation (a tile costs ~NT + a fixed part;
+// the CTA with the most tiles sets the time).  Widths that are not a multiple of 32 drain in 16-token chunks: a small penalty.
+int choose_nt(int M, int n_tiles, int sms) {
+  const int cand[] = {256, 240, 224, 192, 160, 128};
+  int best = 256;
+  double best_cost = 1e30;
+  for (int nt : cand) {
+    const long long m_tiles = (M + nt - 1) / nt, tiles = m_tiles * n_tiles, rounds = (tiles + sms - 1) / sms;
+    double cost = (double)rounds * (nt + 12);
+    if (nt % 32) cost *= 1.03;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = nt; }
+  }
+  return best;
+}
+
+template <class T, bool SWIGLU>
+int launch_wide(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
+                const EpiParams& epi, int mode, int dtype, cudaStream_t st) {
+  constexpr int FEATS = SWIGLU ? 64 : 128;
+  const int sms = sm_count();
+  WideParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.n_tiles = (N + FEATS - 1) / FEATS;
+  p.NT = g_wide_force_nt > 0 ? g_wide_force_nt : choose_nt(M, p.n_tiles, sms);
+  p.CR = (p.NT % 32 == 0) ? 32 : 16;
+  p.m_tiles = (M + p.NT - 1) / p.NT;
+  const long long tiles = (long long)p.m_tiles * p.n_tiles;
+  if (tiles < g_wide_min_tiles || tiles > 0x3fffffff) return 0;
+  p.tiles = (int)tiles;
+  p.m_fast = ((int64_t)(SWIGLU ? 2 : 1) * N > (int64_t)M) ? 1 : 0;
+  p.mode = mode; p.act = epi.act; p.has_res = (!SWIGLU && epi.residual != nullptr) ? 1 : 0; p.bias = epi.bias;
+  {
+    // 224 KB of shared memory: deep-K tiles want pipeline stages, K <= 128 tiles (one or two k-blocks, all epilogue) want the
+    // residual prefetch to run far ahead instead
+    const int kb = (K + BK - 1) / BK;
+    p.stages = g_wide_force_stages > 0 ? g_wide_force_stages : (kb <= 2 ? 2 : kb <= 4 ? 3 : 4);
+    p.nbuf = 4 + (MAX_STAGES - p.stages) * (STAGE_BYTES / BUF_BYTES);
+    if (p.nbuf > MAX_NBUF) p.nbuf = MAX_NBUF;
+  }
+  CUtensorMap map_w, map_x, map_out, map_res;
+  RD_CHECK(rd_tc_make_map(&map_w, w, ldw, SWIGLU ? 2 * N : N, K, FEATS, BK, dtype, 1));
+  RD_CHECK(rd_tc_make_map(&map_x, x, ldx, M, K, p.NT, BK, dtype, 1));
+  RD_CHECK(rd_tc_make_map(&map_out, out, ldo, M, N, p.CR, FEATS, dtype, 0));
+  if (p.has_res) RD_CHECK(rd_tc_make_map(&map_res, epi.residual, epi.ld_res, M, N, p.CR, FEATS, dtype, 0));
+  else map_res = map_out;
+  RD_SMEM_ATTR_ONCE(SMEM_BYTES, linear_wide_kernel<T, SWIGLU>);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(p.tiles < sms ? p.tiles : sms)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (rd_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_wide_kernel<T, SWIGLU>, map_w, map_x, map_out, map_res, p));
+  return 1;
+}
+
+}  // namespace
+
+// 1: launched, 0: shape / epilogue not handled here (caller falls through to linear_tc_kernel), < 0: error
+int rd_linear_wide_try(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
+                       const EpiParams& epi, int dtype, cudaStream_t st) {
+  if (!g_wide_persistent || M <= 128) return 0;
+  const bool sw = epi.act == RD_ACT_SWIGLU;
+  const bool simple = epi.bias == nullptr && (epi.act == RD_ACT_NONE || sw);
+  int mode;
+  if (epi.lora_r != 0) return 0;
+  if (simple && epi.residual == nullptr) mode = W_PLAIN;
+  else if (!sw && simple && epi.residual != nullptr && epi.res_mode == 1) mode = W_RES1;
+  else if (!sw && (epi.residual == nullptr || epi.res_mode == 2)) mode = W_AFFINE;
+  else return 0;
+  // TMA store / residual load: 16-byte aligned base and row pitch
+  if (((uintptr_t)out & 15) != 0 || ldo % 8 != 0) return 0;
+  if (epi.residual != nullptr && (((uintptr_t)epi.residual & 15) != 0 || epi.ld_res % 8 != 0)) return 0;
+  RD_DISPATCH_DTYPE(dtype, T, {
+    if (sw) return launch_wide<T, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
+    return launch_wide<T, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
+  });
+}

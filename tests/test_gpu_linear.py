@@ -192,10 +192,80 @@ def test_tmem_staged_decode_tiles_bit_identical(cuda_dev, lib, dtype, M, N, K, a
     for ts in (0, 1):
         lib.rd_linear_tmem_staging(ts)
         outs[ts] = [run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, act=act, residual=residual, ws=ws) for _ in range(2)]
-    lib.rd_linear_tmem_staging(1)
+    lib.rd_linear_tmem_staging(0)
     assert torch.equal(outs[1][0], outs[1][1]), "TMEM-staged kernel is not deterministic run to run"
     assert torch.equal(outs[0][0], outs[1][0]), f"max diff {(outs[0][0].float() - outs[1][0].float()).abs().max().item():.4g}"
     ref = ref_linear(x, w, dtype, act=act, residual=residual, N=N)
     ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
     scale = ref.float().abs().max().item()
     assert (outs[1][0].float() - ref.float()).abs().max().item() <= 2 * ulp * scale
+
+
+WIDE_CASES = [
+    # M, N, K, act, bias, res_mode (0 = no residual)
+    (2048, 4096, 4096, 0, False, 1),            # prefill o_proj
+    (2048, 1536, 1024, _lib.ACT_SWIGLU, False, 0),
+    (1000, 1000, 704, 0, False, 0),             # ragged M / N / K tails
+    (777, 328, 72, _lib.ACT_RELU, True, 2),     # conv-like: bias + fp32 residual + ReLU, K barely over one k-block
+    (3136, 256, 64, 0, True, 0),                # one k-block per tile (layer-1 1x1 conv)
+    (1290, 776, 256, _lib.ACT_GELU, True, 0),
+    (515, 520, 1152, _lib.ACT_SWIGLU, False, 0),
+    (300, 4096, 512, 0, False, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", WIDE_CASES)
+@pytest.mark.parametrize("nt,stages", [(0, 0), (128, 2), (160, 3), (240, 4)])
+def test_persistent_wide_kernel_bit_identical(cuda_dev, lib, dtype, case, nt, stages):
+    """linear_wide.cu (persistent CTAs, double-buffered TMEM accumulators, TMA residual load / store, runtime token-tile
+    width) against the one-tile-per-CTA kernel: same products, same k-block order, same epilogue arithmetic, so bit-identical
+    - and both within an ulp of the fp32 reference.  min_tiles = 1 forces the persistent kernel onto the small shapes too."""
+    M, N, K, act, has_bias, res_mode = case
+    g = torch.Generator().manual_seed(M + 3 * N + 5 * K + nt)
+    rows = 2 * N if act == _lib.ACT_SWIGLU else N
+    w = (torch.randn(rows, K, generator=g) * 0.05).to(dtype).to(cuda_dev)
+    x = (torch.randn(M, K, generator=g) * 0.5).to(dtype).to(cuda_dev)
+    bias = (torch.randn(N, generator=g) * 0.1).to(cuda_dev) if has_bias else None
+    residual = (torch.randn(M, N, generator=g) * 0.5).to(dtype).to(cuda_dev) if res_mode else None
+    ws = torch.zeros(int(lib.rd_linear_workspace_bytes(M, N, K)) + 256, dtype=torch.uint8, device=cuda_dev)
+    kw = dict(act=act, bias=bias, residual=residual, res_mode=res_mode or 1, ws=ws)
+    outs = {}
+    try:
+        lib.rd_linear_wide_min_tiles(1)
+        lib.rd_linear_wide_force_nt(nt)
+        lib.rd_linear_wide_force_stages(stages)
+        for on in (0, 1):
+            lib.rd_linear_wide_persistent(on)
+            outs[on] = [run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, **kw) for _ in range(2)]
+    finally:
+        lib.rd_linear_wide_persistent(1)
+        lib.rd_linear_wide_min_tiles(149)
+        lib.rd_linear_wide_force_nt(0)
+        lib.rd_linear_wide_force_stages(0)
+    assert torch.isfinite(outs[1][0].float()).all(), "persistent kernel left outputs unwritten"
+    assert torch.equal(outs[1][0], outs[1][1]), "persistent kernel is not deterministic run to run"
+    assert torch.equal(outs[0][0], outs[1][0]), f"max diff {(outs[0][0].float() - outs[1][0].float()).abs().max().item():.4g}"
+    ref = ref_linear(x, w, dtype, bias=bias, act=act, residual=residual, res_mode=res_mode or 1, N=N)
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    scale = ref.float().abs().max().item()
+    assert (outs[1][0].float() - ref.float()).abs().max().item() <= 2 * ulp * scale
+
+
+def test_persistent_wide_kernel_many_tiles_per_cta(cuda_dev, lib):
+    """More than two rounds of tiles per CTA (accumulator-buffer and chunk-buffer phases wrap several times), on the prefill
+    gate|up shape, against the fp32 reference and the one-tile-per-CTA kernel."""
+    dtype = torch.bfloat16
+    M, N, K = 2048, 11008, 512
+    g = torch.Generator().manual_seed(11)
+    w = (torch.randn(2 * N, K, generator=g) * 0.05).to(dtype).to(cuda_dev)
+    x = (torch.randn(M, K, generator=g) * 0.5).to(dtype).to(cuda_dev)
+    a = run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, act=_lib.ACT_SWIGLU)
+    lib.rd_linear_wide_persistent(0)
+    try:
+        b = run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, act=_lib.ACT_SWIGLU)
+    finally:
+        lib.rd_linear_wide_persistent(1)
+    assert torch.equal(a, b)
+    ref = ref_linear(x, w, dtype, act=_lib.ACT_SWIGLU, N=N)
+    assert (a.float() - ref.float()).abs().max().item() <= 2 * 2.0 ** -7 * ref.float().abs().max().item()
