@@ -355,7 +355,7 @@ def run_own_arm(args):
     if rank == 0:
         pk = peaks()
         hbm_peak = pk["hbm"]
-        roof, prof, mega = dominant_kernel_roofline(llm, B, hbm_peak, pk["src"], with_mega=not args.no_mega)
+        roof, prof = dominant_kernel_roofline(llm, B, hbm_peak, pk["src"])
         dec_ms = sum(s["decode_ms"] for s in stats) / len(stats) / (NEW - 1)
         c_mid = T_PROMPT + NEW // 2
         step_bytes = W_DEC_BYTES + B * KV_BYTES_PER_TOKEN * (c_mid + 1)
@@ -390,8 +390,6 @@ def run_own_arm(args):
             "phases_ms": phases,
             "kernel_classes_ms_per_decode_step": {k: v["ms"] / PROFILE_STEPS for k, v in prof.items()},
         }
-        if mega is not None:
-            out["persistent_kernel"] = mega
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -419,7 +417,7 @@ def run_own_arm(args):
         dist.destroy_process_group()
 
 
-def dominant_kernel_roofline(llm, B, hbm_peak, peak_src, with_mega=True):
+def dominant_kernel_roofline(llm, B, hbm_peak, peak_src):
     """Dominant kernel of the default (one kernel per op) decode path = the fused gate|up projection GEMM
     (linear_tc_kernel<NT, SWIGLU>, ~28 % of a decode step's kernel time, profiles/).
     Algorithmic bytes per launch = its weights, 180,355,072 B.  Average launch duration, live, with CUDA
@@ -471,21 +469,7 @@ def dominant_kernel_roofline(llm, B, hbm_peak, peak_src, with_mega=True):
             "traffic_source": traffic_src,
             "how": f"CUDA events around {rounds} x {len(layers)} back-to-back launches over the 32 layers' distinct weights, launch "
                    "attributes as in the timed run; after the timed region"}
-    mega = None
-    if with_mega:
-        llm.set_mega(True)
-        try:
-            pm = llm.profile_decode_steps(B, T_PROMPT, steps=PROFILE_STEPS)
-        finally:
-            llm.set_mega(False)
-        mega_ms = pm["mega"]["ms"] / max(1, pm["mega"]["launches"])
-        c_mean = T_PROMPT + 1 + (PROFILE_STEPS - 1) / 2.0          # cached tokens seen by the profiled steps
-        mega_bytes = LAYER_W_BYTES + B * KV_BYTES_PER_TOKEN * (c_mean + 1)
-        mega = {"note": "experimental persistent kernel (rd_llm_set_mega(1), off by default): all 32 decoder layers of a step in one launch",
-                "ms_per_launch": mega_ms, "algorithmic_bytes_per_launch": int(mega_bytes),
-                "achieved_gbs": mega_bytes / (mega_ms * 1e-3) / 1e9 if mega_ms > 0 else None,
-                "frac_of_hbm_peak": mega_bytes / (mega_ms * 1e-3) / 1e9 / hbm_peak if mega_ms > 0 else None}
-    return roof, prof, mega
+    return roof, prof
 
 
 def bench_b1(pipe, llm, dev, new_tokens, hbm_peak):
@@ -504,7 +488,7 @@ def bench_b1(pipe, llm, dev, new_tokens, hbm_peak):
     ms = e0.elapsed_time(e1)
     dec_ms = pipe.last_stats["decode_ms"] / (new_tokens - 1)
     step_bytes = W_DEC_BYTES + KV_BYTES_PER_TOKEN * (T_PROMPT + new_tokens // 2 + 1)
-    roof, _, _ = dominant_kernel_roofline(llm, 1, hbm_peak, "", with_mega=False)
+    roof, _ = dominant_kernel_roofline(llm, 1, hbm_peak, "")
     return {"reports_per_s": 1e3 / ms, "ms_per_report": ms, "decode_ms_per_token": dec_ms,
             "decode_step_gbs": step_bytes / (dec_ms * 1e-3) / 1e9, "decode_step_frac_of_hbm_peak": step_bytes / (dec_ms * 1e-3) / 1e9 / hbm_peak,
             "gate_up_gbs": roof["achieved"], "gate_up_frac": roof["frac"]}
@@ -594,7 +578,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-b1", action="store_true", help="skip the batch-1 latency leg")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference GPU PyTorch path leg")
-    ap.add_argument("--no-mega", action="store_true", help="skip timing the experimental persistent kernel")
+    ap.add_argument("--no-mega", action="store_true", help=argparse.SUPPRESS)      # accepted for old command lines; no effect
     ap.add_argument("--ref-dec-tokens", type=int, default=4, help="decode steps per bounded CPU sample")
     ap.add_argument("--no-full-report", action="store_true", help="reference arm: skip the one complete 128-token report in the warm-up")
     args = ap.parse_args()

@@ -192,21 +192,6 @@ void rd_llm_destroy(rd_llm* h);
 int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* ptr_dev);
 /* GEMM path: 0 auto, 1 GEMV, 2 tcgen05, 3 SIMT (validation) */
 int rd_llm_set_algo(rd_llm* h, int algo);
-/* Single-token decode steps with B <= 32 run ALL decoder layers in one persistent kernel (one CTA per SM, weights of
- * every phase streamed through one TMA ring, stream-K work split, grid barriers between phases; csrc/decode_mega.cu).
- * on = 1 / 0 (default) = one kernel per op.  Same rounding contract either way (LlamaDecoderLayer.forward,
- * modeling_llama_imgemb.py:266-318).  Call outside stream capture.                                              */
-int rd_llm_set_mega(rd_llm* h, int on);
-/* The GEMMs of single-token decode steps with B <= 32 as stream-K kernels (one CTA per SM, equal contiguous runs of
- * (weight tile, k-block) units, fp32 fix-up through L2 in fixed split order) with the RMSNorm of
- * LlamaDecoderLayer.forward (modeling_llama_imgemb.py:287,305) applied to the token tiles in shared memory instead of by
- * a separate kernel (csrc/linear_sk.cu).  on = 1 / 0 (default) = tile x split-K kernels + norm kernels.  Same rounding
- * contract either way.  Call outside stream capture.                                                              */
-int rd_llm_set_streamk(rd_llm* h, int on);
-/* Single-token steps with B <= 32: LlamaRMSNorm (modeling_llama_imgemb.py:85-93) applied to the token tiles inside the
- * QKV / gate|up GEMMs (row statistics from sum-of-squares partials written by the o_proj / down_proj epilogues) instead of
- * by separate kernels.  on = 1 / 0 (default).  Bit-identical results (tests/test_gpu_llm.py).                    */
-int rd_llm_set_fused_norm(rd_llm* h, int on);
 /* Single-token steps with B <= 32 (default ON): the QKV GEMM (q_proj|k_proj|v_proj (+lora_A), modeling_llama_imgemb.py:178-181)
  * leaves its fp32 split-K partials in an L2-resident slab and the attention kernel sums them in split order and applies the
  * single rounding T(Wx) while reading q/k/v - the GEMM has no cross-CTA reduction tail.  0 = the GEMM reduces them itself

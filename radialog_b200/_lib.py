@@ -19,7 +19,7 @@ ALGO_AUTO, ALGO_GEMV, ALGO_TC, ALGO_SIMT = 0, 1, 2, 3
 W_EMBED, W_FINAL_NORM, W_LM_HEAD, W_IMG_PROJ_W, W_IMG_PROJ_B, W_ROPE_COS, W_ROPE_SIN = 0, 1, 2, 3, 4, 5, 6
 W_QKV, W_O, W_GATE_UP, W_DOWN, W_LN1, W_LN2, W_LORA_A, W_LORA_B = 10, 11, 12, 13, 14, 15, 16, 17
 
-PROFILE_CLASSES = ("rmsnorm", "qkv", "rope", "attn", "o", "gate_up", "down", "lm_head", "argmax", "embed", "mega")
+PROFILE_CLASSES = ("rmsnorm", "qkv", "rope", "attn", "o", "gate_up", "down", "lm_head", "argmax", "embed")
 
 
 class Epilogue(C.Structure):
@@ -73,9 +73,6 @@ SIGNATURES = {
     "rd_llm_destroy": (None, [_p]),
     "rd_llm_set_weight": (_i, [_p, _i, _i, _p]),
     "rd_llm_set_algo": (_i, [_p, _i]),
-    "rd_llm_set_mega": (_i, [_p, _i]),
-    "rd_llm_set_streamk": (_i, [_p, _i]),
-    "rd_llm_set_fused_norm": (_i, [_p, _i]),
     "rd_llm_set_qkv_partials": (_i, [_p, _i]),
     "rd_llm_set_od_partials": (_i, [_p, _i]),
     "rd_llm_set_l2_prefetch": (_i, [_p, C.c_longlong, C.c_longlong, C.c_longlong]),

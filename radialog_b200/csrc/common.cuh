@@ -231,15 +231,8 @@ static inline cudaError_t rd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 int rd_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
                  const EpiParams& epi, int dtype, void* ws, int64_t ws_bytes, cudaStream_t st);
 int64_t rd_linear_tc_workspace_bytes(int M, int N, int K);
-// decode (M <= 32) extras of the tcgen05 GEMM: RMSNorm fused on the input (x = raw residual stream, rstd from the
-// [norm_tiles][32] sum-of-squares partials at norm_ssq) and / or the sum of squares of the residual-epilogue output per
-// 128-row tile written to ssq_out[tile][m] (feeds the next fused norm).
+// decode (M <= 32) extra of the tcgen05 GEMM
 struct TcFuse {
-  const float* norm_ssq;
-  const void* norm_w;
-  int norm_tiles;
-  float norm_eps;
-  float* ssq_out;
   // partials-out split-K (see TcParams::part_out in linear_tc.cu): the GEMM leaves its fp32 split-K partials in
   // part_out[splits][NT][N] for the consumer to sum; splits_out[0..1] receives the split count and the slab's row count NT.
   float* part_out = nullptr;

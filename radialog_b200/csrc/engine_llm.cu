@@ -6,8 +6,6 @@
 #include <stdlib.h>
 #include <vector>
 #include "common.cuh"
-#include "decode_mega.h"
-#include "linear_sk.h"
 
 extern "C" int rd_attention_decode(const void*, int64_t, const int32_t*, const void*, const void*, void*, void*, const uint8_t*,
                                    const int32_t*, void*, int, int, int, int, int, const void*, int, float, int, void*);
@@ -22,7 +20,7 @@ extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const i
 extern "C" int rd_argmax_step(const void*, int64_t, int, int64_t*, int64_t*, int64_t, int32_t*, uint8_t*, int, int32_t*,
                               int32_t*, int32_t*, int32_t*, uint32_t*, int, int, int, int, int, int, void*);
 
-enum { C_RMSNORM = 0, C_QKV, C_ROPE, C_ATTN, C_O, C_GATEUP, C_DOWN, C_LMHEAD, C_ARGMAX, C_EMBED, C_MEGA, C_NCLASS };
+enum { C_RMSNORM = 0, C_QKV, C_ROPE, C_ATTN, C_O, C_GATEUP, C_DOWN, C_LMHEAD, C_ARGMAX, C_EMBED, C_NCLASS };
 
 struct LayerW {
   const void *qkv = nullptr, *o = nullptr, *gate_up = nullptr, *down = nullptr, *ln1 = nullptr, *ln2 = nullptr,
@@ -36,22 +34,6 @@ struct rd_llm {
   const float* img_b = nullptr;
   int algo = 0;
   int esz = 2;
-  // persistent decode-layer kernel (decode_mega.cu): 1 = use it whenever the shape allows (B <= 32), 0 = per-op kernels.
-  // Off by default: at Vicuna-7B size its 5 grid barriers per layer (phase tails of 6-8 us) still cost more than the
-  // per-op path's launch boundaries (measured 4.4 ms vs 3.5 ms per B=32 step); see DESIGN.md section 4.
-  int mega_mode = 0;
-  rd_mega* mega = nullptr;
-  // stream-K decode GEMMs with the RMSNorm fused on their input (linear_sk.cu) for single-token steps with B <= 32.
-  // Off by default: measured slower than the tile x split-K kernels (B=32: qkv 37 vs 29 us, gate|up 56 vs 43 us per launch) -
-  // the fix-up through L2 costs more than the cluster/DSMEM reduction, and <= 113 KB of smem per CTA is too little in flight.
-  int sk_mode = 0;
-  rd_sk* sk = nullptr;
-  float* ssq = nullptr;          // [H/128][32] sum-of-squares partials of the residual stream
-  // single-token steps with B <= 32: the two RMSNorms of a layer are applied inside the QKV / gate|up GEMMs (statistics
-  // from sum-of-squares partials written by the o_proj / down_proj epilogues) instead of by separate kernels.
-  // Off by default: bit-identical results, but normalising the token tile inside a 3-5 stage W+X pipeline lengthens every
-  // stage (measured B=32: 4.23 vs 3.77 ms per step; B=1: 3.01 vs 2.92 ms).
-  int fuse_norm = 0;
   // single-token steps with B <= 32 (default ON): the QKV GEMM leaves its fp32 split-K partials in `qkv_part` and the attention
   // kernel sums them (fixed order, one rounding) when it reads q/k/v - no cross-CTA reduction pass in the GEMM's tail.
   int qkv_partials = 1;
@@ -128,7 +110,6 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
   A((char**)&h->pos, Mt * 4); A((char**)&h->pos_cur, Bm * 4); A((char**)&h->npos, Bm * 4); A((char**)&h->finished, Bm * 4);
   A((char**)&h->ctx_len, 16); A((char**)&h->n_gen, 16); A((char**)&h->done_ctr, 16);
   A((char**)&h->cur_tok, Bm * 8); A((char**)&h->gen, Bm * C * 8);
-  A((char**)&h->ssq, (H / 128 + 1) * 32 * 4);
   h->qkv_part_bytes = (int64_t)16 * 32 * (3 * H + 64) * 4;          // <= 16 splits x 32 tokens x (3H + 2r) fp32
   A((char**)&h->qkv_part, h->qkv_part_bytes);
   h->od_part_bytes = (int64_t)16 * 32 * H * 4;                        // <= 16 splits x 32 tokens x H fp32
@@ -155,9 +136,6 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
                   h->pos, h->pos_cur, h->npos, h->finished, h->ctx_len, h->n_gen, h->done_ctr, h->cur_tok, h->gen};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
-  rd_mega_destroy(h->mega);
-  rd_sk_destroy(h->sk);
-  if (h->ssq) cudaFree(h->ssq);
   if (h->qkv_part) cudaFree(h->qkv_part);
   if (h->od_part) cudaFree(h->od_part);
   if (h->kc_alt) cudaFree(h->kc_alt);
@@ -168,7 +146,6 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
 extern "C" int rd_llm_set_weight(rd_llm* h, int layer, int slot, const void* p) {
   RD_REQUIRE(h && p, "rd_llm_set_weight: null argument");
   RD_REQUIRE(((uintptr_t)p & 15) == 0, "rd_llm_set_weight: pointer for slot %d must be 16-byte aligned", slot);
-  if (h->mega && slot >= 10) { rd_mega_destroy(h->mega); h->mega = nullptr; }      // its tensor maps point at the old layer weights
   if (slot < 10) {
     switch (slot) {
       case RD_W_EMBED: h->embed = p; break;
@@ -248,104 +225,6 @@ static int linear(rd_llm* h, int cls, const void* x, int64_t ldx, const void* w,
   return rd_linear(x, ldx, w, ldw, out, ldo, M, N, K, e, h->c.dtype, algo, h->ws, h->ws_bytes, st);
 }
 
-static MegaCreate mega_config(const rd_llm* h) {
-  const rd_llm_config& c = h->c;
-  MegaCreate mc{};
-  mc.H = c.hidden; mc.I = c.inter; mc.nh = c.heads; mc.layers = c.layers; mc.lora_r = c.lora_r > 0 ? c.lora_r : 0; mc.dtype = c.dtype;
-  mc.max_batch = c.max_batch; mc.cmax = c.max_ctx; mc.lora_scale = c.lora_scale; mc.eps = c.rms_eps;
-  return mc;
-}
-
-// whether single-token steps of B rows go through the persistent kernel
-static bool mega_wanted(const rd_llm* h, int B) {
-  if (!h->mega_mode || h->algo != 0 || B > 32) return false;
-  const MegaCreate mc = mega_config(h);
-  return rd_mega_unsupported_reason(&mc) == nullptr;
-}
-
-// builds the persistent kernel's tables (tensor maps of all layer weights, work schedule); allocates, so it must not
-// run inside a stream capture - prefill / extend call it ahead of the first decode step
-static int mega_ensure(rd_llm* h) {
-  if (h->mega) return RD_OK;
-  const MegaCreate mc = mega_config(h);
-  std::vector<MegaLayerDesc> d(h->c.layers);
-  for (int l = 0; l < h->c.layers; ++l) {
-    const LayerW& w = h->L[l];
-    d[l].qkv = w.qkv; d[l].o = w.o; d[l].gate_up = w.gate_up; d[l].down = w.down; d[l].ln1 = w.ln1; d[l].ln2 = w.ln2;
-    d[l].lora_b = h->c.lora_r ? w.lora_b : nullptr;
-    d[l].kc = h->kc + (int64_t)l * h->kv_layer_bytes; d[l].vc = h->vc + (int64_t)l * h->kv_layer_bytes;
-  }
-  return rd_mega_create(&mc, d.data(), &h->mega);
-}
-
-static int run_layers_mega(rd_llm* h, int B, const int32_t* pos, cudaStream_t st) {
-  ProfScope ps(h, st, C_MEGA);
-  MegaStep s{};
-  s.x = h->x; s.qkv = h->qkv; s.att = h->att; s.mid = h->mid; s.keymask = h->keymask; s.ctx_len = h->ctx_len; s.pos = pos;
-  s.cos = h->cos; s.sin = h->sin; s.B = B; s.layer_begin = 0; s.layer_end = h->c.layers;
-  return rd_mega_launch(h->mega, &s, st);
-}
-
-// ---- stream-K decode path -------------------------------------------------------------------------------------------------
-static bool sk_wanted(const rd_llm* h, int B) {
-  const rd_llm_config& c = h->c;
-  return h->sk_mode && h->algo == 0 && B <= 32 && c.hidden % 128 == 0 && c.inter % 64 == 0;
-}
-
-// plans + buffers of the stream-K GEMMs (allocates: called from prefill / extend, never inside a stream capture)
-static int sk_ensure(rd_llm* h) {
-  const rd_llm_config& c = h->c;
-  const int H = c.hidden, I = c.inter, R2 = c.lora_r ? 2 * c.lora_r : 0;
-  if (!h->sk) RD_CHECK(rd_sk_create(&h->sk));
-  RD_CHECK(rd_sk_plan(h->sk, 3 * H + R2, H, RD_SK_PLAIN));
-  RD_CHECK(rd_sk_plan(h->sk, H, H, RD_SK_RES1));
-  RD_CHECK(rd_sk_plan(h->sk, I, H, RD_SK_SWIGLU));
-  RD_CHECK(rd_sk_plan(h->sk, H, I, RD_SK_RES1));
-  RD_CHECK(rd_sk_plan(h->sk, c.vocab, H, RD_SK_PLAIN));
-  return RD_OK;
-}
-
-static int run_layers_sk(rd_llm* h, int B, const int32_t* pos, cudaStream_t st) {
-  const rd_llm_config& c = h->c;
-  const int H = c.hidden, I = c.inter, nh = c.heads, hd = H / nh, dt = c.dtype;
-  const int R2 = c.lora_r ? 2 * c.lora_r : 0;
-  const int64_t ldq = 3 * H + R2;
-  const bool fuse_qkv = rd_sk_max_segments(h->sk, 3 * H + R2, H, RD_SK_PLAIN) <= 2;
-  const bool fuse_gu = rd_sk_max_segments(h->sk, I, H, RD_SK_SWIGLU) <= 2;
-  for (int l = 0; l < c.layers; ++l) {
-    const LayerW& w = h->L[l];
-    char* kc = h->kc + (int64_t)l * h->kv_layer_bytes;
-    char* vc = h->vc + (int64_t)l * h->kv_layer_bytes;
-    SkNorm n1{h->ssq, H / 128, w.ln1, c.rms_eps}, n2{h->ssq, H / 128, w.ln2, c.rms_eps};
-    if (l == 0 || !fuse_qkv) {     // the first layer's input comes from the embedding kernel: no partials yet
-      { ProfScope ps(h, st, C_RMSNORM);
-        RD_CHECK(rd_rmsnorm(h->x, w.ln1, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
-      ProfScope ps(h, st, C_QKV);
-      RD_CHECK(rd_sk_linear(h->sk, h->xn, H, w.qkv, H, h->qkv, ldq, B, 3 * H + R2, H, RD_SK_PLAIN, nullptr, 0, nullptr, nullptr, dt, st));
-    } else {
-      ProfScope ps(h, st, C_QKV);
-      RD_CHECK(rd_sk_linear(h->sk, h->x, H, w.qkv, H, h->qkv, ldq, B, 3 * H + R2, H, RD_SK_PLAIN, nullptr, 0, &n1, nullptr, dt, st));
-    }
-    { ProfScope ps(h, st, C_ATTN);
-      RD_CHECK(rd_attention_decode(h->qkv, ldq, pos, h->cos, h->sin, kc, vc, h->keymask, h->ctx_len, h->att, B, nh, hd, c.max_ctx,
-                                   h->ctx_host, c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st)); }
-    { ProfScope ps(h, st, C_O);
-      RD_CHECK(rd_sk_linear(h->sk, h->att, H, w.o, H, h->x, H, B, H, H, RD_SK_RES1, h->x, H, nullptr, h->ssq, dt, st)); }
-    if (fuse_gu) {
-      ProfScope ps(h, st, C_GATEUP);
-      RD_CHECK(rd_sk_linear(h->sk, h->x, H, w.gate_up, H, h->mid, I, B, I, H, RD_SK_SWIGLU, nullptr, 0, &n2, nullptr, dt, st));
-    } else {
-      { ProfScope ps(h, st, C_RMSNORM);
-        RD_CHECK(rd_rmsnorm(h->x, w.ln2, h->xn, B, H, c.rms_eps, nullptr, 0, nullptr, dt, st)); }
-      ProfScope ps(h, st, C_GATEUP);
-      RD_CHECK(rd_sk_linear(h->sk, h->xn, H, w.gate_up, H, h->mid, I, B, I, H, RD_SK_SWIGLU, nullptr, 0, nullptr, nullptr, dt, st));
-    }
-    { ProfScope ps(h, st, C_DOWN);
-      RD_CHECK(rd_sk_linear(h->sk, h->mid, I, w.down, I, h->x, H, B, H, I, RD_SK_RES1, h->x, H, nullptr, h->ssq, dt, st)); }
-  }
-  return RD_OK;
-}
-
 static int linear_fused(rd_llm* h, int cls, const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M,
                         int N, int K, const rd_epilogue* e, const TcFuse* f, cudaStream_t st) {
   ProfScope ps(h, st, cls);
@@ -367,18 +246,12 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     const int64_t ldq = 3 * H + R2;
     const bool decode = q_len == 1 && h->l2_prefetch;
     const long long qkv_bytes = (long long)(3 * H + R2) * H * 2, o_bytes = (long long)H * H * 2, gu_bytes = (long long)2 * I * H * 2;
-    // decode with B <= 32: RMSNorm inside the consuming GEMM (layer 0's input comes from the embedding kernel: no partials yet)
-    const bool fuse = h->fuse_norm && q_len == 1 && M <= 32 && h->algo == 0 && H % 128 == 0;
-    TcFuse f_in1{h->ssq, w.ln1, H / 128, c.rms_eps, nullptr}, f_in2{h->ssq, w.ln2, H / 128, c.rms_eps, nullptr};
-    TcFuse f_out{nullptr, nullptr, 0, 0.f, h->ssq};
     // decode, B <= 32: QKV split-K partials go straight to the attention kernel (no reduction pass in the GEMM)
-    const bool qpart = h->qkv_partials && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && (3 * H + R2) % 4 == 0;
+    const bool qpart = h->qkv_partials && q_len == 1 && M <= 32 && h->algo == 0 && (3 * H + R2) % 4 == 0;
     // decode, B <= 32: o_proj / down_proj partials are finished by the norm kernel that follows them (see od_partials)
-    const bool odp = h->od_partials && !fuse && q_len == 1 && M <= 32 && h->algo == 0 && H <= 16384 && H % 32 == 0;
+    const bool odp = h->od_partials && q_len == 1 && M <= 32 && h->algo == 0 && H <= 16384 && H % 32 == 0;
     int qsplit[2] = {0, 0};
-    if (fuse && l > 0) {
-      RD_CHECK(linear_fused(h, C_QKV, h->x, H, w.qkv, H, h->qkv, ldq, M, 3 * H + R2, H, nullptr, &f_in1, st));
-    } else {
+    {
       if (!(odp && l > 0)) {      // with od partials the previous layer's down_proj + this norm ran as one launch already
         ProfScope ps(h, st, C_RMSNORM);
         // decode: the norm kernels are latency bound and leave HBM idle -> they pull the next GEMM's weights into L2
@@ -411,13 +284,7 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     }
     rd_epilogue eo{};
     eo.residual_dev = h->x; eo.ld_res = H; eo.res_mode = 1;
-    if (fuse) {
-      RD_CHECK(linear_fused(h, C_O, h->att, H, w.o, H, h->x, H, M, H, H, &eo, &f_out, st));
-      rd_epilogue eg{};
-      eg.act = RD_ACT_SWIGLU;
-      RD_CHECK(linear_fused(h, C_GATEUP, h->x, H, w.gate_up, H, h->mid, I, M, I, H, &eg, &f_in2, st));
-      RD_CHECK(linear_fused(h, C_DOWN, h->mid, I, w.down, I, h->x, H, M, H, I, &eo, &f_out, st));
-    } else if (odp) {
+    if (odp) {
       // o_proj partials -> [sum + residual + post_attention_layernorm] -> gate|up -> down_proj partials -> [sum + residual + the
       // NEXT norm on the path: input_layernorm of layer l+1, or model.norm after the last layer (modeling_llama_imgemb.py:658)]
       int sp[2] = {0, 0};
@@ -494,8 +361,6 @@ static int extend_impl(rd_llm* h, const int64_t* ids, const void* img_embeds, in
   }
   { ProfScope ps(h, st, C_EMBED);
     RD_CHECK(rd_embed_splice(ids, h->embed, img_rows, h->x, B, T, H, c.vocab, dt, st)); }
-  if (mega_wanted(h, B)) RD_CHECK(mega_ensure(h));
-  if (sk_wanted(h, B)) RD_CHECK(sk_ensure(h));
   RD_CHECK(run_layers(h, B, T, h->pos, st));
   RD_CHECK(head_and_select(h, B, T, all_logits, st));
   h->ctx_host += T;
@@ -555,29 +420,10 @@ extern "C" int rd_llm_decode_step(rd_llm* h, void* stream) {
   { ProfScope ps(h, st, C_EMBED);
     RD_CHECK(rd_embed_splice(h->cur_tok, h->embed, nullptr, h->x, h->B, 1, c.hidden, c.vocab, c.dtype, st)); }
   h->xn_ready = false;
-  if (mega_wanted(h, h->B) && h->mega != nullptr) RD_CHECK(run_layers_mega(h, h->B, h->pos_cur, st));
-  else if (sk_wanted(h, h->B) && h->sk != nullptr) RD_CHECK(run_layers_sk(h, h->B, h->pos_cur, st));
-  else RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
+  RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
   RD_CHECK(head_and_select(h, h->B, 1, nullptr, st));
   h->ctx_host += 1;
   h->n_generated += 1;
-  return RD_OK;
-}
-
-// 1: single-token steps with B <= 32 run all layers in the persistent kernel of decode_mega.cu; 0 (default): per-op kernels.
-// Call it outside stream capture (switching it on may allocate the kernel's tables).
-extern "C" int rd_llm_set_mega(rd_llm* h, int on) {
-  RD_REQUIRE(h, "rd_llm_set_mega: null handle");
-  h->mega_mode = on ? 1 : 0;
-  if (h->mega_mode && h->mega == nullptr && h->B > 0 && mega_wanted(h, h->B) && check_weights(h) == RD_OK) return mega_ensure(h);
-  return RD_OK;
-}
-
-// 1: in single-token steps with B <= 32 the two RMSNorms of a layer run inside the QKV / gate|up GEMMs
-// (linear_tc.cu: statistics from sum-of-squares partials of the o_proj / down_proj epilogues); 0 (default): separate norm kernels.
-extern "C" int rd_llm_set_fused_norm(rd_llm* h, int on) {
-  RD_REQUIRE(h, "rd_llm_set_fused_norm: null handle");
-  h->fuse_norm = on ? 1 : 0;
   return RD_OK;
 }
 
@@ -595,15 +441,6 @@ extern "C" int rd_llm_set_od_partials(rd_llm* h, int on) {
 extern "C" int rd_llm_set_qkv_partials(rd_llm* h, int on) {
   RD_REQUIRE(h, "rd_llm_set_qkv_partials: null handle");
   h->qkv_partials = on ? 1 : 0;
-  return RD_OK;
-}
-
-// 1: the GEMMs of single-token steps with B <= 32 run as stream-K kernels with the RMSNorm fused on their input
-// (linear_sk.cu); 0 (default): tile x split-K kernels of linear_tc.cu + separate norm kernels.  Call it outside stream capture.
-extern "C" int rd_llm_set_streamk(rd_llm* h, int on) {
-  RD_REQUIRE(h, "rd_llm_set_streamk: null handle");
-  h->sk_mode = on ? 1 : 0;
-  if (h->sk_mode && h->B > 0 && sk_wanted(h, h->B) && check_weights(h) == RD_OK) return sk_ensure(h);
   return RD_OK;
 }
 
@@ -633,7 +470,6 @@ extern "C" int rd_llm_state(rd_llm* h, const int64_t** gen, const int32_t** fini
 // drop any captured decode graph afterwards (the cache pointers change).
 extern "C" int rd_llm_reorder_cache(rd_llm* h, const int32_t* beam_idx_dev, void* stream) {
   RD_REQUIRE(h && beam_idx_dev && h->B > 0, "rd_llm_reorder_cache: no generation in flight");
-  RD_REQUIRE(h->mega == nullptr, "rd_llm_reorder_cache: not available with the persistent decode kernel (its tables hold the cache pointers)");
   const rd_llm_config& c = h->c;
   const int64_t bytes = h->kv_layer_bytes * c.layers;
   if (h->kc_alt == nullptr) {

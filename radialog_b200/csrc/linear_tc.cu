@@ -259,10 +259,7 @@ template <int NT, bool SWIGLU> struct TcCfg {
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = tmem_cols_for(ACCS * NT);
-  // fused RMSNorm on the input (decode tiles): rstd[32] + a [4][32] fp32 scratch; aliases the residual / lora_t staging
-  // area where there is one (the fused GEMMs have plain epilogues), otherwise 640 B of its own
-  static constexpr int NORM_BYTES = (NT <= 32 && !STAGE_EPI) ? 640 : 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EXTRA_BYTES + NORM_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EXTRA_BYTES;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
@@ -285,7 +282,7 @@ template <int NT, bool SWIGLU> struct TsCfg {
   static constexpr int RING_BYTES = WST * W_STAGE + XST * X_STAGE;
   static constexpr int BAR_BYTES = 512;
   static constexpr bool STAGE_EPI = (NT <= 32) && !SWIGLU;
-  static constexpr int EXTRA_BYTES = STAGE_EPI ? (NT * BLOCK_N * 2 + NT * 16 * 2) : 640;
+  static constexpr int EXTRA_BYTES = STAGE_EPI ? (NT * BLOCK_N * 2 + NT * 16 * 2) : 0;
   static constexpr int SMEM_BYTES = RING_BYTES + 1024 + BAR_BYTES + EXTRA_BYTES;
   static constexpr bool OK = TSLOTS >= 2 && TSLOTS <= 8 && WST >= 2 && WST <= 8 && XST >= 2 && XST <= 8;
 };
@@ -300,13 +297,6 @@ struct TcParams {
   uint32_t* ws_ctr;      // [tiles]
   uint64_t hint_w, hint_x;
   unsigned long long* trace;   // development aid: [cta][8] globaltimer stamps (nullptr = off)
-  // RMSNorm fused on the input (m_tiles == 1, NT <= 32): x is the raw residual stream; rstd from the [norm_tiles][32]
-  // sum-of-squares partials the producing GEMM left at norm_ssq; xn = T(w * T(x * rstd)) formed in the smem stage
-  const float* norm_ssq;
-  const void* norm_w;
-  int norm_tiles;
-  float norm_eps;
-  float* ssq_out;              // EPI_RES1 (N % 128 == 0): sum_n out[m,n]^2 of this 128-row tile -> ssq_out[tile][m]
   // "partials out" split-K (decode QKV GEMM, m_tiles == 1, plain epilogue): every CTA stores its fp32 partial tile to the slab
   // part_out[split][NT][N] and is done - no cluster, no DSMEM, no reduction pass.  The consumer (attention_decode_kernel) sums
   // the splits in fixed order and applies the single rounding T(Wx) when it reads q/k/v.
@@ -353,7 +343,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   uint32_t* flag_smem = tmem_ptr_smem + 1;
-  uint64_t* xn_bar = reinterpret_cast<uint64_t*>(flag_smem + 1);     // [STAGES] "token tile normalised" (fused RMSNorm)
   // TS barriers (same area, own layout): W ring full/empty, token ring full/empty, TMEM slot ready/empty, accumulators, misc
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
   uint64_t* w_empty = w_full + 8;
@@ -367,10 +356,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     flag_smem = tmem_ptr_smem + 1;
   }
   volatile uint32_t* dep_flag = flag_smem + 1;                       // TS: set once the producing kernel's output may be read
-  const bool fuse_norm = !TS && NT <= 32 && p.norm_ssq != nullptr;
-  // rstd[32] + [4][32] scratch of the fused norm / of the sum-of-squares epilogue
-  float* s_norm = reinterpret_cast<float*>(smem + RING_BYTES + BAR_BYTES);                       // fused norm (plain epilogues)
-  float* s_ssq4 = reinterpret_cast<float*>(smem + RING_BYTES + BAR_BYTES + NT * BLOCK_N * 2);    // = lora_t staging area (EPI_RES1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // raster order: blockIdx.x runs fastest in the hardware's CTA dispatch.  m_fast puts the token tiles there, so that CTAs
@@ -397,7 +382,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       }
       *dep_flag = 0u;
     } else {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&xn_bar[s], 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -531,7 +516,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     int s = 0;
     uint32_t ph = 0;
     for (int i = 0; i < nkb; ++i) {
-      mbar_wait(fuse_norm ? &xn_bar[s] : &full_bar[s], ph, 2);
+      mbar_wait(&full_bar[s], ph, 2);
       tc_fence_after();
       const uint64_t da = d0 + (uint64_t)((uint32_t)s * (Cfg::STAGE_BYTES >> 4));
       const uint64_t du = da + (uint64_t)(Cfg::A_BYTES >> 4);
@@ -604,61 +589,6 @@ _Pragma("unroll")
       }
     }
     pdl_wait();
-    if (NT <= 32 && fuse_norm) {
-      // ---- RMSNorm fused on the input: statistics from the producer's per-tile partials (fixed order), then every
-      // ---- token tile is normalised in its smem stage between the TMA and the MMA by the warp that owns the stage
-      const int e = threadIdx.x - 64, ew = warp - 2;
-      {
-        const int j = e & 31, part = e >> 5;
-        float v = 0.f;
-#pragma unroll 4
-        for (int t = part; t < p.norm_tiles; t += 4) v += __ldcg(p.norm_ssq + t * 32 + j);
-        s_norm[32 + part * 32 + j] = v;
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (e < 32) {
-          const float tot = ((s_norm[32 + e] + s_norm[64 + e]) + s_norm[96 + e]) + s_norm[128 + e];
-          s_norm[e] = 1.0f / sqrtf(tot / (float)p.K + p.norm_eps);       // torch.rsqrt(variance + eps), fp32
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-      }
-      const T* lnw = reinterpret_cast<const T*>(p.norm_w);
-      const int pc = lane & 7, ra = lane >> 3;
-      // A stage always belongs to the same warp, so each warp meets the phases of its stages' barriers in order (waiting
-      // for phase k of a barrier whose phase k-1 is still open would return at once: mbarrier parity aliasing).
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        if ((s & 3) != ew) continue;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        // the two 16-byte chunks of the norm weights this lane needs for the tile (rows ra + 4i: r & 7 is ra or ra + 4)
-        const T* wk = lnw + (int64_t)(kb_begin + i) * BLOCK_K;
-        const Vec8<T> w0 = ld16(wk + (pc ^ ra) * 8), w1 = ld16(wk + (pc ^ (ra + 4)) * 8);
-        if (lane == 0) mbar_wait(&full_bar[s], ph, 4);
-        __syncwarp();
-        uint8_t* xt = smem + s * Cfg::STAGE_BYTES + Cfg::ACCS * Cfg::A_BYTES;
-#pragma unroll
-        for (int q = 0; q < NT / 4; ++q) {
-          const int r = ra + 4 * q;
-          if (r >= m_valid) break;
-          const float rs = s_norm[r];
-          uint4* cp = reinterpret_cast<uint4*>(xt + r * 128 + pc * 16);
-          uint4 raw = *cp;
-          const Vec8<T> xv = *reinterpret_cast<const Vec8<T>*>(&raw);
-          const Vec8<T>& wv = (q & 1) ? w1 : w0;
-          Vec8<T> o;
-#pragma unroll
-          for (int el = 0; el < 8; ++el) {
-            const float y = Tr<T>::rr(Tr<T>::f(xv.v[el]) * rs);          // .to(weight.dtype)
-            o.v[el] = Tr<T>::r(Tr<T>::f(wv.v[el]) * y);                  // weight * hidden_states
-          }
-          *cp = *reinterpret_cast<const uint4*>(&o);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&xn_bar[s])) : "memory");
-        }
-      }
-    }
     cx.outp = out + n; cx.ldo = p.ldo;
     cx.resp = reinterpret_cast<const T*>(p.epi.residual) + n; cx.ld_res = p.epi.ld_res;
     cx.lora_t = reinterpret_cast<const T*>(p.epi.lora_t); cx.lora_scale = p.epi.lora_scale;
@@ -802,29 +732,15 @@ _Pragma("unroll")
 _Pragma("unroll")
               for (int j = 0; j < 16; ++j) resv[j] = (c + j < m_valid) ? Tr<T>::f(rsrc[(int64_t)(m0 + c + j) * cx.ld_res]) : 0.f;
             }
-            float yv[16];
 _Pragma("unroll")
             for (int j = 0; j < 16; ++j) {
-              yv[j] = 0.f;
               if (c + j < m_valid)
-                yv[j] = finish_store<T, SWIGLU, MODE>(p.epi, cx, __uint_as_float(r[j]), SWIGLU ? __uint_as_float(ru[j]) : 0.f, m0 + c + j, n, c + j,
+                finish_store<T, SWIGLU, MODE>(p.epi, cx, __uint_as_float(r[j]), SWIGLU ? __uint_as_float(ru[j]) : 0.f, m0 + c + j, n, c + j,
                                                       (MODE == EPI_RES1 || MODE == EPI_AFFINE) && rsrc != nullptr, resv[j]);
-            }
-            if (MODE == EPI_RES1 && Cfg::STAGE_EPI && p.ssq_out != nullptr) {      // N % 128 == 0: the whole warp is here
-_Pragma("unroll")
-              for (int j = 0; j < 16; ++j) {
-                const float t2 = warp_sum(yv[j] * yv[j]);
-                if (lane == 0) s_ssq4[(warp - 2) * 32 + c + j] = t2;
-              }
             }
           }
         }
       )
-      if (Cfg::STAGE_EPI && p.epi_mode == EPI_RES1 && p.ssq_out != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int e = threadIdx.x - 64;
-        if (e < m_valid) p.ssq_out[n_tile * 32 + e] = ((s_ssq4[e] + s_ssq4[32 + e]) + s_ssq4[64 + e]) + s_ssq4[96 + e];
-      }
     } else if (p.cluster) {
       // split-K inside a thread-block cluster: park the fp32 partial tile in this CTA's (now idle) pipeline smem;
       // after the cluster barrier every CTA reduces its own slice of the token columns over DSMEM.
@@ -923,20 +839,11 @@ _Pragma("unroll")
               float acc = 0.f, accu = 0.f;
 _Pragma("unroll")
               for (int s = 0; s < 8; ++s) { acc += v[t][s]; if (SWIGLU) accu += vu[t][s]; }
-              const float yv = finish_store<T, SWIGLU, MODE>(p.epi, cx, acc, accu, m0 + j, n, j);
-              if (MODE == EPI_RES1 && Cfg::STAGE_EPI && p.ssq_out != nullptr) {    // N % 128 == 0: the whole warp is here
-                const float t2 = warp_sum(yv * yv);
-                if (lane == 0) s_ssq4[(warp - 2) * 32 + j] = t2;
-              }
+              finish_store<T, SWIGLU, MODE>(p.epi, cx, acc, accu, m0 + j, n, j);
             }
           }
         }
       )
-      if (Cfg::STAGE_EPI && p.epi_mode == EPI_RES1 && p.ssq_out != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int e = threadIdx.x - 64;
-        if (e < m_valid && (e % p.splits) == split) p.ssq_out[n_tile * 32 + e] = ((s_ssq4[e] + s_ssq4[32 + e]) + s_ssq4[64 + e]) + s_ssq4[96 + e];
-      }
     }
     // nobody leaves (and frees its smem) while a peer may still be reading it
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -1129,15 +1036,6 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
   if (g_fuse != nullptr) {
     const TcFuse& f = *g_fuse;
     RD_REQUIRE(NT <= 32 && m_tiles == 1, "rd_linear_tc_fused: needs M <= 32");
-    if (f.norm_ssq != nullptr) {
-      RD_REQUIRE(p.epi_mode == EPI_PLAIN, "rd_linear_tc_fused: the fused RMSNorm needs a plain (or SwiGLU) epilogue");
-      p.norm_ssq = f.norm_ssq; p.norm_w = f.norm_w; p.norm_tiles = f.norm_tiles; p.norm_eps = f.norm_eps;
-    }
-    if (f.ssq_out != nullptr) {
-      RD_REQUIRE(p.epi_mode == EPI_RES1 && N % BLOCK_N == 0 && (splits == 1 || use_cluster) && Cfg::STAGE_EPI,
-                 "rd_linear_tc_fused: sum-of-squares output needs the residual epilogue, N %% 128 == 0 and no workspace split-K");
-      p.ssq_out = f.ssq_out;
-    }
     if (f.part_out != nullptr) {
       const bool plain = !SWIGLU && p.epi_mode == EPI_PLAIN;
       const int64_t need = (int64_t)splits * NT * N * 4;
@@ -1189,8 +1087,8 @@ int launch_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out,
   cfg.attrs = attr; cfg.numAttrs = na;
   if constexpr (NT <= 32) {
     // TMEM-staged variant: decode tiles with a plain / residual / SwiGLU epilogue (see TsCfg)
-    const bool ts = TsCfg<NT, SWIGLU>::OK && g_ts_mode && m_tiles == 1 && (p.epi_mode == EPI_PLAIN || p.epi_mode == EPI_RES1) && p.norm_ssq == nullptr &&
-                    p.ssq_out == nullptr && kb_total / splits >= 2;
+    const bool ts = TsCfg<NT, SWIGLU>::OK && g_ts_mode && m_tiles == 1 && (p.epi_mode == EPI_PLAIN || p.epi_mode == EPI_RES1) &&
+                    kb_total / splits >= 2;
     if (ts) {
       using Ts = TsCfg<NT, SWIGLU>;
       RD_SMEM_ATTR_ONCE(Ts::SMEM_BYTES, linear_tc_kernel<T, NT, SWIGLU, true>);

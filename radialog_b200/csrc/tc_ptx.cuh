@@ -1,4 +1,4 @@
-// PTX wrappers shared by the persistent decode kernel (decode_mega.cu): mbarrier, TMA (cp.async.bulk[.tensor]),
+// PTX wrappers shared by linear_wide.cu and attention_prefill_tc.cu: mbarrier, TMA (cp.async.bulk[.tensor]),
 // tcgen05 (alloc / mma / commit / ld) and the UMMA descriptors.  sm_100a only.
 #pragma once
 #include <cuda.h>
@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t mbar_wait(uint64_t* bar, uint32_t parity, in
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 6000000000ll) {      // ~3 s
-        printf("decode_mega: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x, parity);
+        printf("tcptx: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x, parity);
         __trap();
       }
     }

@@ -151,9 +151,6 @@ class LlamaForCausalLM:
         self._cached_ids: Optional[torch.Tensor] = None     # device copy of the ids whose KV are in the cache
         self._img_w_packed = None
         self.algo = _lib.ALGO_AUTO
-        self.mega = False     # persistent all-layers decode kernel (experimental)
-        self.fused_norm = False   # RMSNorm inside the decode GEMMs (experimental)
-        self.streamk = False  # stream-K decode GEMMs with fused RMSNorm (experimental)
         self.qkv_partials = True  # QKV GEMM hands its fp32 split-K partials to the attention kernel (default)
         self.od_partials = True   # o_proj / down_proj partials finished by the norm launch that follows them (default)
         self.use_cuda_graph = True
@@ -336,9 +333,6 @@ class LlamaForCausalLM:
             for key, t in lw.items():
                 _lib.check(sw(h, i, slots[key], _lib.ptr(t)), f"set_weight layer {i} {key}")
         _lib.check(self._lib.rd_llm_set_algo(h, self.algo), "set_algo")
-        _lib.check(self._lib.rd_llm_set_mega(h, 1 if self.mega else 0), "set_mega")
-        _lib.check(self._lib.rd_llm_set_streamk(h, 1 if self.streamk else 0), "set_streamk")
-        _lib.check(self._lib.rd_llm_set_fused_norm(h, 1 if self.fused_norm else 0), "set_fused_norm")
         _lib.check(self._lib.rd_llm_set_qkv_partials(h, 1 if self.qkv_partials else 0), "set_qkv_partials")
         _lib.check(self._lib.rd_llm_set_od_partials(h, 1 if self.od_partials else 0), "set_od_partials")
 
@@ -359,13 +353,6 @@ class LlamaForCausalLM:
         if self._h is not None:
             _lib.check(self._lib.rd_llm_set_algo(self._h, algo), "set_algo")
 
-    def set_fused_norm(self, on: bool):
-        """RMSNorm inside the QKV / gate|up GEMMs of single-token steps, or (default) as separate kernels."""
-        self.fused_norm = bool(on)
-        self._graphs = {}
-        if self._h is not None:
-            _lib.check(self._lib.rd_llm_set_fused_norm(self._h, 1 if on else 0), "set_fused_norm")
-
     def set_od_partials(self, on: bool):
         """Single-token steps: o_proj / down_proj leave fp32 split-K partials and the norm launch that follows sums them, adds the
         residual and normalises (default), or the GEMMs reduce over their cluster and plain norm kernels follow."""
@@ -381,20 +368,6 @@ class LlamaForCausalLM:
         self._graphs = {}
         if self._h is not None:
             _lib.check(self._lib.rd_llm_set_qkv_partials(self._h, 1 if on else 0), "set_qkv_partials")
-
-    def set_streamk(self, on: bool):
-        """Decode GEMMs as stream-K kernels with fused RMSNorm, or (default) tile x split-K kernels + norm kernels."""
-        self.streamk = bool(on)
-        self._graphs = {}
-        if self._h is not None:
-            _lib.check(self._lib.rd_llm_set_streamk(self._h, 1 if on else 0), "set_streamk")
-
-    def set_mega(self, on: bool):
-        """Single-token steps through the persistent all-layers kernel, or (default) one kernel per op."""
-        self.mega = bool(on)
-        self._graphs = {}
-        if self._h is not None:
-            _lib.check(self._lib.rd_llm_set_mega(self._h, 1 if on else 0), "set_mega")
 
     def _state(self):
         gen, fin, logits, hidden = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -226,82 +226,6 @@ def test_sixteen_image_set_token_id_equality_real_width(cuda_dev):
     assert_ids_match(out, o_ids, o_scores, prompts.shape[1], dtype, "16-image set", min_exact_rows=0.75)
 
 
-@pytest.mark.parametrize("dtype_name,B,layers", [("float16", 3, 2), ("bfloat16", 32, 3), ("float16", 1, 2), ("float16", 17, 2)])
-def test_persistent_decode_kernel_matches_per_op_kernels(cuda_dev, dtype_name, B, layers):
-    """decode_mega.cu (all layers of a decode step in one persistent kernel) against the one-kernel-per-op path and the
-    oracle: same rounding contract, so step logits agree to fp32-summation-order noise and greedy ids match."""
-    dtype = DT[dtype_name]
-    cfg = synth.tiny_llama_cfg(num_hidden_layers=layers)
-    model, orc, _ = build(cfg, dtype, cuda_dev)
-    prompts = synth.make_prompts(B, seed=99 + B, ragged=True)
-    img = img_tokens(B, cfg, seed=B)
-    n_new = 9
-    outs = {}
-    for mega in (False, True):
-        model.set_mega(mega)
-        outs[mega] = model.generate(prompts.to(cuda_dev), img_embeds=img.to(cuda_dev), max_new_tokens=n_new, suppress_eos=True,
-                                    return_dict_in_generate=True, output_scores=True)
-    model.set_mega(False)
-    a, b = outs[False], outs[True]
-    scale = a.scores[1].float().abs().max().item()
-    # step 0 comes from the prefill (identical code either way); step 1 is the first decode step
-    err1 = (a.scores[1].float() - b.scores[1].float()).abs().max().item()
-    tol = (2e-3 if dtype == torch.float16 else 1.6e-2) * scale      # ~2 storage-dtype ulps at the logit scale
-    assert err1 <= tol, f"first decode step logits differ between the two paths: {err1:.4g} vs scale {scale:.4g}"
-    o_ids, o_scores = orc.generate(prompts, img, n_new, suppress_eos=True, return_scores=True)
-    assert_ids_match(b.sequences.cpu(), o_ids, o_scores, prompts.shape[1], dtype, f"mega {dtype_name} B={B}", min_exact_rows=0.75)
-
-
-@pytest.mark.parametrize("dtype_name,B,layers", [("float16", 3, 2), ("bfloat16", 32, 3), ("float16", 1, 2), ("bfloat16", 17, 2)])
-def test_streamk_decode_gemms_match_tile_splitk_path(cuda_dev, dtype_name, B, layers):
-    """linear_sk.cu (stream-K decode GEMMs with the RMSNorm fused on their input) against the tile x split-K kernels +
-    norm kernels and the oracle: same rounding contract, only the fp32 summation order differs."""
-    dtype = DT[dtype_name]
-    cfg = synth.tiny_llama_cfg(num_hidden_layers=layers)
-    model, orc, _ = build(cfg, dtype, cuda_dev)
-    prompts = synth.make_prompts(B, seed=199 + B, ragged=True)
-    img = img_tokens(B, cfg, seed=B + 1)
-    n_new = 9
-    outs = {}
-    for sk in (False, True):
-        model.set_streamk(sk)
-        outs[sk] = model.generate(prompts.to(cuda_dev), img_embeds=img.to(cuda_dev), max_new_tokens=n_new, suppress_eos=True,
-                                  return_dict_in_generate=True, output_scores=True)
-    model.set_streamk(False)
-    a, b = outs[False], outs[True]
-    scale = a.scores[1].float().abs().max().item()
-    err1 = (a.scores[1].float() - b.scores[1].float()).abs().max().item()
-    tol = (2e-3 if dtype == torch.float16 else 1.6e-2) * scale      # ~2 storage-dtype ulps at the logit scale
-    assert err1 <= tol, f"first decode step logits differ between the two paths: {err1:.4g} vs scale {scale:.4g}"
-    o_ids, o_scores = orc.generate(prompts, img, n_new, suppress_eos=True, return_scores=True)
-    assert_ids_match(b.sequences.cpu(), o_ids, o_scores, prompts.shape[1], dtype, f"stream-K {dtype_name} B={B}", min_exact_rows=0.75)
-
-
-@pytest.mark.parametrize("dtype_name,B,layers", [("float16", 3, 2), ("bfloat16", 32, 3), ("float16", 1, 2), ("bfloat16", 9, 2)])
-def test_rmsnorm_fused_into_decode_gemms_matches_separate_norm_kernels(cuda_dev, dtype_name, B, layers):
-    """Default decode path (RMSNorm applied to the token tiles inside the QKV / gate|up GEMMs, statistics from the
-    o_proj / down_proj epilogues) against separate norm kernels and the oracle."""
-    dtype = DT[dtype_name]
-    cfg = synth.tiny_llama_cfg(num_hidden_layers=layers)
-    model, orc, _ = build(cfg, dtype, cuda_dev)
-    prompts = synth.make_prompts(B, seed=299 + B, ragged=True)
-    img = img_tokens(B, cfg, seed=B + 2)
-    n_new = 9
-    outs = {}
-    for fused in (False, True):
-        model.set_fused_norm(fused)
-        outs[fused] = model.generate(prompts.to(cuda_dev), img_embeds=img.to(cuda_dev), max_new_tokens=n_new, suppress_eos=True,
-                                     return_dict_in_generate=True, output_scores=True)
-    model.set_fused_norm(False)
-    a, b = outs[False], outs[True]
-    scale = a.scores[1].float().abs().max().item()
-    err1 = (a.scores[1].float() - b.scores[1].float()).abs().max().item()
-    tol = (2e-3 if dtype == torch.float16 else 1.6e-2) * scale      # ~2 storage-dtype ulps at the logit scale
-    assert err1 <= tol, f"first decode step logits differ between the two paths: {err1:.4g} vs scale {scale:.4g}"
-    o_ids, o_scores = orc.generate(prompts, img, n_new, suppress_eos=True, return_scores=True)
-    assert_ids_match(b.sequences.cpu(), o_ids, o_scores, prompts.shape[1], dtype, f"fused norm {dtype_name} B={B}", min_exact_rows=0.75)
-
-
 @pytest.mark.parametrize("dtype_name,B,layers,lora", [("float16", 3, 2, True), ("bfloat16", 32, 3, True), ("float16", 1, 2, True),
                                                       ("float16", 17, 2, False), ("float16", 32, 4, True)])
 def test_qkv_partials_to_attention_bit_identical_to_gemm_side_reduction(cuda_dev, dtype_name, B, layers, lora):

@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--shapes", default="")
     ap.add_argument("--stages", default="0", help="comma list of pipeline depths to try per nt (0 = by K)")
+    ap.add_argument("--sustained", type=int, default=0, help="N > 0: time N back-to-back launches with no L2 flush in between (power-limited "
+                    "clocks, as inside a prefill) and print torch.matmul (cuBLAS) on the same shape beside it")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -75,7 +77,17 @@ def main():
                 run()
             torch.cuda.synchronize()
             ts = []
-            for _ in range(args.iters):
+            if args.sustained > 0:
+                for _ in range(args.sustained):      # bring the chip to its sustained state first
+                    run()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(args.sustained):
+                    run()
+                b.record()
+                torch.cuda.synchronize()
+                ts = [a.elapsed_time(b) * 1e3 / args.sustained]
+            for _ in range(args.iters if args.sustained == 0 else 0):
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -86,6 +98,18 @@ def main():
             ts.sort()
             us = ts[len(ts) // 2]
             line.append(f"{label}: {us:7.1f} us ({flops / us / 1e6 / peak:.2f})")
+        if args.sustained > 0:
+            wt = w.t().contiguous()
+            for _ in range(args.sustained):
+                torch.matmul(x, wt)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.sustained):
+                torch.matmul(x, wt)
+            b.record()
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b) * 1e3 / args.sustained
+            line.append(f"cuBLAS (no epilogue): {us:7.1f} us ({flops / us / 1e6 / peak:.2f})")
         lib.rd_linear_wide_force_stages(0)
         lib.rd_linear_wide_persistent(1)
         lib.rd_linear_wide_force_nt(0)

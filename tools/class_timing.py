@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Per-kernel-class time of eager decode steps (CUDA events around each launch) for the stream-K and the tile x split-K
-decode paths (development tool).  python tools/class_timing.py [B]"""
+"""Per-kernel-class time of eager decode steps (CUDA events around each launch), with the o_proj / down_proj partials finished
+by the norm kernel (default) and by the GEMMs' own cluster reduction (development tool).  python tools/class_timing.py [B]"""
 import os
 import sys
 
@@ -19,9 +19,8 @@ cfg = synth.LlamaCfg()
 sd = synth.make_llama_weights(cfg, seed=0, dtype=dtype, device="cuda:0")
 llm = LlamaForCausalLM.from_state_dict(cfg, sd, torch_dtype=dtype, device=dev)
 del sd
-modes = [("fused_norm", lambda: (llm.set_streamk(False), llm.set_fused_norm(True))),
-         ("separate_norm", lambda: (llm.set_streamk(False), llm.set_fused_norm(False))),
-         ("streamk", lambda: llm.set_streamk(True))]
+modes = [("od_partials", lambda: llm.set_od_partials(True)),
+         ("cluster_reduce", lambda: llm.set_od_partials(False))]
 for sk, fn in modes:
     fn()
     prof = llm.profile_decode_steps(B, 64, steps=8)
