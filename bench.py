@@ -579,6 +579,7 @@ def main():
     ap.add_argument("--no-b1", action="store_true", help="skip the batch-1 latency leg")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference GPU PyTorch path leg")
     ap.add_argument("--no-mega", action="store_true", help=argparse.SUPPRESS)      # accepted for old command lines; no effect
+    ap.add_argument("--wide-pair", type=int, default=-1, help=argparse.SUPPRESS)   # A/B switch of the CTA-pair GEMM (development)
     ap.add_argument("--ref-dec-tokens", type=int, default=4, help="decode steps per bounded CPU sample")
     ap.add_argument("--no-full-report", action="store_true", help="reference arm: skip the one complete 128-token report in the warm-up")
     args = ap.parse_args()
@@ -587,6 +588,9 @@ def main():
     elif args.workload == "chat":
         run_chat(args)
     else:
+        if args.wide_pair >= 0:
+            from radialog_b200 import _lib
+            _lib.load().rd_linear_wide_pair(args.wide_pair)
         run_own_arm(args)
 
 

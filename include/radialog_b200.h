@@ -94,7 +94,11 @@ int rd_linear_tmem_staging(int on);
 int rd_linear_wide_persistent(int on);
 int rd_linear_wide_min_tiles(int n);
 int rd_linear_wide_force_nt(int nt);
-int rd_linear_wide_force_stages(int stages);   /* 2..4 pipeline stages (the rest of the 224 KB holds epilogue chunk buffers); 0 = by K */
+int rd_linear_wide_force_stages(int stages);   /* 2..6 pipeline stages (the rest of the 224 KB holds epilogue chunk buffers); 0 = by K */
+/* 1 (default): the persistent kernel runs as CTA pairs - clusters of two CTAs issue one 256-row tcgen05.mma.cta_group::2 per
+ * k-step, each CTA staging its own 128 weight rows and HALF of the shared token tile (a third less shared-memory and L2 traffic
+ * per flop, 6 instead of 4 pipeline stages); 0: every CTA on its own.  Bit-identical results. */
+int rd_linear_wide_pair(int on);
 /* Launch every kernel with the programmatic-dependent-launch attribute (prologue of kernel N+1 — barrier init, TMEM
  * allocation, the first weight tiles — overlaps the tail of kernel N).  On by default; 0 switches it off. */
 int rd_set_pdl(int on);

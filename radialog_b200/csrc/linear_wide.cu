@@ -37,7 +37,9 @@ extern "C" int rd_linear_wide_persistent(int on) { g_wide_persistent = on; retur
 static int g_wide_force_nt = 0;      // test hook: token-tile width (0 = heuristic)
 extern "C" int rd_linear_wide_force_nt(int nt) { g_wide_force_nt = nt; return RD_OK; }
 static int g_wide_force_stages = 0;  // test hook: pipeline stages 2..4 (0 = by K)
-extern "C" int rd_linear_wide_force_stages(int s) { g_wide_force_stages = (s >= 2 && s <= 4) ? s : 0; return RD_OK; }
+extern "C" int rd_linear_wide_force_stages(int s) { g_wide_force_stages = (s >= 2 && s <= 6) ? s : 0; return RD_OK; }
+static int g_wide_pair = 1;          // 1: CTA pairs (cta_group::2, 256-row UMMA, each CTA stages half of the token tile)
+extern "C" int rd_linear_wide_pair(int on) { g_wide_pair = on; return RD_OK; }
 static int g_wide_min_tiles = 149;   // below this the one-tile-per-CTA kernel is used (nothing to overlap)
 extern "C" int rd_linear_wide_min_tiles(int n) { g_wide_min_tiles = n; return RD_OK; }
 
@@ -50,9 +52,13 @@ constexpr int UK = 16;
 constexpr int W_BYTES = WROWS * BK * 2;          // 16 KB
 constexpr int X_BYTES_MAX = 256 * BK * 2;        // 32 KB
 constexpr int STAGE_BYTES = W_BYTES + X_BYTES_MAX;
+constexpr int PAIR_X_BYTES_MAX = 128 * BK * 2;   // CTA pair: each CTA stages half of the token tile
+constexpr int PAIR_STAGE_BYTES = W_BYTES + PAIR_X_BYTES_MAX;   // 32 KB
 constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES_PAIR = 6;
 constexpr int MAX_NBUF = 16;
 constexpr int BUF_BYTES = 32 * 128 * 2;          // epilogue chunk buffer: CR <= 32 token rows of 128 features (residual in, result out)
+static_assert(MAX_STAGES * STAGE_BYTES == MAX_STAGES_PAIR * PAIR_STAGE_BYTES, "both variants split the same 192 KB ring");
 constexpr int RING_EPI_BYTES = MAX_STAGES * STAGE_BYTES + 4 * BUF_BYTES;   // 224 KB split between the pipeline and the chunk buffers:
                                                  // 4 stages + 4 buffers (deep K), 3 + 10, or 2 + 16 (K <= 128: the tile is all epilogue)
 constexpr int BAR_BYTES = 512;
@@ -78,7 +84,45 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-template <class T, bool SWIGLU>
+// ---- CTA pair (cta_group::2) helpers: the two CTAs of a cluster run one 256-row UMMA; the even CTA (rank 0) issues it ----
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {      // shared::cluster address of CTA `rank`'s copy
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into this CTA's shared memory whose transaction bytes are counted on the mbarrier at cluster address `bar_cluster`
+// (the leader CTA's "stage full" barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// MMA completion -> the mbarrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+template <class T, bool SWIGLU, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                    const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const WideParams p) {
@@ -87,20 +131,28 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int STAGES = p.stages;
+  constexpr int SB = PAIR ? PAIR_STAGE_BYTES : STAGE_BYTES;    // bytes per pipeline stage
+  constexpr int MAXS = PAIR ? MAX_STAGES_PAIR : MAX_STAGES;
+  // CTA pair: both CTAs walk the same list of (256 weight rows x NT tokens) tiles; CTA `rank` owns weight rows [128 rank, +128)
+  // (its A operand and its accumulator lanes) and stages token rows [NT/2 rank, +NT/2) of the shared B operand
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;           // index / count of the tile walkers
+  const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // SwiGLU result rows are 64 features wide: twice as many (half-size) buffers, minus the T(g) / T(u) exchange (2 x 4 KB)
   const int NBUF = SWIGLU ? (2 * p.nbuf - 2 < MAX_NBUF ? 2 * p.nbuf - 2 : MAX_NBUF) : p.nbuf;
-  uint8_t* epi_s = smem + STAGES * STAGE_BYTES;
+  uint8_t* epi_s = smem + STAGES * SB;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_EPI_BYTES);
-  uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tfull = empty_bar + MAX_STAGES;      // [2] accumulator buffer complete
-  uint64_t* tempty = tfull + 2;                  // [2] accumulator buffer drained (128 epilogue threads arrive)
+  uint64_t* empty_bar = full_bar + MAXS;
+  uint64_t* tfull = empty_bar + MAXS;            // [2] accumulator buffer complete
+  uint64_t* tempty = tfull + 2;                  // [2] accumulator buffer drained (every epilogue thread of the tile arrives; pair: on the leader's)
   uint64_t* res_full = tempty + 2;               // [NBUF] residual chunk landed
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_full + MAX_NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_total = (p.K + BK - 1) / BK;
   const int NT = p.NT, CR = p.CR;
-  const uint32_t stage_tx = (uint32_t)(W_BYTES + NT * BK * 2);
+  const int XROWS = PAIR ? NT / 2 : NT;          // token rows this CTA stages per k-block
+  const uint32_t stage_tx = (uint32_t)((PAIR ? 2 : 1) * (W_BYTES + XROWS * BK * 2));   // pair: both CTAs' bytes land on the leader's barrier
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -109,16 +161,22 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
     if (p.has_res) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_res)) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PAIR ? 256 : 128); }
     for (int b = 0; b < MAX_NBUF; ++b) mbar_init(&res_full[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's TMA loads and barrier arrivals target this CTA's (now initialised) mbarriers
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -126,58 +184,69 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     int mt, nt;
     if (p.m_fast) { mt = t % p.m_tiles; nt = t / p.m_tiles; } else { nt = t % p.n_tiles; mt = t / p.n_tiles; }
     m0 = mt * NT;
-    n0 = nt * FEATS;
+    n0 = (PAIR ? nt * 2 + (int)rank : nt) * FEATS;
   };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    auto load = [&](void* dst, const CUtensorMap* map, int s, int c0, int c1) {
+      if (PAIR) tma_load_2d_pair(dst, map, mapa_u32(smem_u32(&full_bar[s]), 0u), c0, c1, HINT_NORMAL);
+      else tma_load_2d(dst, map, &full_bar[s], c0, c1, HINT_NORMAL);
+    };
     auto load_w = [&](int s, int kb, int n0) {
-      uint8_t* sp = smem + s * STAGE_BYTES;
+      uint8_t* sp = smem + s * SB;
       if (SWIGLU) {
-        tma_load_2d(sp, &map_w, &full_bar[s], kb * BK, n0, HINT_NORMAL);                        // 64 gate rows
-        tma_load_2d(sp + W_BYTES / 2, &map_w, &full_bar[s], kb * BK, p.N + n0, HINT_NORMAL);    // 64 up rows
+        load(sp, &map_w, s, kb * BK, n0);                        // 64 gate rows
+        load(sp + W_BYTES / 2, &map_w, s, kb * BK, p.N + n0);    // 64 up rows
       } else {
-        tma_load_2d(sp, &map_w, &full_bar[s], kb * BK, n0, HINT_NORMAL);
+        load(sp, &map_w, s, kb * BK, n0);
       }
     };
+    const bool expects = !PAIR || rank == 0;     // pair: the leader's barrier carries the expected byte count of both CTAs
     // weights never depend on the previous kernel: the first stages' weight k-blocks are requested before the PDL wait
     int pre = 0;
-    if ((int)blockIdx.x < p.tiles) {
+    if (unit < p.tiles) {
       int m0, n0;
-      tile_coords(blockIdx.x, m0, n0);
+      tile_coords(unit, m0, n0);
       pre = kb_total < STAGES ? kb_total : STAGES;
       if (elect_one()) {
-        for (int i = 0; i < pre; ++i) { mbar_expect_tx(&full_bar[i], stage_tx); load_w(i, i, n0); }
+        for (int i = 0; i < pre; ++i) {
+          if (expects) mbar_expect_tx(&full_bar[i], stage_tx);
+          load_w(i, i, n0);
+        }
       }
       __syncwarp();
     }
     pdl_wait();
     int s = 0, it = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+    for (int t = unit; t < p.tiles; t += n_units) {
       int m0, n0;
       tile_coords(t, m0, n0);
       for (int kb = 0; kb < kb_total; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1u, 1);        // first pass: the barrier's "previous phase" counts as complete
         __syncwarp();
         if (elect_one()) {
-          if (it >= pre) { mbar_expect_tx(&full_bar[s], stage_tx); load_w(s, kb, n0); }
-          tma_load_2d(smem + s * STAGE_BYTES + W_BYTES, &map_x, &full_bar[s], kb * BK, m0, HINT_NORMAL);
+          if (it >= pre) {
+            if (expects) mbar_expect_tx(&full_bar[s], stage_tx);
+            load_w(s, kb, n0);
+          }
+          load(smem + s * SB + W_BYTES, &map_x, s, kb * BK, m0 + (int)rank * XROWS);
         }
         __syncwarp();
         if (it < STAGES) ++it;
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc(Tr<T>::umma_fmt, WROWS, NT);
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (pair: the leader CTA issues the 256-row UMMA for both) =====================
+    const uint32_t idesc = make_idesc(Tr<T>::umma_fmt, PAIR ? 2 * WROWS : WROWS, NT);
     const uint64_t d0 = make_smem_desc(smem_u32(smem));
     int s = 0, tl = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
+    for (int t = unit; t < p.tiles; t += n_units, ++tl) {
       const int buf = tl & 1;
-      mbar_wait(&tempty[buf], (uint32_t)((tl >> 1) & 1) ^ 1u, 2);      // epilogue has drained this accumulator buffer
+      mbar_wait(&tempty[buf], (uint32_t)((tl >> 1) & 1) ^ 1u, 2);      // epilogue(s) have drained this accumulator buffer
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
       for (int kb = 0; kb < kb_total; ++kb) {
@@ -185,21 +254,27 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         tc_fence_after();
         __syncwarp();
         if (elect_one()) {
-          const uint64_t da = d0 + (uint64_t)((uint32_t)s * (STAGE_BYTES >> 4));
+          const uint64_t da = d0 + (uint64_t)((uint32_t)s * (SB >> 4));
           const uint64_t db = da + (uint64_t)(W_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t koff = (uint64_t)((k * UK * 2) >> 4);
-            tc_mma_f16(d_tmem, da + koff, db + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (PAIR) tc_mma_f16_pair(d_tmem, da + koff, db + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else tc_mma_f16(d_tmem, da + koff, db + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);
-          if (kb == kb_total - 1) tc_commit(&tfull[buf]);
+          if (PAIR) {
+            tc_commit_pair(&empty_bar[s]);
+            if (kb == kb_total - 1) tc_commit_pair(&tfull[buf]);
+          } else {
+            tc_commit(&empty_bar[s]);
+            if (kb == kb_total - 1) tc_commit(&tfull[buf]);
+          }
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue (warps 2..5 = TMEM lane quadrants 2, 3, 0, 1) =====================
     const int e = threadIdx.x - 64;
     const int quad = warp & 3;
@@ -215,7 +290,7 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     };
     pdl_wait();                                   // residual reads and every store come after the previous kernel
     // residual prefetch iterator (thread e == 32): runs D chunks ahead of the chunk being finished
-    int pf_t = blockIdx.x, pf_c = 0, pf_g = 0;
+    int pf_t = unit, pf_c = 0, pf_g = 0;
     auto issue_res = [&]() {
       if (pf_t >= p.tiles) return;
       int m0, n0;
@@ -224,7 +299,7 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       mbar_expect_tx(&res_full[b], (uint32_t)(CR * FEATS * 2));
       tma_load_2d(epi_s + b * CBUF, &map_res, &res_full[b], n0, m0 + pf_c * CR, HINT_NORMAL);
       ++pf_g;
-      if (++pf_c == n_chunks_of(pf_t)) { pf_c = 0; pf_t += gridDim.x; }
+      if (++pf_c == n_chunks_of(pf_t)) { pf_c = 0; pf_t += n_units; }
     };
     // stores allowed to be still reading their buffer after a new one is committed; the residual of chunk g + D goes into the
     // buffer chunk g - E - 1 was stored from.  The store side (thread 0) and the residual loads (thread 32) are separate
@@ -240,7 +315,7 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 #else
 #define PROF(i)
 #endif
-    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++tl) {
+    for (int t = unit; t < p.tiles; t += n_units, ++tl) {
       int m0, n0;
       tile_coords(t, m0, n0);
       const int buf = tl & 1;
@@ -270,7 +345,8 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         PROF(4)
         if (c == nch - 1) {                       // accumulators of this tile are in registers: hand the buffer back
           tc_fence_before();
-          mbar_arrive(&tempty[buf]);
+          if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[buf]), 0u));     // the leader's MMA warp waits for both CTAs
+          else mbar_arrive(&tempty[buf]);
         }
         if (SWIGLU) {
           // lanes 0..63 hold the gate rows, lanes 64..127 the up rows of the same 64 features: both halves park T(.) of their
@@ -359,10 +435,12 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 #endif
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // nobody leaves while the peer may still read this CTA's operands or signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -378,34 +456,31 @@ int sm_count() {
   return cache[dev];
 }
 
-// token-tile width: the candidate that spends the fewest MMA cycles on round quantisation (a tile costs ~NT + a fixed part;
-// the CTA with the most tiles sets the time).  Widths that are not a multiple of 32 drain in 16-token chunks: a small penalty.
-int choose_nt(int M, int n_tiles, int sms) {
-  const int cand[] = {256, 240, 224, 192, 160, 128};
-  int best = 256;
-  double best_cost = 1e30;
-  for (int nt : cand) {
-    const long long m_tiles = (M + nt - 1) / nt, tiles = m_tiles * n_tiles, rounds = (tiles + sms - 1) / sms;
-    double cost = (double)rounds * (nt + 12);
-    if (nt % 32) cost *= 1.03;
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = nt; }
-  }
-  return best;
+// token-tile width.  Measured on B200 (tools/bench_wide.py): with a 4..6-stage ring a tile's time barely depends on its width
+// between 160 and 256 tokens (the per-k-block TMA round trip, not the MMA, paces the narrower tiles), so narrower tiles only add
+// rounds: 256 unless the whole problem is narrower.
+int choose_nt(int M) {
+  if (M >= 256) return 256;
+  return (M + 15) / 16 * 16;
 }
 
-template <class T, bool SWIGLU>
+template <class T, bool SWIGLU, bool PAIR>
 int launch_wide(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
                 const EpiParams& epi, int mode, int dtype, cudaStream_t st) {
   constexpr int FEATS = SWIGLU ? 64 : 128;
   const int sms = sm_count();
   WideParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.n_tiles = (N + FEATS - 1) / FEATS;
-  p.NT = g_wide_force_nt > 0 ? g_wide_force_nt : choose_nt(M, p.n_tiles, sms);
+  constexpr int TILE_FEATS = PAIR ? 2 * FEATS : FEATS;       // a CTA pair covers two weight tiles
+  constexpr int MAXS = PAIR ? MAX_STAGES_PAIR : MAX_STAGES;
+  constexpr int SB = PAIR ? PAIR_STAGE_BYTES : STAGE_BYTES;
+  const int units = PAIR ? sms / 2 : sms;
+  p.n_tiles = (N + TILE_FEATS - 1) / TILE_FEATS;
+  p.NT = g_wide_force_nt > 0 ? g_wide_force_nt : choose_nt(M);
   p.CR = (p.NT % 32 == 0) ? 32 : 16;
   p.m_tiles = (M + p.NT - 1) / p.NT;
   const long long tiles = (long long)p.m_tiles * p.n_tiles;
-  if (tiles < g_wide_min_tiles || tiles > 0x3fffffff) return 0;
+  if (tiles * (PAIR ? 2 : 1) < g_wide_min_tiles || tiles > 0x3fffffff) return 0;
   p.tiles = (int)tiles;
   p.m_fast = ((int64_t)(SWIGLU ? 2 : 1) * N > (int64_t)M) ? 1 : 0;
   p.mode = mode; p.act = epi.act; p.has_res = (!SWIGLU && epi.residual != nullptr) ? 1 : 0; p.bias = epi.bias;
@@ -413,28 +488,35 @@ int launch_wide(const void* x, int64_t ldx, const void* w, int64_t ldw, void* ou
     // 224 KB of shared memory: deep-K tiles want pipeline stages, K <= 128 tiles (one or two k-blocks, all epilogue) want the
     // residual prefetch to run far ahead instead
     const int kb = (K + BK - 1) / BK;
-    p.stages = g_wide_force_stages > 0 ? g_wide_force_stages : (kb <= 2 ? 2 : kb <= 4 ? 3 : 4);
-    p.nbuf = 4 + (MAX_STAGES - p.stages) * (STAGE_BYTES / BUF_BYTES);
+    p.stages = g_wide_force_stages > 0 ? g_wide_force_stages : (kb <= 2 ? 2 : kb <= 4 ? 3 : MAXS);
+    if (p.stages > MAXS) p.stages = MAXS;
+    p.nbuf = 4 + (MAXS - p.stages) * (SB / BUF_BYTES);
     if (p.nbuf > MAX_NBUF) p.nbuf = MAX_NBUF;
   }
   CUtensorMap map_w, map_x, map_out, map_res;
   RD_CHECK(rd_tc_make_map(&map_w, w, ldw, SWIGLU ? 2 * N : N, K, FEATS, BK, dtype, 1));
-  RD_CHECK(rd_tc_make_map(&map_x, x, ldx, M, K, p.NT, BK, dtype, 1));
+  RD_CHECK(rd_tc_make_map(&map_x, x, ldx, M, K, PAIR ? p.NT / 2 : p.NT, BK, dtype, 1));
   RD_CHECK(rd_tc_make_map(&map_out, out, ldo, M, N, p.CR, FEATS, dtype, 0));
   if (p.has_res) RD_CHECK(rd_tc_make_map(&map_res, epi.residual, epi.ld_res, M, N, p.CR, FEATS, dtype, 0));
   else map_res = map_out;
-  RD_SMEM_ATTR_ONCE(SMEM_BYTES, linear_wide_kernel<T, SWIGLU>);
+  RD_SMEM_ATTR_ONCE(SMEM_BYTES, linear_wide_kernel<T, SWIGLU, PAIR>);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(p.tiles < sms ? p.tiles : sms)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  const unsigned walkers = (unsigned)(p.tiles < units ? p.tiles : units);
+  cfg.gridDim = dim3(PAIR ? 2 * walkers : walkers); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
   int na = 0;
   if (rd_pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr; cfg.numAttrs = na;
-  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_wide_kernel<T, SWIGLU>, map_w, map_x, map_out, map_res, p));
+  RD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_wide_kernel<T, SWIGLU, PAIR>, map_w, map_x, map_out, map_res, p));
   return 1;
 }
 
@@ -455,8 +537,17 @@ int rd_linear_wide_try(const void* x, int64_t ldx, const void* w, int64_t ldw, v
   // TMA store / residual load: 16-byte aligned base and row pitch
   if (((uintptr_t)out & 15) != 0 || ldo % 8 != 0) return 0;
   if (epi.residual != nullptr && (((uintptr_t)epi.residual & 15) != 0 || epi.ld_res % 8 != 0)) return 0;
+  // CTA pairs need a token tile that splits into two swizzle-aligned halves
+  const int nt = g_wide_force_nt > 0 ? g_wide_force_nt : choose_nt(M);
+  // ... and pay off when the MMAs dominate: deep K, and enough weight tiles that the second CTA of a pair is not idle
+  const int w_tiles = (N + (sw ? 64 : 128) - 1) / (sw ? 64 : 128);
+  const bool pair = g_wide_pair && nt % 16 == 0 && K >= 8 * BK && w_tiles >= 2 && (w_tiles % 2 == 0 || w_tiles >= 8);
   RD_DISPATCH_DTYPE(dtype, T, {
-    if (sw) return launch_wide<T, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
-    return launch_wide<T, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
+    if (pair) {
+      if (sw) return launch_wide<T, true, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
+      return launch_wide<T, false, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
+    }
+    if (sw) return launch_wide<T, true, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
+    return launch_wide<T, false, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
   });
 }

@@ -235,17 +235,21 @@ def test_persistent_wide_kernel_bit_identical(cuda_dev, lib, dtype, case, nt, st
         lib.rd_linear_wide_min_tiles(1)
         lib.rd_linear_wide_force_nt(nt)
         lib.rd_linear_wide_force_stages(stages)
-        for on in (0, 1):
-            lib.rd_linear_wide_persistent(on)
+        for on in (0, 1, 2):               # 0: one tile per CTA, 1: persistent CTA pairs (cta_group::2), 2: persistent single CTAs
+            lib.rd_linear_wide_persistent(1 if on else 0)
+            lib.rd_linear_wide_pair(1 if on == 1 else 0)
             outs[on] = [run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, **kw) for _ in range(2)]
     finally:
         lib.rd_linear_wide_persistent(1)
+        lib.rd_linear_wide_pair(1)
         lib.rd_linear_wide_min_tiles(149)
         lib.rd_linear_wide_force_nt(0)
         lib.rd_linear_wide_force_stages(0)
     assert torch.isfinite(outs[1][0].float()).all(), "persistent kernel left outputs unwritten"
     assert torch.equal(outs[1][0], outs[1][1]), "persistent kernel is not deterministic run to run"
-    assert torch.equal(outs[0][0], outs[1][0]), f"max diff {(outs[0][0].float() - outs[1][0].float()).abs().max().item():.4g}"
+    assert torch.equal(outs[0][0], outs[1][0]), f"pair: max diff {(outs[0][0].float() - outs[1][0].float()).abs().max().item():.4g}"
+    assert torch.equal(outs[0][0], outs[2][0]), f"single: max diff {(outs[0][0].float() - outs[2][0].float()).abs().max().item():.4g}"
+    assert torch.equal(outs[2][0], outs[2][1]), "persistent single-CTA kernel is not deterministic run to run"
     ref = ref_linear(x, w, dtype, bias=bias, act=act, residual=residual, res_mode=res_mode or 1, N=N)
     ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
     scale = ref.float().abs().max().item()

@@ -63,9 +63,11 @@ def main():
         e.act = act
         flops = 2.0 * M * rows * K
         line = [f"{name:9s} M={M:6d} N={N:5d} K={K:5d}"]
-        configs = [("old", 0, 0, 0)] + [(f"nt={nt} s={sg}", 1, int(nt), int(sg)) for nt in args.nt.split(",") for sg in args.stages.split(",")]
-        for label, on, nt, sg in configs:
+        configs = [("old", 0, 0, 0, 0)] + [(f"{'pair' if pr else 'single'} nt={nt} s={sg}", 1, int(nt), int(sg), pr) for pr in (0, 1)
+                                          for nt in args.nt.split(",") for sg in args.stages.split(",")]
+        for label, on, nt, sg, pr in configs:
             lib.rd_linear_wide_persistent(on)
+            lib.rd_linear_wide_pair(pr)
             lib.rd_linear_wide_force_nt(nt)
             lib.rd_linear_wide_force_stages(sg)
             st = _lib.current_stream()
@@ -111,6 +113,7 @@ def main():
             us = a.elapsed_time(b) * 1e3 / args.sustained
             line.append(f"cuBLAS (no epilogue): {us:7.1f} us ({flops / us / 1e6 / peak:.2f})")
         lib.rd_linear_wide_force_stages(0)
+        lib.rd_linear_wide_pair(1)
         lib.rd_linear_wide_persistent(1)
         lib.rd_linear_wide_force_nt(0)
         print("  |  ".join(line), flush=True)
