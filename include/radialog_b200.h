@@ -99,6 +99,15 @@ int rd_linear_wide_force_stages(int stages);   /* 2..6 pipeline stages (the rest
  * k-step, each CTA staging its own 128 weight rows and HALF of the shared token tile (a third less shared-memory and L2 traffic
  * per flop, 6 instead of 4 pipeline stages); 0: every CTA on its own.  Bit-identical results. */
 int rd_linear_wide_pair(int on);
+/* Convolution as an implicit GEMM (biovil_t/resnet.py:25-47 Bottleneck conv2 3x3 and the stride-2 1x1 downsample; eval BatchNorm
+ * folded into w / bias): out[(b,oh,ow), n] = epilogue(sum_{kh,kw,c} x[b, oh*stride-pad+kh, ow*stride-pad+kw, c] . w[n, (kh*ks+kw)*C+c]).
+ * x is NHWC [B,H,W,C], w is [Cout, ks*ks*C] - the column order of rd_im2col_nhwc, so the result is bit-identical to
+ * rd_im2col_nhwc + rd_linear; the gather happens inside the GEMM's TMA producer (im2col-mode tensor map), no matrix in HBM.
+ * Returns 1 = launched, 0 = shape not eligible (C % 64 != 0, M <= 128, unaligned out: use the explicit path), < 0 = error.
+ * rd_conv_set_implicit(0) makes it always return 0 (test hook). */
+int rd_conv_nhwc_implicit(const void* x_dev, const void* w_dev, void* out_dev, int64_t ldo, int B, int H, int W, int C, int Cout,
+                          int ks, int stride, int pad, const rd_epilogue* epi, int dtype, void* stream);
+int rd_conv_set_implicit(int on);
 /* Launch every kernel with the programmatic-dependent-launch attribute (prologue of kernel N+1 — barrier init, TMEM
  * allocation, the first weight tiles — overlaps the tail of kernel N).  On by default; 0 switches it off. */
 int rd_set_pdl(int on);

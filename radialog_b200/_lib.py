@@ -62,6 +62,9 @@ SIGNATURES = {
     "rd_linear_wide_force_nt": (_i, [_i]),
     "rd_linear_wide_force_stages": (_i, [_i]),
     "rd_linear_wide_pair": (_i, [_i]),
+    "rd_conv_nhwc_implicit": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(Epilogue), _i, _p]),
+    "rd_conv_set_implicit": (_i, [_i]),
+    "rd_im2col_nhwc": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rd_rmsnorm": (_i, [_p, _p, _p, _i, _i, _f, _p, _i, _p, _i, _p]),
     "rd_layernorm": (_i, [_p, _p, _p, _p, _i, _i, _f, _i, _p]),
     "rd_rope_kv_store": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _f, _i, _p]),

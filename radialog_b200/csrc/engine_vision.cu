@@ -13,6 +13,7 @@
 
 extern "C" int rd_stem_im2col(const float*, void*, int, int, int, int, void*);
 extern "C" int rd_im2col_nhwc(const void*, void*, int, int, int, int, int, int, int, int, void*);
+extern "C" int rd_conv_nhwc_implicit(const void*, const void*, void*, int64_t, int, int, int, int, int, int, int, int, const rd_epilogue*, int, void*);
 extern "C" int rd_maxpool3x3s2(const void*, void*, int, int, int, int, int, void*);
 extern "C" int rd_ln_vision_tokens(const void*, const float*, const float*, void*, float*, int, int, int, float, int, void*);
 extern "C" int rd_small_attention(const void*, int64_t, const void*, const void*, int64_t, void*, int64_t, int, int, int, int, int, int, void*);
@@ -122,6 +123,24 @@ struct Ctx {
     h->launches++;
     err = rd_linear(x, ldx, w, K, out, ldo, M, N, K, &e, dt, 2, h->ws, h->ws_bytes, st);
   }
+  // out[(b,oh,ow), Cout] = act(conv_ks x ks(x NHWC) + b (+ res)): implicit GEMM (im2col-mode TMA inside the GEMM's producer) when the
+  // shape allows, else an explicit im2col matrix in h->col followed by the GEMM.  Same products and k order either way.
+  void conv(const void* x, int B, int Hi, int Wi, int C, int ks, int stride, int pad, const std::string& wname, void* out, int64_t ldo, int Cout,
+            int act, const void* res = nullptr, int64_t ld_res = 0) {
+    if (err != RD_OK) return;
+    rd_epilogue e{};
+    const void* w = W(wname + ".w");
+    e.bias_dev = (const float*)W(wname + ".b");
+    if (err != RD_OK) return;
+    e.act = act;
+    if (res) { e.residual_dev = res; e.ld_res = ld_res; e.res_mode = 2; }
+    const int r = rd_conv_nhwc_implicit(x, w, out, ldo, B, Hi, Wi, C, Cout, ks, stride, pad, &e, dt, st);
+    if (r == 1) { h->launches++; return; }
+    if (r < 0) { err = r; return; }
+    const int OH = (Hi + 2 * pad - ks) / stride + 1, OW = (Wi + 2 * pad - ks) / stride + 1;
+    chk(rd_im2col_nhwc(x, h->col, B, Hi, Wi, C, ks, stride, pad, dt, st));
+    gemm(h->col, (int64_t)ks * ks * C, wname, true, out, ldo, B * OH * OW, Cout, ks * ks * C, act, res, ld_res);
+  }
   void ln(const void* x, const std::string& name, void* out, int M, int H, float eps) {
     if (err != RD_OK) return;
     const float* g = (const float*)W(name + ".g"); const float* b = (const float*)W(name + ".b");
@@ -156,13 +175,11 @@ static void trunk_b2v(rd_vision* h, Ctx& X, const float* images, int B, void* pa
       const int ohw = hw / stride;
       const int Min = B * hw * hw, Mout = B * ohw * ohw;
       X.gemm(cur, inpl, p + ".conv1", true, h->t1, planes, Min, planes, inpl, RD_ACT_RELU);
-      X.chk(rd_im2col_nhwc(h->t1, h->col, B, hw, hw, planes, 3, stride, 1, dt, st));
-      X.gemm(h->col, 9 * planes, p + ".conv2", true, h->t2, planes, Mout, planes, 9 * planes, RD_ACT_RELU);
+      X.conv(h->t1, B, hw, hw, planes, 3, stride, 1, p + ".conv2", h->t2, planes, planes, RD_ACT_RELU);
       const void* idt = cur;
       if (b == 0) {
-        const void* src = cur;
-        if (stride == 2) { X.chk(rd_im2col_nhwc(cur, h->col, B, hw, hw, inpl, 1, 2, 0, dt, st)); src = h->col; }
-        X.gemm(src, inpl, p + ".downsample", true, h->idt, planes * 4, Mout, planes * 4, inpl, RD_ACT_NONE);
+        if (stride == 2) X.conv(cur, B, hw, hw, inpl, 1, 2, 0, p + ".downsample", h->idt, planes * 4, planes * 4, RD_ACT_NONE);
+        else X.gemm(cur, inpl, p + ".downsample", true, h->idt, planes * 4, Mout, planes * 4, inpl, RD_ACT_NONE);
         idt = h->idt;
       }
       X.gemm(h->t2, planes, p + ".conv3", true, nxt, planes * 4, Mout, planes * 4, planes, RD_ACT_RELU, idt, planes * 4);

@@ -936,9 +936,16 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t ld, int rows, int K, int
 
 // token-tile width.  Many tokens but only one or two k-blocks (the 1x1 convolutions of ResNet layer1/2, K = 64 / 128): such a CTA
 // is all prologue + epilogue, so it gets the 128-token tile whose parked epilogue tile (64 KB) lets two CTAs share an SM.
-int pick_nt(int M, int K) {
+// Mid-size problems (Q-Former: 1024 query tokens x 768 features = 24 tiles of 256 tokens on 148 SMs) take the widest tile that
+// still yields ~100 CTAs.
+int pick_nt(int M, int N, int K) {
   if (M > 128 && K <= 2 * BLOCK_K) return 128;
-  return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+  if (M <= 128) return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
+  const long long n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  for (int nt : {256, 128}) {
+    if (n_tiles * ((M + nt - 1) / nt) >= 96) return nt;
+  }
+  return 64;
 }
 
 // Max CTAs of the decode-tile kernel that are co-resident when launched as clusters of (1,1,cs).  Measured on B200
@@ -1128,7 +1135,7 @@ static int g_force_splits = 0;   // test hook: 0 = heuristic
 extern "C" int rd_linear_force_splits(int s) { g_force_splits = s; return RD_OK; }
 
 int64_t rd_linear_tc_workspace_bytes(int M, int N, int K) {
-  const int nt = pick_nt(M, K);
+  const int nt = pick_nt(M, N, K);
   const int64_t n_tiles = (N + BLOCK_N - 1) / BLOCK_N, m_tiles = (M + nt - 1) / nt;
   const int64_t splits = 16;      // upper bound of pick_splits / the test hook
   return (n_tiles * m_tiles * 4 + 255) / 256 * 256 + splits * n_tiles * m_tiles * 2 * nt * BLOCK_N * 4 + 256;
@@ -1156,7 +1163,7 @@ int rd_linear_tc(const void* x, int64_t ldx, const void* w, int64_t ldw, void* o
     const int r = rd_linear_wide_try(x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, st);
     if (r != 0) return r < 0 ? r : RD_OK;
   }
-  const int nt = pick_nt(M, K);
+  const int nt = pick_nt(M, N, K);
   const int splits = g_force_splits > 0 ? g_force_splits : 0;     // 0: chosen per kernel variant from its occupancy
   const bool sw = epi.act == RD_ACT_SWIGLU;
   RD_DISPATCH_DTYPE(dtype, T, {

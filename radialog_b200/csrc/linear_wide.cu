@@ -26,6 +26,7 @@
 // SwiGLU triple rounding); the k-blocks are accumulated in the same order, so the two kernels agree bit for bit.
 #include <cuda.h>
 #include <stdlib.h>
+#include <vector>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -75,6 +76,10 @@ struct WideParams {
   int m_fast;                 // consecutive tiles (= CTAs running together) share the weight tile
   int mode, act, has_res;
   int stages, nbuf;           // pipeline stages, 8 KB epilogue chunk buffers
+  // implicit-GEMM convolution (conv_ks > 0): the token operand is gathered from the NHWC activation [B, H, W, C] by im2col-mode TMA
+  // loads - token m = output pixel (b, oh, ow), k-block kb = 64 channels of filter tap (kb * 64) / C - instead of read from a
+  // materialised [M, ks*ks*C] matrix
+  int conv_ks, conv_C, conv_OW, conv_OHW, conv_stride, conv_pad;
   const float* bias;
 };
 
@@ -104,6 +109,24 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+// im2col-mode TMA load (NHWC tensor map from cuTensorMapEncodeIm2col): `pixelsPerColumn` output pixels starting at the window whose
+// top-left input position is (w, h) of image n, 64 channels from c, filter tap (off_w, off_h); out-of-image taps are zero-filled
+__device__ __forceinline__ void tma_load_im2col(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h, int n,
+                                                uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c, int w, int h, int n,
+                                                     uint16_t off_w, uint16_t off_h, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h),
+        "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -203,6 +226,28 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       }
     };
     const bool expects = !PAIR || rank == 0;     // pair: the leader's barrier carries the expected byte count of both CTAs
+    // token operand of k-block kb for the tile whose first token is m0
+    int cv_w = 0, cv_h = 0, cv_n = 0;            // conv: window origin of this CTA's first output pixel of the current tile
+    auto set_tile_x = [&](int m0) {
+      if (p.conv_ks > 0) {
+        int ms = m0 + (int)rank * XROWS;
+        if (ms >= p.M) ms = 0;                    // pair: the peer's half lies wholly past the last pixel - any valid window (results clipped)
+        cv_n = ms / p.conv_OHW;
+        const int r = ms - cv_n * p.conv_OHW, oh = r / p.conv_OW, ow = r - oh * p.conv_OW;
+        cv_w = ow * p.conv_stride - p.conv_pad;
+        cv_h = oh * p.conv_stride - p.conv_pad;
+      }
+    };
+    auto load_x = [&](int s, int kb, int m0) {
+      uint8_t* dst = smem + s * SB + W_BYTES;
+      if (p.conv_ks > 0) {
+        const int k0 = kb * BK, tap = k0 / p.conv_C, c0 = k0 - tap * p.conv_C, kh = tap / p.conv_ks, kw = tap - kh * p.conv_ks;
+        if (PAIR) tma_load_im2col_pair(dst, &map_x, mapa_u32(smem_u32(&full_bar[s]), 0u), c0, cv_w, cv_h, cv_n, (uint16_t)kw, (uint16_t)kh, HINT_NORMAL);
+        else tma_load_im2col(dst, &map_x, &full_bar[s], c0, cv_w, cv_h, cv_n, (uint16_t)kw, (uint16_t)kh);
+      } else {
+        load(dst, &map_x, s, kb * BK, m0 + (int)rank * XROWS);
+      }
+    };
     // weights never depend on the previous kernel: the first stages' weight k-blocks are requested before the PDL wait
     int pre = 0;
     if (unit < p.tiles) {
@@ -223,6 +268,7 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     for (int t = unit; t < p.tiles; t += n_units) {
       int m0, n0;
       tile_coords(t, m0, n0);
+      set_tile_x(m0);
       for (int kb = 0; kb < kb_total; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1u, 1);        // first pass: the barrier's "previous phase" counts as complete
         __syncwarp();
@@ -231,7 +277,7 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
             if (expects) mbar_expect_tx(&full_bar[s], stage_tx);
             load_w(s, kb, n0);
           }
-          load(smem + s * SB + W_BYTES, &map_x, s, kb * BK, m0 + (int)rank * XROWS);
+          load_x(s, kb, m0);
         }
         __syncwarp();
         if (it < STAGES) ++it;
@@ -464,9 +510,65 @@ int choose_nt(int M) {
   return (M + 15) / 16 * 16;
 }
 
+// implicit-GEMM convolution: geometry of the NHWC activation the token operand is gathered from (nullptr = plain GEMM)
+struct ConvGeom { int B, H, W, C, ks, stride, pad, OH, OW; };
+
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                     const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// NHWC tensor map in im2col mode (rank 4: C, W, H, N): the bounding box of window origins is [-pad, dim + pad - ks] per spatial
+// dimension, windows advance by `stride`, a load brings `pixels` consecutive output pixels (w fastest, then h, then n) x 64
+// channels into a 128-byte-swizzled [pixels][64] tile - the same shared-memory image as a box of a materialised im2col matrix.
+struct Im2colKey { const void* ptr; ConvGeom g; int pixels, dtype; };
+struct Im2colSlot { Im2colKey k; CUtensorMap m; };
+
+int make_im2col_map(CUtensorMap* map, const void* x, const ConvGeom& g, int pixels, int dtype) {
+  static thread_local std::vector<Im2colSlot>* cache = nullptr;
+  if (cache == nullptr) cache = new std::vector<Im2colSlot>();
+  for (const Im2colSlot& sl : *cache) {
+    const Im2colKey& k = sl.k;
+    if (k.ptr == x && k.pixels == pixels && k.dtype == dtype && k.g.B == g.B && k.g.H == g.H && k.g.W == g.W && k.g.C == g.C && k.g.ks == g.ks &&
+        k.g.stride == g.stride && k.g.pad == g.pad) {
+      *map = sl.m;
+      return RD_OK;
+    }
+  }
+  static PFN_encodeIm2col enc = nullptr;
+  if (enc == nullptr) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      enc = (PFN_encodeIm2col)fp;
+  }
+  RD_REQUIRE(enc != nullptr, "cuTensorMapEncodeIm2col entry point not available");
+  cuuint64_t gdim[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t gstr[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad - (g.ks - 1), g.pad - (g.ks - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+  Im2colSlot sl;
+  CUresult r = enc(&sl.m, dtype == RD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr,
+                   lower, upper, (cuuint32_t)BK, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d) B=%d H=%d W=%d C=%d ks=%d stride=%d pixels=%d", (int)r, g.B, g.H, g.W, g.C, g.ks,
+             g.stride, pixels);
+  // drivers up to CUDA 13.1 set a descriptor bit that is wrong for tensors under 128 KB (same fix-up as CUTLASS's
+  // copy_traits_sm90_im2col.hpp applies)
+  {
+    int drv = 0;
+    if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (int64_t)g.B * g.H * g.W * g.C * 2 < 131072)
+      reinterpret_cast<uint64_t*>(&sl.m)[1] &= ~(1llu << 21);
+  }
+  sl.k = Im2colKey{x, g, pixels, dtype};
+  if (cache->size() < 256) cache->push_back(sl);
+  *map = sl.m;
+  return RD_OK;
+}
+
 template <class T, bool SWIGLU, bool PAIR>
 int launch_wide(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
-                const EpiParams& epi, int mode, int dtype, cudaStream_t st) {
+                const EpiParams& epi, int mode, int dtype, cudaStream_t st, const ConvGeom* conv = nullptr) {
   constexpr int FEATS = SWIGLU ? 64 : 128;
   const int sms = sm_count();
   WideParams p{};
@@ -480,7 +582,8 @@ int launch_wide(const void* x, int64_t ldx, const void* w, int64_t ldw, void* ou
   p.CR = (p.NT % 32 == 0) ? 32 : 16;
   p.m_tiles = (M + p.NT - 1) / p.NT;
   const long long tiles = (long long)p.m_tiles * p.n_tiles;
-  if (tiles * (PAIR ? 2 : 1) < g_wide_min_tiles || tiles > 0x3fffffff) return 0;
+  // (a convolution is taken at any size: even one tile per CTA saves the im2col round trip through HBM)
+  if ((conv == nullptr && tiles * (PAIR ? 2 : 1) < g_wide_min_tiles) || tiles > 0x3fffffff) return 0;
   p.tiles = (int)tiles;
   p.m_fast = ((int64_t)(SWIGLU ? 2 : 1) * N > (int64_t)M) ? 1 : 0;
   p.mode = mode; p.act = epi.act; p.has_res = (!SWIGLU && epi.residual != nullptr) ? 1 : 0; p.bias = epi.bias;
@@ -495,7 +598,12 @@ int launch_wide(const void* x, int64_t ldx, const void* w, int64_t ldw, void* ou
   }
   CUtensorMap map_w, map_x, map_out, map_res;
   RD_CHECK(rd_tc_make_map(&map_w, w, ldw, SWIGLU ? 2 * N : N, K, FEATS, BK, dtype, 1));
-  RD_CHECK(rd_tc_make_map(&map_x, x, ldx, M, K, PAIR ? p.NT / 2 : p.NT, BK, dtype, 1));
+  if (conv != nullptr) {
+    p.conv_ks = conv->ks; p.conv_C = conv->C; p.conv_OW = conv->OW; p.conv_OHW = conv->OH * conv->OW; p.conv_stride = conv->stride; p.conv_pad = conv->pad;
+    RD_CHECK(make_im2col_map(&map_x, x, *conv, PAIR ? p.NT / 2 : p.NT, dtype));
+  } else {
+    RD_CHECK(rd_tc_make_map(&map_x, x, ldx, M, K, PAIR ? p.NT / 2 : p.NT, BK, dtype, 1));
+  }
   RD_CHECK(rd_tc_make_map(&map_out, out, ldo, M, N, p.CR, FEATS, dtype, 0));
   if (p.has_res) RD_CHECK(rd_tc_make_map(&map_res, epi.residual, epi.ld_res, M, N, p.CR, FEATS, dtype, 0));
   else map_res = map_out;
@@ -520,11 +628,8 @@ int launch_wide(const void* x, int64_t ldx, const void* w, int64_t ldw, void* ou
   return 1;
 }
 
-}  // namespace
-
-// 1: launched, 0: shape / epilogue not handled here (caller falls through to linear_tc_kernel), < 0: error
-int rd_linear_wide_try(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
-                       const EpiParams& epi, int dtype, cudaStream_t st) {
+static int wide_dispatch(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
+                         const EpiParams& epi, int dtype, cudaStream_t st, const ConvGeom* conv) {
   if (!g_wide_persistent || M <= 128) return 0;
   const bool sw = epi.act == RD_ACT_SWIGLU;
   const bool simple = epi.bias == nullptr && (epi.act == RD_ACT_NONE || sw);
@@ -544,10 +649,41 @@ int rd_linear_wide_try(const void* x, int64_t ldx, const void* w, int64_t ldw, v
   const bool pair = g_wide_pair && nt % 16 == 0 && K >= 8 * BK && w_tiles >= 2 && (w_tiles % 2 == 0 || w_tiles >= 8);
   RD_DISPATCH_DTYPE(dtype, T, {
     if (pair) {
-      if (sw) return launch_wide<T, true, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
-      return launch_wide<T, false, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
+      if (sw) return launch_wide<T, true, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, conv);
+      return launch_wide<T, false, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, conv);
     }
-    if (sw) return launch_wide<T, true, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
-    return launch_wide<T, false, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st);
+    if (sw) return launch_wide<T, true, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, conv);
+    return launch_wide<T, false, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, conv);
   });
+}
+
+}  // namespace
+
+// 1: launched, 0: shape / epilogue not handled here (caller falls through to linear_tc_kernel), < 0: error
+int rd_linear_wide_try(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
+                       const EpiParams& epi, int dtype, cudaStream_t st) {
+  return wide_dispatch(x, ldx, w, ldw, out, ldo, M, N, K, epi, dtype, st, nullptr);
+}
+
+static int g_conv_implicit = 1;     // test hook: 0 = convolutions always go through the explicit im2col matrix
+extern "C" int rd_conv_set_implicit(int on) { g_conv_implicit = on; return RD_OK; }
+
+// Convolution as an implicit GEMM: out[(b,oh,ow), n] = epilogue( sum_{kh,kw,c} x[b, oh*stride-pad+kh, ow*stride-pad+kw, c] . w[n, (kh*ks+kw)*C + c] ),
+// NHWC activations, weights [Cout, ks*ks*C] (the layout rd_im2col_nhwc + rd_linear use; eval-BatchNorm folded into w / bias).
+// Returns 1 if launched, 0 if this shape has to take the explicit path (C not a multiple of 64, tiny M, unaligned output), < 0 on error.
+extern "C" int rd_conv_nhwc_implicit(const void* x_dev, const void* w_dev, void* out_dev, int64_t ldo, int B, int H, int W, int C, int Cout,
+                                     int ks, int stride, int pad, const rd_epilogue* epi, int dtype, void* stream) {
+  if (!g_conv_implicit) return 0;
+  if (C % BK != 0 || ks < 1 || ks > 7 || stride < 1 || pad < 0 || pad > 8 || ((uintptr_t)x_dev & 15) != 0) return 0;
+  ConvGeom g{B, H, W, C, ks, stride, pad, (H + 2 * pad - ks) / stride + 1, (W + 2 * pad - ks) / stride + 1};
+  if (g.OH < 1 || g.OW < 1) return 0;
+  const int64_t M = (int64_t)B * g.OH * g.OW;
+  if (M > 0x7fffffff) return 0;
+  EpiParams e{};
+  if (epi != nullptr) {
+    e.bias = epi->bias_dev; e.residual = epi->residual_dev; e.ld_res = epi->ld_res; e.res_mode = epi->res_mode; e.act = epi->act;
+    e.lora_t = epi->lora_t_dev; e.lora_b = epi->lora_b_dev; e.lora_r = epi->lora_r; e.lora_scale = epi->lora_scale;
+  }
+  const int K = ks * ks * C;
+  return wide_dispatch(x_dev, 0, w_dev, K, out_dev, ldo, (int)M, Cout, K, e, dtype, (cudaStream_t)stream, &g);
 }

@@ -238,8 +238,10 @@ def test_persistent_wide_kernel_bit_identical(cuda_dev, lib, dtype, case, nt, st
         for on in (0, 1, 2):               # 0: one tile per CTA, 1: persistent CTA pairs (cta_group::2), 2: persistent single CTAs
             lib.rd_linear_wide_persistent(1 if on else 0)
             lib.rd_linear_wide_pair(1 if on == 1 else 0)
+            lib.rd_linear_force_splits(0 if on else 1)      # the one-tile-per-CTA kernel without split-K: one summation order
             outs[on] = [run_linear(lib, x, w, M, N, K, dtype, _lib.ALGO_TC, **kw) for _ in range(2)]
     finally:
+        lib.rd_linear_force_splits(0)
         lib.rd_linear_wide_persistent(1)
         lib.rd_linear_wide_pair(1)
         lib.rd_linear_wide_min_tiles(149)
@@ -273,3 +275,57 @@ def test_persistent_wide_kernel_many_tiles_per_cta(cuda_dev, lib):
     assert torch.equal(a, b)
     ref = ref_linear(x, w, dtype, act=_lib.ACT_SWIGLU, N=N)
     assert (a.float() - ref.float()).abs().max().item() <= 2 * 2.0 ** -7 * ref.float().abs().max().item()
+
+
+CONV_CASES = [
+    # B, H, W, C, Cout, ks, stride, pad, act, residual
+    (2, 56, 56, 64, 64, 3, 1, 1, _lib.ACT_RELU, False),      # layer1 conv2 (one half-empty weight tile)
+    (3, 28, 20, 128, 128, 3, 2, 1, _lib.ACT_RELU, False),    # stride 2, H != W, tokens not a multiple of the tile
+    (2, 28, 28, 256, 256, 3, 1, 1, _lib.ACT_RELU, False),    # two weight tiles, K = 2304: CTA pairs
+    (1, 14, 14, 512, 512, 3, 1, 1, _lib.ACT_RELU, False),    # 196 output pixels: one ragged tile
+    (2, 56, 56, 256, 512, 1, 2, 0, 0, False),                # stride-2 1x1 downsample
+    (5, 9, 11, 64, 136, 3, 1, 1, 0, True),                   # odd sizes, Cout not a multiple of 128, fp32 residual
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_implicit_gemm_convolution_bit_identical_to_im2col_path(cuda_dev, lib, dtype, case):
+    """rd_conv_nhwc_implicit (im2col-mode TMA loads inside the persistent GEMM's producer) against rd_im2col_nhwc + rd_linear
+    (same products, same k order: bit-identical) and against torch.nn.functional.conv2d in fp32."""
+    B, H, W, Cin, Cout, ks, stride, pad, act, has_res = case
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + Cin + ks)
+    x = (torch.randn(B, H, W, Cin, generator=g) * 0.5).to(dtype).to(cuda_dev)
+    w = (torch.randn(Cout, ks, ks, Cin, generator=g) * 0.05).to(dtype).to(cuda_dev)      # [Cout, kh, kw, c] = the im2col column order
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(cuda_dev)
+    OH, OW = (H + 2 * pad - ks) // stride + 1, (W + 2 * pad - ks) // stride + 1
+    M, K = B * OH * OW, ks * ks * Cin
+    residual = (torch.randn(M, Cout, generator=g) * 0.5).to(dtype).to(cuda_dev) if has_res else None
+    e = _lib.Epilogue()
+    e.bias_dev = _lib.ptr(bias)
+    e.residual_dev = _lib.ptr(residual)
+    e.ld_res = Cout
+    e.res_mode = 2
+    e.act = act
+    out_i = torch.full((M, Cout), float("nan"), device=cuda_dev, dtype=dtype)
+    r = lib.rd_conv_nhwc_implicit(_lib.ptr(x), _lib.ptr(w), _lib.ptr(out_i), Cout, B, H, W, Cin, Cout, ks, stride, pad, C.byref(e),
+                                  _lib.dtype_code(dtype), _lib.current_stream())
+    assert r == 1, f"implicit path declined this shape (r={r}): {lib.rd_last_error()}"
+    torch.cuda.synchronize()
+    col = torch.empty(M, K, device=cuda_dev, dtype=dtype)
+    _lib.check(lib.rd_im2col_nhwc(_lib.ptr(x), _lib.ptr(col), B, H, W, Cin, ks, stride, pad, _lib.dtype_code(dtype), _lib.current_stream()), "im2col")
+    lib.rd_linear_wide_min_tiles(1)          # the explicit GEMM through the same persistent kernel (no split-K): same summation order
+    try:
+        out_e = run_linear(lib, col, w.reshape(Cout, K), M, Cout, K, dtype, _lib.ALGO_TC, bias=bias, act=act, residual=residual, res_mode=2)
+    finally:
+        lib.rd_linear_wide_min_tiles(149)
+    assert torch.isfinite(out_i.float()).all(), "implicit conv left outputs unwritten"
+    assert torch.equal(out_i, out_e), f"max diff {(out_i.float() - out_e.float()).abs().max().item():.4g}"
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad)
+    ref = ref.permute(0, 2, 3, 1).reshape(M, Cout)
+    if has_res:
+        ref = ref + residual.float()
+    if act == _lib.ACT_RELU:
+        ref = torch.relu(ref)
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    assert (out_i.float() - ref).abs().max().item() <= 2 * ulp * ref.abs().max().item() + 1e-3

@@ -53,10 +53,13 @@ def test_full_resnet50_qformer_vs_reference_golden(cuda_dev, golden_dir, dtype, 
         print(f"\n[vision full size {dtype}] image_embeds rel err {rel_err(e.cpu()[:, ::7, ::11], ref_e):.3e}, q_out rel err {rel_err(q.cpu(), ref_q):.3e}")
     assert rel_err(e.cpu()[:, ::7, ::11], ref_e) <= tol, f"image_embeds rel err {rel_err(e.cpu()[:, ::7, ::11], ref_e):.3e}"
     assert rel_err(q.cpu(), ref_q) <= tol, f"q_out rel err {rel_err(q.cpu(), ref_q):.3e}"
-    # batch invariance: chunked execution (max_batch 1) gives the same bits as one batch of B
+    # chunked execution (max_batch 1) against one batch of B: the GEMM tiling (token-tile width, split-K, CTA pairs) is chosen
+    # per problem size, so the fp32 summation order - not the arithmetic - differs; both must meet the same bar, and agree with
+    # each other to within it
     model1 = Blip2Qformer.from_state_dict(cfg, sd, torch_dtype=dtype, device=cuda_dev, max_batch=1)
     q1, _ = model1.forward_image(imgs.to(cuda_dev))
-    assert rel_err(q1.cpu(), q.cpu()) <= 2e-3
+    assert rel_err(q1.cpu(), ref_q) <= tol, f"chunked q_out rel err {rel_err(q1.cpu(), ref_q):.3e}"
+    assert rel_err(q1.cpu(), q.cpu()) <= tol
 
 
 def test_two_image_temporal_branch_tiny_vs_oracle(cuda_dev):
