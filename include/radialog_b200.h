@@ -86,11 +86,11 @@ int rd_linear_splitk_mode(int mode);
  * from shared memory.  Same
  * products, same accumulation order: bit-identical results. */
 int rd_linear_tmem_staging(int on);
-/* Wide token counts (M > 128: prefill, convolutions, Q-Former image side): 1 (default) runs GEMMs with at least
- * rd_linear_wide_min_tiles (default 149 = more tiles than SMs) output tiles on the persistent kernel of linear_wide.cu - one CTA
- * per SM walks the tiles, two TMEM accumulator buffers so the epilogue of tile i (TMA residual load / TMA store) overlaps the
- * MMAs of tile i+1; 0 keeps every shape on the one-tile-per-CTA kernel.  Bit-identical results either way.
- * rd_linear_wide_force_nt: token-tile width of that kernel (multiple of 16, 128..256; 0 = chosen to minimise round quantisation). */
+/* Wide token counts (M > 128: prefill, convolutions, Q-Former): 1 (default) runs them on the persistent kernel of linear_wide.cu -
+ * one CTA (pair) per SM walks the output tiles, two TMEM accumulator buffers so the epilogue of tile i (TMA residual load / TMA
+ * store) overlaps the MMAs of tile i+1; 0 keeps every shape on the one-tile-per-CTA kernel.  Same products and k order either
+ * way.  rd_linear_wide_min_tiles: GEMMs with fewer output tiles stay on the one-tile-per-CTA kernel (default 1 = none).
+ * rd_linear_wide_force_nt: token-tile width of that kernel (multiple of 16, <= 256; 0 = by problem size). */
 int rd_linear_wide_persistent(int on);
 int rd_linear_wide_min_tiles(int n);
 int rd_linear_wide_force_nt(int nt);

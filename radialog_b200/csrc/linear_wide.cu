@@ -41,7 +41,7 @@ static int g_wide_force_stages = 0;  // test hook: pipeline stages 2..4 (0 = by 
 extern "C" int rd_linear_wide_force_stages(int s) { g_wide_force_stages = (s >= 2 && s <= 6) ? s : 0; return RD_OK; }
 static int g_wide_pair = 1;          // 1: CTA pairs (cta_group::2, 256-row UMMA, each CTA stages half of the token tile)
 extern "C" int rd_linear_wide_pair(int on) { g_wide_pair = on; return RD_OK; }
-static int g_wide_min_tiles = 149;   // below this the one-tile-per-CTA kernel is used (nothing to overlap)
+static int g_wide_min_tiles = 1;     // test hook: GEMMs with fewer output tiles stay on the one-tile-per-CTA kernel
 extern "C" int rd_linear_wide_min_tiles(int n) { g_wide_min_tiles = n; return RD_OK; }
 
 namespace {
@@ -503,11 +503,15 @@ int sm_count() {
 }
 
 // token-tile width.  Measured on B200 (tools/bench_wide.py): with a 4..6-stage ring a tile's time barely depends on its width
-// between 160 and 256 tokens (the per-k-block TMA round trip, not the MMA, paces the narrower tiles), so narrower tiles only add
-// rounds: 256 unless the whole problem is narrower.
-int choose_nt(int M) {
-  if (M >= 256) return 256;
-  return (M + 15) / 16 * 16;
+// between 160 and 256 tokens (the per-k-block TMA round trip, not the MMA, paces the narrower tiles), so big problems take 256.
+// Mid-size problems (Q-Former: 1024 query tokens x 768 features = 24 tiles of 256 tokens for 148 SMs) take the widest of
+// 256 / 128 / 64 that still yields ~100 tiles (qf dense 36.8 -> 14.3 us, fc2 42 -> 24 us against the one-tile-per-CTA kernel).
+int choose_nt(int M, int w_tiles) {
+  const int m16 = (M + 15) / 16 * 16;
+  for (int nt : {256, 128}) {
+    if ((long long)((M + nt - 1) / nt) * w_tiles >= 120) return nt < m16 ? nt : m16;
+  }
+  return 64 < m16 ? 64 : m16;
 }
 
 // implicit-GEMM convolution: geometry of the NHWC activation the token operand is gathered from (nullptr = plain GEMM)
@@ -568,7 +572,7 @@ int make_im2col_map(CUtensorMap* map, const void* x, const ConvGeom& g, int pixe
 
 template <class T, bool SWIGLU, bool PAIR>
 int launch_wide(const void* x, int64_t ldx, const void* w, int64_t ldw, void* out, int64_t ldo, int M, int N, int K,
-                const EpiParams& epi, int mode, int dtype, cudaStream_t st, const ConvGeom* conv = nullptr) {
+                const EpiParams& epi, int mode, int dtype, cudaStream_t st, int nt, const ConvGeom* conv = nullptr) {
   constexpr int FEATS = SWIGLU ? 64 : 128;
   const int sms = sm_count();
   WideParams p{};
@@ -578,7 +582,7 @@ int launch_wide(const void* x, int64_t ldx, const void* w, int64_t ldw, void* ou
   constexpr int SB = PAIR ? PAIR_STAGE_BYTES : STAGE_BYTES;
   const int units = PAIR ? sms / 2 : sms;
   p.n_tiles = (N + TILE_FEATS - 1) / TILE_FEATS;
-  p.NT = g_wide_force_nt > 0 ? g_wide_force_nt : choose_nt(M);
+  p.NT = nt;
   p.CR = (p.NT % 32 == 0) ? 32 : 16;
   p.m_tiles = (M + p.NT - 1) / p.NT;
   const long long tiles = (long long)p.m_tiles * p.n_tiles;
@@ -643,17 +647,17 @@ static int wide_dispatch(const void* x, int64_t ldx, const void* w, int64_t ldw,
   if (((uintptr_t)out & 15) != 0 || ldo % 8 != 0) return 0;
   if (epi.residual != nullptr && (((uintptr_t)epi.residual & 15) != 0 || epi.ld_res % 8 != 0)) return 0;
   // CTA pairs need a token tile that splits into two swizzle-aligned halves
-  const int nt = g_wide_force_nt > 0 ? g_wide_force_nt : choose_nt(M);
-  // ... and pay off when the MMAs dominate: deep K, and enough weight tiles that the second CTA of a pair is not idle
   const int w_tiles = (N + (sw ? 64 : 128) - 1) / (sw ? 64 : 128);
+  const int nt = g_wide_force_nt > 0 ? g_wide_force_nt : choose_nt(M, w_tiles);
+  // ... and pay off when the MMAs dominate: deep K, and enough weight tiles that the second CTA of a pair is not idle
   const bool pair = g_wide_pair && nt % 16 == 0 && K >= 8 * BK && w_tiles >= 2 && (w_tiles % 2 == 0 || w_tiles >= 8);
   RD_DISPATCH_DTYPE(dtype, T, {
     if (pair) {
-      if (sw) return launch_wide<T, true, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, conv);
-      return launch_wide<T, false, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, conv);
+      if (sw) return launch_wide<T, true, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, nt, conv);
+      return launch_wide<T, false, true>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, nt, conv);
     }
-    if (sw) return launch_wide<T, true, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, conv);
-    return launch_wide<T, false, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, conv);
+    if (sw) return launch_wide<T, true, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, nt, conv);
+    return launch_wide<T, false, false>(x, ldx, w, ldw, out, ldo, M, N, K, epi, mode, dtype, st, nt, conv);
   });
 }
 

@@ -244,7 +244,7 @@ def test_persistent_wide_kernel_bit_identical(cuda_dev, lib, dtype, case, nt, st
         lib.rd_linear_force_splits(0)
         lib.rd_linear_wide_persistent(1)
         lib.rd_linear_wide_pair(1)
-        lib.rd_linear_wide_min_tiles(149)
+        lib.rd_linear_wide_min_tiles(1)
         lib.rd_linear_wide_force_nt(0)
         lib.rd_linear_wide_force_stages(0)
     assert torch.isfinite(outs[1][0].float()).all(), "persistent kernel left outputs unwritten"
@@ -318,7 +318,7 @@ def test_implicit_gemm_convolution_bit_identical_to_im2col_path(cuda_dev, lib, d
     try:
         out_e = run_linear(lib, col, w.reshape(Cout, K), M, Cout, K, dtype, _lib.ALGO_TC, bias=bias, act=act, residual=residual, res_mode=2)
     finally:
-        lib.rd_linear_wide_min_tiles(149)
+        lib.rd_linear_wide_min_tiles(1)
     assert torch.isfinite(out_i.float()).all(), "implicit conv left outputs unwritten"
     assert torch.equal(out_i, out_e), f"max diff {(out_i.float() - out_e.float()).abs().max().item():.4g}"
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad)

@@ -24,6 +24,12 @@ SHAPES = [
     ("l2_conv2", 25088, 128, 1152, _lib.ACT_RELU, False),
     ("l3_conv3", 6272, 1024, 256, _lib.ACT_RELU, True),
     ("l4_conv2", 1568, 512, 4608, _lib.ACT_RELU, False),
+    ("qf_self_qkv", 1024, 2304, 768, _lib.ACT_RELU, False),
+    ("qf_dense", 1024, 768, 768, _lib.ACT_RELU, True),
+    ("qf_fc1", 1024, 3072, 768, _lib.ACT_RELU, False),
+    ("qf_fc2", 1024, 768, 3072, _lib.ACT_RELU, True),
+    ("qf_cross_kv", 6272, 9216, 1408, _lib.ACT_RELU, False),
+    ("proj", 6272, 1408, 1408, _lib.ACT_RELU, False),
 ]
 
 
@@ -35,8 +41,10 @@ def main():
     ap.add_argument("--stages", default="0", help="comma list of pipeline depths to try per nt (0 = by K)")
     ap.add_argument("--sustained", type=int, default=0, help="N > 0: time N back-to-back launches with no L2 flush in between (power-limited "
                     "clocks, as inside a prefill) and print torch.matmul (cuBLAS) on the same shape beside it")
+    ap.add_argument("--min-tiles", type=int, default=1)
     args = ap.parse_args()
     lib = _lib.load()
+    lib.rd_linear_wide_min_tiles(args.min_tiles)
     dev = torch.device("cuda:0")
     dtype = torch.bfloat16
     peak = 1404.0
