@@ -93,6 +93,16 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
     }
   }
   pdl_wait();
+  // lora_B rows of the two q (threads 0..63) or two v (threads 64..127) outputs this thread finishes: requested first, so they are in
+  // flight together with the position / rotary-table / projection loads of the prologue instead of after them.
+  // (They must NOT move above the PDL wait: measured on B200, eager launches then read stale rows - tools/debug_graph_eager.py.)
+  constexpr int half_hd = HD / 2;
+  Vec8<T> lb_lo, lb_hi;
+  if (lora_r == 8 && tid < 2 * half_hd) {
+    const int n_row = tid < half_hd ? h * HD + tid : nh * HD + h * HD + (tid - half_hd);
+    lb_lo = ld16(lora_b + (int64_t)n_row * 8);
+    lb_hi = ld16(lora_b + (int64_t)(n_row + half_hd) * 8);
+  }
 
   const int ctx = ctx_len_p[0];                  // cached keys; the new token goes to slot ctx
   const int n_kv = (ctx + CH - 1) / CH;          // chunks that hold real keys
@@ -153,8 +163,7 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
       }
     };
     // peft LoRA (unmerged): the GEMM wrote t = T(lora_A . xn) after the 3H projection columns (q's r values, then v's)
-    auto lora8 = [&](float y, int n_row, const float* t) {
-      const Vec8<T> bv = ld16(lora_b + (int64_t)n_row * 8);
+    auto lora8 = [&](float y, const Vec8<T>& bv, const float* t) {
       float sdot = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) sdot = fmaf(Tr<T>::f(bv.v[i]), t[i], sdot);
@@ -169,16 +178,16 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
     const bool l8 = lora_r == 8;
     if (tid < half) {
       const int d = tid, p = pos[b];
-      const float c_lo = Tr<T>::f(cos_t[(int64_t)p * HD + d]), c_hi = Tr<T>::f(cos_t[(int64_t)p * HD + d + half]);
-      const float s_lo = Tr<T>::f(sin_t[(int64_t)p * HD + d]), s_hi = Tr<T>::f(sin_t[(int64_t)p * HD + d + half]);
       int cols[12] = {h * HD + d, h * HD + d + half, H + h * HD + d, H + h * HD + d + half, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int i = 0; i < 8; ++i) cols[4 + i] = 3 * H + i;
+      const float c_lo = Tr<T>::f(cos_t[(int64_t)p * HD + d]), c_hi = Tr<T>::f(cos_t[(int64_t)p * HD + d + half]);
+      const float s_lo = Tr<T>::f(sin_t[(int64_t)p * HD + d]), s_hi = Tr<T>::f(sin_t[(int64_t)p * HD + d + half]);
       float v[12];
       gather(cols, l8 ? 12 : 4, v);
       float lo = v[0], hi = v[1];
       const float klo = v[2], khi = v[3];
-      if (l8) { lo = lora8(lo, h * HD + d, v + 4); hi = lora8(hi, h * HD + d + half, v + 4); }
+      if (l8) { lo = lora8(lo, lb_lo, v + 4); hi = lora8(hi, lb_hi, v + 4); }
       else if (lora_r > 0) { lo = lora_any(lo, h * HD + d, 3 * H); hi = lora_any(hi, h * HD + d + half, 3 * H); }
       s_q[d] = Tr<T>::rr(Tr<T>::rr(lo * c_lo) + Tr<T>::rr(-hi * s_lo));
       s_q[d + half] = Tr<T>::rr(Tr<T>::rr(hi * c_hi) + Tr<T>::rr(lo * s_hi));
@@ -194,7 +203,7 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
       float v[12];
       gather(cols, l8 ? 10 : 2, v);
       float v_lo = v[0], v_hi = v[1];
-      if (l8) { v_lo = lora8(v_lo, H + h * HD + d, v + 2); v_hi = lora8(v_hi, H + h * HD + d + half, v + 2); }
+      if (l8) { v_lo = lora8(v_lo, lb_lo, v + 2); v_hi = lora8(v_hi, lb_hi, v + 2); }
       else if (lora_r > 0) {
         v_lo = lora_any(v_lo, H + h * HD + d, 3 * H + lora_r);
         v_hi = lora_any(v_hi, H + h * HD + d + half, 3 * H + lora_r);
