@@ -19,6 +19,7 @@
 // before griddepcontrol.wait and only then loads the activations.
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 
 // Tuning knobs of the decode tiles (compile-time; defaults = the measured best)
@@ -814,36 +815,41 @@ _Pragma("unroll")
     if (warp >= 2 && n < p.N) {
       const uint32_t red_addr = smem_u32(red);
       // this CTA's slice of the token columns: j = split, split + splits, ...; RT columns per round so that their partials
-      // are in flight together over DSMEM; summed in fixed split order.
-      constexpr int RT = SWIGLU ? 4 : 8;       // token columns per round (register budget: RT x 8 partials, x2 with SwiGLU)
-      EPI_DISPATCH(p.epi_mode,
-        for (int jb = split; jb < m_valid; jb += RT * p.splits) {
-          float v[RT][8], vu[SWIGLU ? RT : 1][8];
+      // are in flight together over DSMEM; summed in fixed split order.  Register budget: RT x SMAX partials (x2 with SwiGLU) -
+      // with at most 4 splits (gate|up: 3) twice as many columns fit in a round, i.e. one DSMEM round trip less in the tail.
+      auto reduce = [&](auto smax_c, auto rt_c) {
+        constexpr int SMAX = decltype(smax_c)::value, RT = decltype(rt_c)::value;
+        EPI_DISPATCH(p.epi_mode,
+          for (int jb = split; jb < m_valid; jb += RT * p.splits) {
+            float v[RT][SMAX], vu[SWIGLU ? RT : 1][SMAX];
 _Pragma("unroll")
-          for (int t = 0; t < RT; ++t) {
-            const int j = jb + t * p.splits;
+            for (int t = 0; t < RT; ++t) {
+              const int j = jb + t * p.splits;
 _Pragma("unroll")
-            for (int s = 0; s < 8; ++s) {
-              v[t][s] = 0.f;
-              if (SWIGLU) vu[t][s] = 0.f;
-              if (j < m_valid && s < p.splits) {
-                v[t][s] = ld_dsmem_f32(red_addr + (uint32_t)((j * BLOCK_N + n_local) * 4), (uint32_t)s);
-                if (SWIGLU) vu[t][s] = ld_dsmem_f32(red_addr + (uint32_t)(((NT + j) * BLOCK_N + n_local) * 4), (uint32_t)s);
+              for (int s = 0; s < SMAX; ++s) {
+                v[t][s] = 0.f;
+                if (SWIGLU) vu[t][s] = 0.f;
+                if (j < m_valid && s < p.splits) {
+                  v[t][s] = ld_dsmem_f32(red_addr + (uint32_t)((j * BLOCK_N + n_local) * 4), (uint32_t)s);
+                  if (SWIGLU) vu[t][s] = ld_dsmem_f32(red_addr + (uint32_t)(((NT + j) * BLOCK_N + n_local) * 4), (uint32_t)s);
+                }
+              }
+            }
+_Pragma("unroll")
+            for (int t = 0; t < RT; ++t) {
+              const int j = jb + t * p.splits;
+              if (j < m_valid) {
+                float acc = 0.f, accu = 0.f;
+_Pragma("unroll")
+                for (int s = 0; s < SMAX; ++s) { acc += v[t][s]; if (SWIGLU) accu += vu[t][s]; }
+                finish_store<T, SWIGLU, MODE>(p.epi, cx, acc, accu, m0 + j, n, j);
               }
             }
           }
-_Pragma("unroll")
-          for (int t = 0; t < RT; ++t) {
-            const int j = jb + t * p.splits;
-            if (j < m_valid) {
-              float acc = 0.f, accu = 0.f;
-_Pragma("unroll")
-              for (int s = 0; s < 8; ++s) { acc += v[t][s]; if (SWIGLU) accu += vu[t][s]; }
-              finish_store<T, SWIGLU, MODE>(p.epi, cx, acc, accu, m0 + j, n, j);
-            }
-          }
-        }
-      )
+        )
+      };
+      if (p.splits <= 4) reduce(std::integral_constant<int, 4>{}, std::integral_constant<int, 8>{});
+      else reduce(std::integral_constant<int, 8>{}, std::integral_constant<int, SWIGLU ? 4 : 8>{});
     }
     // nobody leaves (and frees its smem) while a peer may still be reading it
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
