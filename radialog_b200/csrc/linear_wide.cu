@@ -336,16 +336,20 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     };
     pdl_wait();                                   // residual reads and every store come after the previous kernel
     // residual prefetch iterator (thread e == 32): runs D chunks ahead of the chunk being finished
-    int pf_t = unit, pf_c = 0, pf_g = 0;
+    // (the tile's coordinates and chunk count are kept between calls: the per-chunk path is an mbarrier arm + one TMA issue, no
+    // integer divisions - this thread's warp sits on every chunk's critical path)
+    int pf_t = unit, pf_c = 0, pf_b = 0, pf_m0 = 0, pf_n0 = 0, pf_nch = 0;
+    if (pf_t < p.tiles) { tile_coords(pf_t, pf_m0, pf_n0); pf_nch = n_chunks_of(pf_t); }
     auto issue_res = [&]() {
       if (pf_t >= p.tiles) return;
-      int m0, n0;
-      tile_coords(pf_t, m0, n0);
-      const int b = pf_g % NBUF;
-      mbar_expect_tx(&res_full[b], (uint32_t)(CR * FEATS * 2));
-      tma_load_2d(epi_s + b * CBUF, &map_res, &res_full[b], n0, m0 + pf_c * CR, HINT_NORMAL);
-      ++pf_g;
-      if (++pf_c == n_chunks_of(pf_t)) { pf_c = 0; pf_t += n_units; }
+      mbar_expect_tx(&res_full[pf_b], (uint32_t)(CR * FEATS * 2));
+      tma_load_2d(epi_s + pf_b * CBUF, &map_res, &res_full[pf_b], pf_n0, pf_m0 + pf_c * CR, HINT_NORMAL);
+      if (++pf_b == NBUF) pf_b = 0;
+      if (++pf_c == pf_nch) {
+        pf_c = 0;
+        pf_t += n_units;
+        if (pf_t < p.tiles) { tile_coords(pf_t, pf_m0, pf_n0); pf_nch = n_chunks_of(pf_t); }
+      }
     };
     // stores allowed to be still reading their buffer after a new one is committed; the residual of chunk g + D goes into the
     // buffer chunk g - E - 1 was stored from.  The store side (thread 0) and the residual loads (thread 32) are separate
@@ -354,7 +358,8 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     if (has_res && e == 32) {
       for (int i = 0; i < D; ++i) issue_res();
     }
-    int g = 0, tl = 0;
+    int g = 0, tl = 0, cb = 0;                    // cb / cph: chunk buffer index and its mbarrier phase (g % NBUF, (g / NBUF) & 1)
+    uint32_t cph = 0;
 #ifdef RD_WIDE_PROF
     long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
 #define PROF(i) { const long long _n = clock64(); pf[i] += _n - pt; pt = _n; }
@@ -374,13 +379,13 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       tc_fence_after();
       PROF(1)
       for (int c = 0; c < nch; ++c, ++g) {
-        const int b = g % NBUF;
+        const int b = cb;
         T* bufp = reinterpret_cast<T*>(epi_s + b * CBUF);
         epi_bar(1);                               // buffer b and the exchange area are free (thread 0 has waited for the store)
         PROF(2)
         if (has_res) {
           if (e == 32) issue_res();               // chunk g + D
-          mbar_wait(&res_full[b], (uint32_t)((g / NBUF) & 1), 5);
+          mbar_wait(&res_full[b], cph, 5);
         }
         PROF(3)
         uint32_t r0[16], r1[16];
@@ -471,6 +476,7 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         PROF(7)
+        if (++cb == NBUF) { cb = 0; cph ^= 1u; }
       }
     }
     if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

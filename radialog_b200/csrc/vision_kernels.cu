@@ -217,10 +217,41 @@ small_attention_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T* kb = k + (int64_t)b * kv_len * ldkv + h * HD;
   const T* vb = v + (int64_t)b * kv_len * ldkv + h * HD;
-  for (int i = tid; i < kv_len * (HD / 2); i += 256) {
-    const int j = i / (HD / 2), d2 = i % (HD / 2);
-    *reinterpret_cast<uint32_t*>(sk + j * LDS + d2 * 2) = *reinterpret_cast<const uint32_t*>(kb + (int64_t)j * ldkv + d2 * 2);
-    *reinterpret_cast<uint32_t*>(sv + j * LDS + d2 * 2) = *reinterpret_cast<const uint32_t*>(vb + (int64_t)j * ldkv + d2 * 2);
+  if ((ldkv & 7) == 0 && ((reinterpret_cast<uintptr_t>(kb) | reinterpret_cast<uintptr_t>(vb)) & 15) == 0) {
+    // 16-byte global loads, four K and four V requests in flight per thread before the first one is consumed (the rows are
+    // padded by one word in shared memory, so they are stored as 4-byte words); the 4-byte loop below paid one global
+    // round trip per element pair and was most of the kernel's time for the 196-key cross attention
+    constexpr int C8 = HD / 8;
+    const int n16 = kv_len * C8;
+    for (int base = tid; base < n16; base += 256 * 4) {
+      uint4 kk[4], vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * 256;
+        if (i < n16) {
+          const int j = i / C8, c = i % C8;
+          kk[u] = *reinterpret_cast<const uint4*>(kb + (int64_t)j * ldkv + c * 8);
+          vv[u] = *reinterpret_cast<const uint4*>(vb + (int64_t)j * ldkv + c * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * 256;
+        if (i < n16) {
+          const int j = i / C8, c = i % C8;
+          uint32_t* dk = reinterpret_cast<uint32_t*>(sk + j * LDS + c * 8);
+          uint32_t* dv = reinterpret_cast<uint32_t*>(sv + j * LDS + c * 8);
+          dk[0] = kk[u].x; dk[1] = kk[u].y; dk[2] = kk[u].z; dk[3] = kk[u].w;
+          dv[0] = vv[u].x; dv[1] = vv[u].y; dv[2] = vv[u].z; dv[3] = vv[u].w;
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < kv_len * (HD / 2); i += 256) {
+      const int j = i / (HD / 2), d2 = i % (HD / 2);
+      *reinterpret_cast<uint32_t*>(sk + j * LDS + d2 * 2) = *reinterpret_cast<const uint32_t*>(kb + (int64_t)j * ldkv + d2 * 2);
+      *reinterpret_cast<uint32_t*>(sv + j * LDS + d2 * 2) = *reinterpret_cast<const uint32_t*>(vb + (int64_t)j * ldkv + d2 * 2);
+    }
   }
   __syncthreads();
   const float scale = 1.0f / sqrtf((float)HD);
