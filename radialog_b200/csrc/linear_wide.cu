@@ -10,13 +10,14 @@
 //
 //   warp 0    TMA producer: 2..4-stage ring of (16 KB weight k-block + NT x 128 B token k-block), runs ahead across tiles
 //   warp 1    tcgen05.mma issuer; the 512 TMEM columns hold TWO accumulator buffers, tile i+1 accumulates while
-//   warps 2-5 drain tile i:  tcgen05.ld -> registers -> epilogue arithmetic -> shared memory -> TMA store, in chunks of CR <= 32
+//   warps 2-9 drain tile i (two warps per TMEM lane quadrant, each half of a chunk's token columns):
+//             tcgen05.ld -> registers -> epilogue arithmetic -> shared memory -> TMA store, in chunks of CR <= 32
 //             tokens.  The residual tile arrives by TMA too (3..15 chunks ahead, same shared-memory buffer the result is
 //             written back into), so the epilogue issues no per-thread global loads or stores at all.
 //
 // SwiGLU (gate|up) tiles hold 64 gate rows + 64 up rows of W in ONE 128-row A tile (two 64-row TMA boxes), so the MMA shape
 // and the single 256-column accumulator are the same as for every other GEMM and double buffering still fits in TMEM; the two
-// lane halves exchange T(g) / T(u) through 8 KB of shared memory and all four epilogue warps share the silu work.
+// lane halves exchange T(g) / T(u) through 8 KB of shared memory and all eight epilogue warps share the silu work.
 //
 // The token-tile width NT is a launch parameter (any multiple of 16 up to 256): the host picks the NT that wastes the
 // fewest MMA cycles to round quantisation (tiles / SMs), e.g. 240 instead of 256 for the 2048-token prefill o_proj/down
@@ -64,7 +65,9 @@ constexpr int RING_EPI_BYTES = MAX_STAGES * STAGE_BYTES + 4 * BUF_BYTES;   // 22
                                                  // 4 stages + 4 buffers (deep K), 3 + 10, or 2 + 16 (K <= 128: the tile is all epilogue)
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_BYTES = RING_EPI_BYTES + BAR_BYTES + 1024;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                     // two warps per TMEM lane quadrant: each takes half of a chunk's token columns
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int THREADS = 64 + EPI_THREADS;
 constexpr uint64_t HINT_NORMAL = 0x1000000000000000ull;
 
 enum { W_PLAIN = 0, W_RES1 = 1, W_AFFINE = 2 };
@@ -87,7 +90,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(EPI_THREADS) : "memory"); }
 
 // ---- CTA pair (cta_group::2) helpers: the two CTAs of a cluster run one 256-row UMMA; the even CTA (rank 0) issues it ----
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -184,7 +187,7 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
     if (p.has_res) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_res)) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PAIR ? 256 : 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PAIR ? 2 * EPI_THREADS : EPI_THREADS); }
     for (int b = 0; b < MAX_NBUF; ++b) mbar_init(&res_full[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -321,9 +324,11 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       }
     }
   } else if (warp >= 2) {
-    // ===================== epilogue (warps 2..5 = TMEM lane quadrants 2, 3, 0, 1) =====================
+    // ===================== epilogue (warps 2..9: TMEM lane quadrant = warp & 3; `sub` = which half of a chunk's columns) ==========
     const int e = threadIdx.x - 64;
     const int quad = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const bool works = (CR == 32) || sub == 0;     // 16-token chunks are not split: the second warp of a quadrant only keeps the barriers
     const int n_local = quad * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int mode = p.mode, act = p.act;
@@ -388,10 +393,9 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           mbar_wait(&res_full[b], cph, 5);
         }
         PROF(3)
-        uint32_t r0[16], r1[16];
-        const uint32_t ta = taddr + (uint32_t)(buf * 256 + c * CR);
-        tc_ld16(ta, r0);
-        if (CR == 32) tc_ld16(ta + 16, r1);
+        uint32_t r0[16];
+        const int jb0 = (CR == 32) ? sub * 16 : 0;   // first token row of the chunk this thread finishes (16 rows)
+        if (works) tc_ld16(taddr + (uint32_t)(buf * 256 + c * CR + jb0), r0);
         tc_wait_ld();
         PROF(4)
         if (c == nch - 1) {                       // accumulators of this tile are in registers: hand the buffer back
@@ -401,28 +405,26 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         }
         if (SWIGLU) {
           // lanes 0..63 hold the gate rows, lanes 64..127 the up rows of the same 64 features: both halves park T(.) of their
-          // accumulators (the reference rounds g and u to the storage type before anything else), then ALL four warps share the
-          // silu / multiply work: thread -> (feature e & 63, half of the chunk's token rows e >> 6)
+          // accumulators (the reference rounds g and u to the storage type before anything else), then ALL epilogue warps share the
+          // silu / multiply work: thread -> (feature e & 63, quarter of the chunk's token rows e >> 6)
           T* exg = reinterpret_cast<T*>(epi_s + NBUF * CBUF);
           T* exu = exg + 32 * 64;
-          T* mine = (quad >= 2 ? exu : exg) + (n_local & 63);
+          T* mine = (quad >= 2 ? exu : exg) + (n_local & 63) + jb0 * 64;
+          if (works) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mine[j * 64] = Tr<T>::r(__uint_as_float(r0[j]));
-          if (CR == 32) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) mine[(16 + j) * 64] = Tr<T>::r(__uint_as_float(r1[j]));
+            for (int j = 0; j < 16; ++j) mine[j * 64] = Tr<T>::r(__uint_as_float(r0[j]));
           }
           epi_bar(3);
-          const int f = e & 63, half = CR >> 1, j0 = (e >> 6) * half;
+          const int f = e & 63, quarter = CR >> 2, j0 = (e >> 6) * quarter;     // 256 threads: 64 features x 4 groups of token rows
           if (CR == 32) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const float gt = Tr<T>::f(exg[(j0 + j) * 64 + f]), u = Tr<T>::f(exu[(j0 + j) * 64 + f]);
               bufp[(j0 + j) * 64 + f] = Tr<T>::r(Tr<T>::rr(silu_f(gt)) * u);      // T(T(silu(T(g))) * T(u))
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               const float gt = Tr<T>::f(exg[(j0 + j) * 64 + f]), u = Tr<T>::f(exu[(j0 + j) * 64 + f]);
               bufp[(j0 + j) * 64 + f] = Tr<T>::r(Tr<T>::rr(silu_f(gt)) * u);
             }
@@ -462,8 +464,7 @@ linear_wide_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
               for (int j = 0; j < 16; ++j) q[j * 128] = Tr<T>::r(__uint_as_float(r[j]));
             }
           };
-          finish(r0, 0);
-          if (CR == 32) finish(r1, 16);
+          if (works) finish(r0, jb0);
         }
         fence_proxy_async_smem();
         PROF(5)
