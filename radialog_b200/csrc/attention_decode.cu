@@ -7,9 +7,14 @@
 // with mbarrier completion instead of per-lane global loads: one elected thread keeps RING copies in flight, the rest of
 // the CTA computes from shared memory.  The first RING K chunks only cover cache rows written by EARLIER decode steps,
 // so they are requested before griddepcontrol.wait and stream in while the QKV GEMM of this layer is still finishing.
-// (Safety of that early read: programmatic launch depth is bounded to a few kernels by SM residency — every GEMM CTA
-// in between holds >100 KB of shared memory — while the writer of those rows is a whole decode step (>200 kernels)
-// back in the stream.  `prefetch_keys` is a host-known lower bound; chunks past the real context are read but ignored.)
+// Safety of that early read.  With programmatic dependent launch every kernel releases its successor at its own start, so the
+// pre-wait sections of a whole chain of kernels can run at once - bounded only by SM residency.  The newest cache row was written
+// by the previous decode step's attention kernel of the same layer: one step back.  With GEMMs that fill the machine (every
+// Vicuna-7B GEMM: 190-260 CTAs x 100 KB of shared memory) at most two or three kernels are co-resident, the writer is > 200
+// kernels back and the early read is safe.  With a toy model a whole step fits on the SMs at once and the early read DID return
+// stale rows (tests/test_gpu_llm.py eager-vs-graph, found when the pre-wait section grew).  So (1) the caller passes a non-zero
+// `prefetch_keys` only for models whose GEMMs fill the machine (engine_llm.cu), and (2) the chunk holding the newest row is never
+// part of the early prefetch.  `prefetch_keys` is a host-known lower bound of the context; chunks past it are not requested early.
 #include "common.cuh"
 
 bool rd_pdl_enabled();
@@ -53,7 +58,7 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
                         int cmax, const int32_t* __restrict__ pos, const T* __restrict__ cos_t, const T* __restrict__ sin_t,
                         int prefetch_keys, const T* __restrict__ lora_b, int lora_r, float lora_scale,
                         const void* pf0, long long pf0_bytes, const void* pf1, long long pf1_bytes,
-                        const float* __restrict__ qkv_part, int n_part, long long part_stride) {
+                        const float* __restrict__ qkv_part, int n_part, long long part_stride, const T* __restrict__ rope_rows) {
   constexpr int GROUPS = THREADS / 16;
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -71,6 +76,13 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
   const T* kbase = kc + ((int64_t)b * nh + h) * cmax * HD;
   const T* vbase = vc + ((int64_t)b * nh + h) * cmax * HD;
 
+#ifdef RD_ATT_PROF
+  long long pt[8]; int pn = 0;
+#define APROF() { if (tid == 0 && pn < 8) pt[pn++] = clock64(); }
+#else
+#define APROF()
+#endif
+  APROF()
   pdl_launch_dependents();
   {                     // weights of the next GEMMs -> L2 while this latency-bound kernel leaves HBM idle
     const int cta = blockIdx.y * gridDim.x + blockIdx.x, n_ctas = gridDim.x * gridDim.y;
@@ -84,7 +96,7 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
   }
   __syncthreads();
   // chunk sequence: K chunks 0..nK-1 then V chunks 0..nV-1; sequence entry s lives in ring slot s % RING
-  int n_pre = prefetch_keys / CH;
+  int n_pre = prefetch_keys > 0 ? (prefetch_keys - 1) / CH : 0;     // whole chunks strictly below the newest cached row
   n_pre = n_pre > RING ? RING : n_pre;
   if (tid == 0) {
     for (int s = 0; s < n_pre; ++s) {            // cache rows of earlier steps: independent of the previous kernel
@@ -92,10 +104,14 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
       bulk_g2s(ring + (size_t)s * CH * HD, kbase + (size_t)s * CH * HD, CHUNK_BYTES, &full_bar[s]);
     }
   }
+  APROF()
   pdl_wait();
+  APROF()
   // lora_B rows of the two q (threads 0..63) or two v (threads 64..127) outputs this thread finishes: requested first, so they are in
-  // flight together with the position / rotary-table / projection loads of the prologue instead of after them.
-  // (They must NOT move above the PDL wait: measured on B200, eager launches then read stale rows - tools/debug_graph_eager.py.)
+  // flight together with the rotary-row / projection loads of the prologue instead of after them.  They are an HBM miss (weights last
+  // touched a step ago) and the longest item of the prologue; requesting them - or even an L2 prefetch hint for them - BEFORE the PDL
+  // wait made eager (non-graph) decode steps of a toy model return different tokens (tools/debug_graph_eager.py; an unrelated
+  // constant load or a delay in the same place does not), which is not understood - so nothing touches lora_B before the wait.
   constexpr int half_hd = HD / 2;
   Vec8<T> lb_lo, lb_hi;
   if (lora_r == 8 && tid < 2 * half_hd) {
@@ -177,12 +193,16 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
     };
     const bool l8 = lora_r == 8;
     if (tid < half) {
-      const int d = tid, p = pos[b];
+      const int d = tid;
       int cols[12] = {h * HD + d, h * HD + d + half, H + h * HD + d, H + h * HD + d + half, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int i = 0; i < 8; ++i) cols[4 + i] = 3 * H + i;
-      const float c_lo = Tr<T>::f(cos_t[(int64_t)p * HD + d]), c_hi = Tr<T>::f(cos_t[(int64_t)p * HD + d + half]);
-      const float s_lo = Tr<T>::f(sin_t[(int64_t)p * HD + d]), s_hi = Tr<T>::f(sin_t[(int64_t)p * HD + d + half]);
+      // cos / sin of this sequence's position: from the per-step gathered rows when the engine provides them (one load, in flight
+      // with the projection values below), else through pos[b] (two dependent loads)
+      const T* cs = rope_rows != nullptr ? rope_rows + (int64_t)b * 2 * HD : cos_t + (int64_t)pos[b] * HD;
+      const T* sn = rope_rows != nullptr ? cs + HD : sin_t + (int64_t)pos[b] * HD;
+      const float c_lo = Tr<T>::f(cs[d]), c_hi = Tr<T>::f(cs[d + half]);
+      const float s_lo = Tr<T>::f(sn[d]), s_hi = Tr<T>::f(sn[d + half]);
       float v[12];
       gather(cols, l8 ? 12 : 4, v);
       float lo = v[0], hi = v[1];
@@ -213,6 +233,7 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
     }
   }
   __syncthreads();
+  APROF()
   float q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) q[e] = s_q[l16 * 8 + e];
@@ -267,6 +288,7 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
     } else {
       const int c = s - nK;
       if (c == 0) {                                // ---- first V chunk: finish the scores, softmax (fp32, rounded) ----
+        APROF()
         if (g == 0) {
           float d = 0.f;
 #pragma unroll
@@ -295,6 +317,7 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
         for (int w = 0; w < WARPS; ++w) sum += sred[w];
         for (int j = tid; j <= ctx; j += THREADS) sc[j] = Tr<T>::rr(sc[j] / sum);     // softmax(fp32).to(dtype)
         __syncthreads();
+        APROF()
       }
       int keys = ctx - c * CH;
       keys = keys > CH ? CH : keys;
@@ -331,16 +354,25 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
 #pragma unroll
   for (int e = 0; e < 8; ++e) spart[g][l16 * 8 + e] = acc[e];
   __syncthreads();
+  APROF()
   if (tid < HD) {
     float o = 0.f;
 #pragma unroll
     for (int gg = 0; gg < GROUPS; ++gg) o += spart[gg][tid];
     out[(int64_t)b * (nh * HD) + h * HD + tid] = Tr<T>::r(o);
   }
+#ifdef RD_ATT_PROF
+  APROF()
+  if (tid == 0 && ((blockIdx.x == 0 && blockIdx.y == 0) || (blockIdx.x == 17 && blockIdx.y == 20)) && ctx_len_p[0] % 40 == 0)
+    printf("att prof cta(%d,%d) ctx %d: pre-wait %lld wait %lld prologue %lld K-loop %lld softmax %lld V-loop %lld out %lld (cycles)\n", blockIdx.x, blockIdx.y,
+           ctx_len_p[0], pt[1] - pt[0], pt[2] - pt[1], pt[3] - pt[2], pt[4] - pt[3], pt[5] - pt[4], pt[6] - pt[5], pt[7] - pt[6]);
+#endif
 }
 
 }  // namespace
 
+static const void* g_rope_rows = nullptr;     // [B][2][128] cos | sin rows of the step (consumed and cleared by the next launch)
+extern "C" int rd_attention_decode_set_rope_rows(const void* rows) { g_rope_rows = rows; return RD_OK; }
 static const void* g_pf0 = nullptr; static long long g_pf0_bytes = 0;
 static const void* g_pf1 = nullptr; static long long g_pf1_bytes = 0;
 // weights the next rd_attention_decode launch should pull into L2 (consumed by that launch)
@@ -369,14 +401,16 @@ static int attention_decode_impl(const void* qkv, int64_t ldq, const int32_t* po
       RD_SMEM_ATTR_ONCE(200 * 1024, attention_decode_kernel<T, 512, 4>);
       RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 512, 4>, dim3(nh, B), dim3(512), smem, (cudaStream_t)stream, rd_pdl_enabled(),
                               (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
-                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes, qkv_part, n_part, part_stride));
+                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes, qkv_part, n_part, part_stride,
+                              (const T*)g_rope_rows));
     } else {
       RD_SMEM_ATTR_ONCE(200 * 1024, attention_decode_kernel<T, 128, 3>);
       RD_CHECK_CUDA(rd_launch(attention_decode_kernel<T, 128, 3>, dim3(nh, B), dim3(128), smem, (cudaStream_t)stream, rd_pdl_enabled(),
                               (const T*)qkv, ldq, (T*)kc, (T*)vc, keymask, ctx_len, (T*)out, nh, cmax, pos, (const T*)cos_t, (const T*)sin_t, pref,
-                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes, qkv_part, n_part, part_stride));
+                              (const T*)lora_b, lora_b ? lora_r : 0, lora_scale, g_pf0, g_pf0_bytes, g_pf1, g_pf1_bytes, qkv_part, n_part, part_stride,
+                              (const T*)g_rope_rows));
     }
-    g_pf0 = nullptr; g_pf1 = nullptr; g_pf0_bytes = 0; g_pf1_bytes = 0;
+    g_pf0 = nullptr; g_pf1 = nullptr; g_pf0_bytes = 0; g_pf1_bytes = 0; g_rope_rows = nullptr;
     return RD_OK;
   });
 }

@@ -16,6 +16,8 @@ int rd_kv_reorder(const void*, const void*, void*, void*, const int32_t*, const 
 int rd_rmsnorm_partials(const float*, int, int64_t, void*, const void*, void*, int, int, float, int, void*);
 extern "C" int rd_rmsnorm_prefetch(const void*, const void*, void*, int, int, float, const void*, long long, int, void*);
 extern "C" int rd_attention_decode_set_l2_prefetch(const void*, long long, const void*, long long);
+extern "C" int rd_attention_decode_set_rope_rows(const void*);
+int rd_embed_decode(const int64_t*, const void*, void*, int, int, int, const int32_t*, const void*, const void*, void*, int, int, void*);
 extern "C" int rd_llm_prep(const int64_t*, uint8_t*, int32_t*, int32_t*, const int32_t*, int, int, int, int, void*);
 extern "C" int rd_argmax_step(const void*, int64_t, int, int64_t*, int64_t*, int64_t, int32_t*, uint8_t*, int, int32_t*,
                               int32_t*, int32_t*, int32_t*, uint32_t*, int, int, int, int, int, int, void*);
@@ -42,6 +44,8 @@ struct rd_llm {
   // lose their cluster-reduction tail, the layer keeps its 7 launches.
   int od_partials = 1;
   bool xn_ready = false;         // the current step's last layer already produced xn = model.norm(x) for the lm_head
+  char* rope_rows = nullptr;     // [max_batch][2][head_dim]: cos | sin rows of the step's positions (written by the embedding kernel)
+  bool rope_rows_valid = false;  // true inside a single-token step whose embedding kernel filled rope_rows
   float* od_part = nullptr;
   int64_t od_part_bytes = 0;
   float* qkv_part = nullptr;
@@ -114,6 +118,7 @@ extern "C" int rd_llm_create(const rd_llm_config* cfg, rd_llm** out) {
   A((char**)&h->qkv_part, h->qkv_part_bytes);
   h->od_part_bytes = (int64_t)16 * 32 * H * 4;                        // <= 16 splits x 32 tokens x H fp32
   A((char**)&h->od_part, h->od_part_bytes);
+  A(&h->rope_rows, Bm * 2 * (H / cfg->heads) * e);
   int64_t ws = 0;
   const int Ms[2] = {(int)Bm, 256};
   for (int mi = 0; mi < 2; ++mi) {
@@ -138,6 +143,7 @@ extern "C" void rd_llm_destroy(rd_llm* h) {
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->qkv_part) cudaFree(h->qkv_part);
   if (h->od_part) cudaFree(h->od_part);
+  if (h->rope_rows) cudaFree(h->rope_rows);
   if (h->kc_alt) cudaFree(h->kc_alt);
   if (h->vc_alt) cudaFree(h->vc_alt);
   delete h;
@@ -245,6 +251,9 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     const int R2 = c.lora_r ? 2 * c.lora_r : 0;
     const int64_t ldq = 3 * H + R2;
     const bool decode = q_len == 1 && h->l2_prefetch;
+    // early (pre-PDL-wait) read of old cache rows by the decode attention kernel: only when every GEMM of a layer fills the machine,
+    // so that SM residency bounds how many kernels run ahead of their dependencies (see attention_decode.cu)
+    const int kv_early = (H >= 2048 && I >= 4096) ? h->ctx_host : 0;
     const long long qkv_bytes = (long long)(3 * H + R2) * H * 2, o_bytes = (long long)H * H * 2, gu_bytes = (long long)2 * I * H * 2;
     // decode, B <= 32: QKV split-K partials go straight to the attention kernel (no reduction pass in the GEMM)
     const bool qpart = h->qkv_partials && q_len == 1 && M <= 32 && h->algo == 0 && (3 * H + R2) % 4 == 0;
@@ -267,13 +276,14 @@ static int run_layers(rd_llm* h, int B, int q_len, const int32_t* pos, cudaStrea
     if (q_len == 1) {      // decode: RoPE + KV append + attention fused in one launch
       ProfScope ps(h, st, C_ATTN);
       if (decode) rd_attention_decode_set_l2_prefetch(w.o, std::min(o_bytes, h->pf_o), w.gate_up, std::min(gu_bytes, h->pf_gu));
+      if (h->rope_rows_valid) rd_attention_decode_set_rope_rows(h->rope_rows);
       if (qpart && qsplit[0] > 0) {
         RD_CHECK(rd_attention_decode_partials(h->qkv_part, qsplit[0], (long long)qsplit[1] * ldq, ldq, pos, h->cos, h->sin, kc, vc, h->keymask,
-                                              h->ctx_len, h->att, B, nh, hd, c.max_ctx, h->ctx_host, c.lora_r ? w.lora_b : nullptr, c.lora_r,
+                                              h->ctx_len, h->att, B, nh, hd, c.max_ctx, kv_early, c.lora_r ? w.lora_b : nullptr, c.lora_r,
                                               c.lora_scale, dt, st));
       } else {
         RD_CHECK(rd_attention_decode(h->qkv, ldq, pos, h->cos, h->sin, kc, vc, h->keymask, h->ctx_len, h->att, B, nh, hd, c.max_ctx,
-                                     h->ctx_host, c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st));
+                                     kv_early, c.lora_r ? w.lora_b : nullptr, c.lora_r, c.lora_scale, dt, st));
       }
     } else {
       { ProfScope ps(h, st, C_ROPE);
@@ -418,9 +428,13 @@ extern "C" int rd_llm_decode_step(rd_llm* h, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const rd_llm_config& c = h->c;
   { ProfScope ps(h, st, C_EMBED);
-    RD_CHECK(rd_embed_splice(h->cur_tok, h->embed, nullptr, h->x, h->B, 1, c.hidden, c.vocab, c.dtype, st)); }
+    RD_CHECK(rd_embed_decode(h->cur_tok, h->embed, h->x, h->B, c.hidden, c.vocab, h->pos_cur, h->cos, h->sin, h->rope_rows, c.hidden / c.heads,
+                             c.dtype, st)); }
   h->xn_ready = false;
-  RD_CHECK(run_layers(h, h->B, 1, h->pos_cur, st));
+  h->rope_rows_valid = true;
+  const int rl = run_layers(h, h->B, 1, h->pos_cur, st);
+  h->rope_rows_valid = false;
+  RD_CHECK(rl);
   RD_CHECK(head_and_select(h, h->B, 1, nullptr, st));
   h->ctx_host += 1;
   h->n_generated += 1;

@@ -832,6 +832,38 @@ extern "C" int rd_embed_splice(const int64_t* ids, const void* embed, const void
   });
 }
 
+// Single-token step: embedding rows of the current tokens + the cos / sin rows of every sequence's position gathered into
+// rope_rows[B][2][hd] - the attention kernels of all 32 layers then read them with one load instead of pos[b] -> table[pos]
+// (two dependent L2 round trips at the head of every layer's attention prologue).
+template <class T>
+__global__ void __launch_bounds__(128)
+embed_decode_kernel(const int64_t* __restrict__ ids, const T* __restrict__ embed, T* __restrict__ out, int H, int vocab,
+                    const int32_t* __restrict__ pos, const T* __restrict__ cos_t, const T* __restrict__ sin_t, T* __restrict__ rope_rows, int hd) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  int64_t id = ids[b];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const T* src = embed + id * H;
+  const int p = pos[b];
+  for (int k = threadIdx.x * 8; k < H; k += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(out + (int64_t)b * H + k) = *reinterpret_cast<const uint4*>(src + k);
+  for (int d = threadIdx.x; d < hd; d += blockDim.x) {
+    rope_rows[(int64_t)b * 2 * hd + d] = cos_t[(int64_t)p * hd + d];
+    rope_rows[(int64_t)b * 2 * hd + hd + d] = sin_t[(int64_t)p * hd + d];
+  }
+}
+
+int rd_embed_decode(const int64_t* ids, const void* embed, void* out, int B, int H, int vocab, const int32_t* pos, const void* cos_t,
+                    const void* sin_t, void* rope_rows, int hd, int dtype, void* stream) {
+  RD_REQUIRE(B > 0 && H % 8 == 0 && rope_rows != nullptr, "rd_embed_decode: bad arguments");
+  RD_DISPATCH_DTYPE(dtype, T, {
+    RD_CHECK_CUDA(rd_launch(embed_decode_kernel<T>, dim3(B), dim3(128), 0, (cudaStream_t)stream, rd_pdl_enabled(), ids, (const T*)embed, (T*)out,
+                            H, vocab, pos, (const T*)cos_t, (const T*)sin_t, (T*)rope_rows, hd));
+    return RD_OK;
+  });
+}
+
 // ------------------------------------------------------------------------------------------------
 // Generation bookkeeping
 // ------------------------------------------------------------------------------------------------
