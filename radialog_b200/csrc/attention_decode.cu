@@ -116,8 +116,8 @@ attention_decode_kernel(const T* __restrict__ qkv, int64_t ldq, T* __restrict__ 
   Vec8<T> lb_lo, lb_hi;
   if (lora_r == 8 && tid < 2 * half_hd) {
     const int n_row = tid < half_hd ? h * HD + tid : nh * HD + h * HD + (tid - half_hd);
-    lb_lo = ld16(lora_b + (int64_t)n_row * 8);
-    lb_hi = ld16(lora_b + (int64_t)(n_row + half_hd) * 8);
+    lb_lo = ld16_keep(lora_b + (int64_t)n_row * 8);
+    lb_hi = ld16_keep(lora_b + (int64_t)(n_row + half_hd) * 8);
   }
 
   const int ctx = ctx_len_p[0];                  // cached keys; the new token goes to slot ctx

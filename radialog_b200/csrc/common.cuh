@@ -97,6 +97,17 @@ __device__ __forceinline__ Vec8<T> ld_stream16(const T* p) {   // streaming read
   *reinterpret_cast<uint4*>(&r) = u;
   return r;
 }
+// small weights that every decode step re-reads (lora_B rows, 4 MB over all layers): loaded with an L2 evict-last policy so that
+// the 13 GB of evict-first weight traffic streaming through the 126 MB L2 in between does not push them out
+template <class T>
+__device__ __forceinline__ Vec8<T> ld16_keep(const T* p) {
+  Vec8<T> r;
+  uint4 u;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p), "l"(0x14F0000000000000ull));
+  *reinterpret_cast<uint4*>(&r) = u;
+  return r;
+}
 template <class T>
 __device__ __forceinline__ Vec8<T> ld16(const T* p) {          // cached (activations)
   Vec8<T> r;
