@@ -46,9 +46,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   } while (!done);
 }
+// K/V rows are read once per step and the next read is 13 GB of traffic later: an L2 evict-first policy keeps the sweep (60-100 MB
+// per layer) from pushing out the small data every layer re-reads (split-K slabs, activations, masks, lora_B rows)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(0x12F0000000000000ull) : "memory");
 }
 
 template <class T, int THREADS, int RING>
