@@ -134,7 +134,7 @@ rmsnorm_partials_kernel(const float* __restrict__ part, int splits, int64_t slab
                         T* __restrict__ out, int H, float eps) {
   pdl_launch_dependents();
   __shared__ float swarp[RNP_THREADS / 32];
-  __shared__ float s_part;
+  __shared__ float s_parts[RNP_CL];     // the four quarter sums of this row, each pushed here by the CTA that owns it
   const int c = blockIdx.x, m = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Hq = H / RNP_CL, groups = Hq / 8;
   const int col0 = c * Hq;
@@ -178,11 +178,16 @@ rmsnorm_partials_kernel(const float* __restrict__ part, int splits, int64_t slab
   ss = warp_sum(ss);
   if (lane == 0) swarp[warp] = ss;
   __syncthreads();
-  if (tid == 0) s_part = ((swarp[0] + swarp[1]) + swarp[2]) + swarp[3];
+  if (tid < RNP_CL) {
+    // every CTA PUSHES its quarter sum into all four CTAs' shared memory (st.shared::cluster) before the one cluster barrier:
+    // after it everybody reads locally, nobody touches a peer's memory any more, and no trailing barrier is needed before exit
+    const float mine = ((swarp[0] + swarp[1]) + swarp[2]) + swarp[3];
+    uint32_t la = (uint32_t)__cvta_generic_to_shared(&s_parts[c]), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"((uint32_t)tid));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(mine) : "memory");
+  }
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  float tot = 0.f;
-#pragma unroll
-  for (int r = 0; r < RNP_CL; ++r) tot += rnp_ld_dsmem(&s_part, (uint32_t)r);        // rank order: the same total in all four CTAs
+  const float tot = ((s_parts[0] + s_parts[1]) + s_parts[2]) + s_parts[3];             // rank order: the same total in all four CTAs
   const float rs = 1.0f / sqrtf(tot / (float)H + eps);       // torch.rsqrt(variance + eps), fp32
 #pragma unroll
   for (int u = 0; u < RNP_MAXG; ++u) {
@@ -197,8 +202,6 @@ rmsnorm_partials_kernel(const float* __restrict__ part, int splits, int64_t slab
       *reinterpret_cast<uint4*>(out + (int64_t)m * H + col0 + g * 8) = *reinterpret_cast<uint4*>(&o);
     }
   }
-  // nobody leaves (and frees its shared memory) while a peer may still be reading its quarter sum
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 int rd_rmsnorm_partials(const float* part, int splits, int64_t slab_stride, void* x, const void* w, void* out, int M, int H, float eps,
