@@ -135,12 +135,22 @@ rmsnorm_partials_kernel(const float* __restrict__ part, int splits, int64_t slab
   pdl_launch_dependents();
   __shared__ float swarp[RNP_THREADS / 32];
   __shared__ float s_parts[RNP_CL];     // the four quarter sums of this row, each pushed here by the CTA that owns it
+  __shared__ __align__(8) uint64_t xbar;  // completes when all four quarter sums (16 bytes) have landed
   const int c = blockIdx.x, m = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Hq = H / RNP_CL, groups = Hq / 8;
   const int col0 = c * Hq;
   Vec8<T> wv[RNP_MAXG], xv[RNP_MAXG];
 #pragma unroll
   for (int u = 0; u < RNP_MAXG; ++u) { const int g = tid + u * RNP_THREADS; if (g < groups) wv[u] = ld16(w + col0 + g * 8); }      // no dependency on the GEMM
+  // the exchange barrier is armed, and the whole cluster knows it, BEFORE the PDL wait: the only cluster-wide barrier of the kernel
+  // costs nothing on the dependent path, which is left with four asynchronous remote stores and a local mbarrier wait
+  if (tid == 0) {
+    const uint32_t ba = (uint32_t)__cvta_generic_to_shared(&xbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ba) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"(4 * RNP_CL) : "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   pdl_wait();
   T* xr = x + (int64_t)m * H + col0;
   const float* pr = part + (int64_t)m * H + col0;
@@ -179,14 +189,27 @@ rmsnorm_partials_kernel(const float* __restrict__ part, int splits, int64_t slab
   if (lane == 0) swarp[warp] = ss;
   __syncthreads();
   if (tid < RNP_CL) {
-    // every CTA PUSHES its quarter sum into all four CTAs' shared memory (st.shared::cluster) before the one cluster barrier:
-    // after it everybody reads locally, nobody touches a peer's memory any more, and no trailing barrier is needed before exit
+    // every CTA PUSHES its quarter sum into all four CTAs' shared memory (st.async: the store completes the receiver's mbarrier);
+    // everybody then waits on its own barrier and reads locally - no cluster barrier on the dependent path, none before exit
     const float mine = ((swarp[0] + swarp[1]) + swarp[2]) + swarp[3];
-    uint32_t la = (uint32_t)__cvta_generic_to_shared(&s_parts[c]), ra;
+    uint32_t la = (uint32_t)__cvta_generic_to_shared(&s_parts[c]), lb = (uint32_t)__cvta_generic_to_shared(&xbar), ra, rb;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"((uint32_t)tid));
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(mine) : "memory");
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"((uint32_t)tid));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(mine)), "r"(rb) : "memory");
   }
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  {
+    const uint32_t ba = (uint32_t)__cvta_generic_to_shared(&xbar);
+    uint32_t done, spins = 0;
+    long long t0 = 0;
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(ba) : "memory");
+      if (!done && (++spins & 0x3FFu) == 0) {          // bounded: a protocol bug must trap, not hang the GPU
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000ll) { printf("rmsnorm_partials: exchange barrier timed out (block %d,%d)\n", blockIdx.x, blockIdx.y); __trap(); }
+      }
+    } while (!done);
+  }
   const float tot = ((s_parts[0] + s_parts[1]) + s_parts[2]) + s_parts[3];             // rank order: the same total in all four CTAs
   const float rs = 1.0f / sqrtf(tot / (float)H + eps);       // torch.rsqrt(variance + eps), fp32
 #pragma unroll
