@@ -120,14 +120,6 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
 // memory in rank order.  Same rounding points as rd_rmsnorm; only the fp32 order of the sum of squares differs.
 constexpr int RNP_CL = 4, RNP_THREADS = 128, RNP_MAXG = 4;
 
-__device__ __forceinline__ float rnp_ld_dsmem(const float* local, uint32_t rank) {
-  uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
-  float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
-  return v;
-}
-
 template <class T>
 __global__ void __launch_bounds__(RNP_THREADS)
 rmsnorm_partials_kernel(const float* __restrict__ part, int splits, int64_t slab_stride, T* __restrict__ x, const T* __restrict__ w,
